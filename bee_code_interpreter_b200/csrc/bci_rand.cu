@@ -1,0 +1,120 @@
+// bci_rand.cu — K8: uniform float64 in [0,1) for the *unseeded* numpy.random.rand of
+// examples/benchmark-numpy.py:20.
+//
+// Generator: Philox4x32-10 (Salmon et al., "Parallel Random Numbers: As Easy as 1,2,3",
+// SC'11; Random123 v1.14) — counter based, so element i needs no state:
+//   counter = (lo32(i/2), hi32(i/2), 0, 0), key = (lo32(seed), hi32(seed));
+//   the 4 output words give elements 2*(i/2) and 2*(i/2)+1 with numpy's own 53-bit
+//   construction  ((a >> 5) * 2^26 + (b >> 6)) / 2^53   (numpy legacy random_double).
+// Same distribution and resolution as numpy's rand, not the MT19937 stream (SURVEY.md
+// hard part 5); seeded legacy calls are never routed here.
+//
+// HBM-write-bound: algorithmic bytes = 8*n.  One CTA = one 32 KiB tile, 4 x STG.256
+// per thread; the 10 round keys are warp-uniform so a round is 2 IMAD.WIDE + 2 LOP3.
+#include "bci_common.cuh"
+#include <vector>
+#include <cstring>
+
+namespace bci {
+
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u, kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
+
+struct Philox4 { uint32_t x, y, z, w; };
+
+// The key schedule (k + r*W) is the same for every counter of a request: it is
+// expanded once per thread and kept in registers, leaving 2 IMAD.WIDE + 2 LOP3 per round.
+struct PhiloxKeys { uint32_t a[10], b[10]; };
+
+__device__ __forceinline__ PhiloxKeys philox_keys(uint32_t k0, uint32_t k1) {
+  PhiloxKeys k;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { k.a[r] = k0 + (uint32_t)r * kPhiloxW0; k.b[r] = k1 + (uint32_t)r * kPhiloxW1; }
+  return k;
+}
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  const PhiloxKeys& k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)kPhiloxM0 * c0;
+    const unsigned long long p1 = (unsigned long long)kPhiloxM1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.a[r];
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.b[r];
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
+  return (double)v * 1.1102230246251565e-16;  // 2^-53, exact scaling
+}
+
+constexpr int kRandUnroll = 4;
+constexpr size_t kRandTile = (size_t)kThreads * kRandUnroll * 4;  // doubles
+
+__global__ void __launch_bounds__(kThreads)
+rand_f64_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B) {
+  const unsigned long long tile = blockIdx.x;
+  const int r = find_req(tile_start, B, tile);
+  const Req q = reqs[r];
+  const size_t base = (size_t)(tile - q.tile_start) * kRandTile;
+  const size_t rem = (size_t)q.n - base;
+  double* __restrict__ o = reinterpret_cast<double*>(q.out) + base;
+  const PhiloxKeys keys = philox_keys((uint32_t)((unsigned long long)q.s1.i), (uint32_t)((unsigned long long)q.s1.i >> 32));
+
+  if (rem >= kRandTile && is_aligned32(o)) {
+#pragma unroll
+    for (int u = 0; u < kRandUnroll; ++u) {
+      const size_t e = base + ((size_t)u * kThreads + threadIdx.x) * 4;  // first element (multiple of 4)
+      const unsigned long long p = e >> 1;
+      const Philox4 a = philox4x32_10((uint32_t)p, (uint32_t)(p >> 32), 0u, 0u, keys);
+      const Philox4 b = philox4x32_10((uint32_t)(p + 1), (uint32_t)((p + 1) >> 32), 0u, 0u, keys);
+      VecOf<double> v;
+      v.v[0] = u53(a.x, a.y);
+      v.v[1] = u53(a.z, a.w);
+      v.v[2] = u53(b.x, b.y);
+      v.v[3] = u53(b.z, b.w);
+      stg256(o + ((size_t)u * kThreads + threadIdx.x) * 4, v.u);
+    }
+  } else {
+    const size_t m = rem < kRandTile ? rem : kRandTile;
+    for (size_t i = threadIdx.x; i < m; i += kThreads) {
+      const size_t e = base + i;
+      const unsigned long long p = e >> 1;
+      const Philox4 a = philox4x32_10((uint32_t)p, (uint32_t)(p >> 32), 0u, 0u, keys);
+      o[i] = (e & 1) ? u53(a.z, a.w) : u53(a.x, a.y);
+    }
+  }
+}
+
+}  // namespace bci
+
+using namespace bci;
+
+extern "C" int bci_rand_f64(int B, void* const* out, const size_t* n, const uint64_t* seed) {
+  BCI_REQUIRE_INIT();
+  if (B <= 0 || !out || !n || !seed) { set_error("bci_rand_f64: bad arguments"); return BCI_ERR_INVALID; }
+  std::vector<Req> reqs((size_t)B);
+  for (int i = 0; i < B; ++i) {
+    Req& q = reqs[i];
+    memset(&q, 0, sizeof q);
+    q.out = out[i];
+    q.n = n[i];
+    q.s1.i = (int64_t)seed[i];
+    if (n[i] && !out[i]) { set_error("bci_rand_f64: NULL buffer in request %d", i); return BCI_ERR_INVALID; }
+  }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  Batch bt;
+  int rc = upload_batch(reqs.data(), B, kRandTile, &bt);
+  if (rc != BCI_OK) return rc;
+  if (bt.total_tiles == 0) return BCI_OK;
+  if (bt.total_tiles > 0x7fffffffull) { set_error("bci_rand_f64: batch too large for one launch"); return BCI_ERR_INVALID; }
+  rand_f64_kernel<<<(unsigned)bt.total_tiles, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B);
+  BCI_CHECK_LAUNCH();
+  return BCI_OK;
+}

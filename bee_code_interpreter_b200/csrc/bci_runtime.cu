@@ -1,0 +1,373 @@
+// bci_runtime.cu — process-wide device context of libbci.so: one process = one GPU.
+// Takes over what kubernetes_code_executor.py:151-264 (warm pod queue) provides in
+// the reference: a ready execution context that requests are dispatched into.
+#include "bci_common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace bci {
+
+static thread_local std::string g_err;
+
+Ctx& ctx() {
+  static Ctx c;
+  return c;
+}
+
+void set_error(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+  cudaGetLastError();  // clear the sticky-less error state
+  return e == cudaErrorMemoryAllocation ? BCI_ERR_OOM : BCI_ERR_CUDA;
+}
+
+static constexpr size_t kStageBytes = 8u << 20;  // descriptor ring
+
+int stage_upload(const void* host, size_t bytes, void** dptr) {
+  Ctx& c = ctx();
+  size_t need = (bytes + 255) & ~size_t(255);
+  if (need > c.stage_bytes) {
+    // oversize descriptor table: grow the ring (rare; B > ~100k)
+    BCI_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.h_stage) cudaFreeHost(c.h_stage);
+    if (c.d_stage) cudaFree(c.d_stage);
+    c.h_stage = nullptr; c.d_stage = nullptr;
+    size_t nb = need * 2;
+    BCI_CUDA(cudaHostAlloc((void**)&c.h_stage, nb, cudaHostAllocDefault));
+    BCI_CUDA(cudaMalloc((void**)&c.d_stage, nb));
+    c.stage_bytes = nb;
+    c.stage_off = 0;
+  }
+  if (c.stage_off + need > c.stage_bytes) {
+    // wrap: every earlier copy out of the pinned mirror must have executed
+    BCI_CUDA(cudaStreamSynchronize(c.stream));
+    c.stage_off = 0;
+  }
+  memcpy(c.h_stage + c.stage_off, host, bytes);
+  BCI_CUDA(cudaMemcpyAsync(c.d_stage + c.stage_off, c.h_stage + c.stage_off, bytes,
+                           cudaMemcpyHostToDevice, c.stream));
+  *dptr = c.d_stage + c.stage_off;
+  c.stage_off += need;
+  return BCI_OK;
+}
+
+int scratch_get(size_t bytes, void** dptr) {
+  Ctx& c = ctx();
+  if (bytes > c.scratch_bytes) {
+    BCI_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.scratch) cudaFree(c.scratch);
+    c.scratch = nullptr; c.scratch_bytes = 0;
+    size_t nb = (bytes + (bytes >> 2) + 4095) & ~size_t(4095);
+    BCI_CUDA(cudaMalloc((void**)&c.scratch, nb));
+    c.scratch_bytes = nb;
+  }
+  *dptr = c.scratch;
+  return BCI_OK;
+}
+
+int result_get(size_t bytes, void** hptr, void** dptr) {
+  Ctx& c = ctx();
+  if (bytes > c.result_bytes) {
+    BCI_CUDA(cudaStreamSynchronize(c.stream));
+    if (c.h_result) cudaFreeHost(c.h_result);
+    if (c.d_result) cudaFree(c.d_result);
+    c.h_result = nullptr; c.d_result = nullptr; c.result_bytes = 0;
+    size_t nb = (bytes * 2 + 4095) & ~size_t(4095);
+    BCI_CUDA(cudaHostAlloc((void**)&c.h_result, nb, cudaHostAllocDefault));
+    BCI_CUDA(cudaMalloc((void**)&c.d_result, nb));
+    c.result_bytes = nb;
+  }
+  *hptr = c.h_result;
+  *dptr = c.d_result;
+  return BCI_OK;
+}
+
+int upload_batch(Req* host_reqs, int B, size_t tile_elems, Batch* out) {
+  // one upload: [Req x B][tile_start x (B+1)]
+  size_t req_bytes = sizeof(Req) * (size_t)B;
+  size_t ts_bytes = sizeof(unsigned long long) * (size_t)(B + 1);
+  std::vector<uint8_t> buf(req_bytes + ts_bytes);
+  unsigned long long* ts = reinterpret_cast<unsigned long long*>(buf.data() + req_bytes);
+  unsigned long long t = 0;
+  for (int i = 0; i < B; ++i) {
+    host_reqs[i].tile_start = t;
+    ts[i] = t;
+    t += (host_reqs[i].n + tile_elems - 1) / tile_elems;
+  }
+  ts[B] = t;
+  memcpy(buf.data(), host_reqs, req_bytes);
+  void* d = nullptr;
+  int rc = stage_upload(buf.data(), buf.size(), &d);
+  if (rc != BCI_OK) return rc;
+  out->d_reqs = reinterpret_cast<Req*>(d);
+  out->d_tile_start = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(d) + req_bytes);
+  out->total_tiles = t;
+  return BCI_OK;
+}
+
+}  // namespace bci
+
+using namespace bci;
+
+extern "C" {
+
+int bci_abi_version(void) { return BCI_ABI_VERSION; }
+
+const char* bci_last_error(void) { return g_err.c_str(); }
+
+int bci_device_count(int* count) {
+  if (!count) { set_error("count is NULL"); return BCI_ERR_INVALID; }
+  *count = 0;
+  BCI_CUDA(cudaGetDeviceCount(count));
+  return BCI_OK;
+}
+
+int bci_init(int device) {
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (c.ready) {
+    if (c.device == device) return BCI_OK;
+    set_error("bci_init: already bound to device %d (one process drives one GPU)", c.device);
+    return BCI_ERR_INVALID;
+  }
+  int count = 0;
+  BCI_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) {
+    set_error("bci_init: device %d out of range (%d visible)", device, count);
+    return BCI_ERR_INVALID;
+  }
+  BCI_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BCI_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("bci_init: device %d is sm_%d%d; libbci.so carries sm_100a code only", device,
+              prop.major, prop.minor);
+    return BCI_ERR_UNSUPPORTED;
+  }
+  c.device = device;
+  c.sm_count = prop.multiProcessorCount;
+  BCI_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.own_stream = true;
+  BCI_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
+  uint64_t thresh = UINT64_MAX;  // keep freed blocks: the next wave of requests reuses them
+  BCI_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  BCI_CUDA(cudaEventCreate(&c.ev0));
+  BCI_CUDA(cudaEventCreate(&c.ev1));
+  BCI_CUDA(cudaHostAlloc((void**)&c.h_stage, kStageBytes, cudaHostAllocDefault));
+  BCI_CUDA(cudaMalloc((void**)&c.d_stage, kStageBytes));
+  c.stage_bytes = kStageBytes;
+  c.stage_off = 0;
+  c.launches = 0;
+  c.ready = true;
+  return BCI_OK;
+}
+
+void bci_shutdown(void) {
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (!c.ready) return;
+  cudaStreamSynchronize(c.stream);
+  if (c.h_stage) cudaFreeHost(c.h_stage);
+  if (c.d_stage) cudaFree(c.d_stage);
+  if (c.scratch) cudaFree(c.scratch);
+  if (c.h_result) cudaFreeHost(c.h_result);
+  if (c.d_result) cudaFree(c.d_result);
+  if (c.flush) cudaFree(c.flush);
+  c.h_stage = c.d_stage = c.scratch = c.h_result = c.d_result = c.flush = nullptr;
+  c.stage_bytes = c.scratch_bytes = c.result_bytes = c.flush_bytes = 0;
+  cudaEventDestroy(c.ev0);
+  cudaEventDestroy(c.ev1);
+  if (c.own_stream) cudaStreamDestroy(c.stream);
+  c.stream = nullptr;
+  c.ready = false;
+  c.device = -1;
+}
+
+int bci_device_info(bci_devinfo* info) {
+  BCI_REQUIRE_INIT();
+  if (!info) { set_error("info is NULL"); return BCI_ERR_INVALID; }
+  Ctx& c = ctx();
+  cudaDeviceProp prop;
+  BCI_CUDA(cudaGetDeviceProperties(&prop, c.device));
+  info->device = c.device;
+  info->sm_count = prop.multiProcessorCount;
+  info->cc_major = prop.major;
+  info->cc_minor = prop.minor;
+  info->total_mem = prop.totalGlobalMem;
+  snprintf(info->name, sizeof info->name, "%s", prop.name);
+  return BCI_OK;
+}
+
+int bci_mem_info(size_t* free_bytes, size_t* total_bytes) {
+  BCI_REQUIRE_INIT();
+  size_t f = 0, t = 0;
+  BCI_CUDA(cudaMemGetInfo(&f, &t));
+  // memory parked in the pool is reusable by bci_alloc: count it as free
+  Ctx& c = ctx();
+  uint64_t reserved = 0, used = 0;
+  cudaMemPoolGetAttribute(c.pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+  cudaMemPoolGetAttribute(c.pool, cudaMemPoolAttrUsedMemCurrent, &used);
+  if (free_bytes) *free_bytes = f + (size_t)(reserved - used);
+  if (total_bytes) *total_bytes = t;
+  return BCI_OK;
+}
+
+int bci_alloc(size_t bytes, void** dptr) {
+  BCI_REQUIRE_INIT();
+  if (!dptr) { set_error("dptr is NULL"); return BCI_ERR_INVALID; }
+  *dptr = nullptr;
+  if (bytes == 0) bytes = 256;  // numpy allows empty arrays; keep a unique non-NULL handle
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  cudaError_t e = cudaMallocFromPoolAsync(dptr, bytes, c.pool, c.stream);
+  if (e != cudaSuccess) {
+    *dptr = nullptr;
+    return cuda_fail(e, "cudaMallocFromPoolAsync", __FILE__, __LINE__);
+  }
+  return BCI_OK;
+}
+
+int bci_free(void* dptr) {
+  BCI_REQUIRE_INIT();
+  if (!dptr) return BCI_OK;
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaFreeAsync(dptr, c.stream));
+  return BCI_OK;
+}
+
+int bci_host_alloc(size_t bytes, void** hptr) {
+  BCI_REQUIRE_INIT();
+  if (!hptr) { set_error("hptr is NULL"); return BCI_ERR_INVALID; }
+  BCI_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return BCI_OK;
+}
+
+int bci_host_free(void* hptr) {
+  BCI_REQUIRE_INIT();
+  if (!hptr) return BCI_OK;
+  BCI_CUDA(cudaFreeHost(hptr));
+  return BCI_OK;
+}
+
+int bci_h2d(void* dst_dev, const void* src_host, size_t bytes) {
+  BCI_REQUIRE_INIT();
+  if (bytes == 0) return BCI_OK;
+  if (!dst_dev || !src_host) { set_error("bci_h2d: NULL pointer"); return BCI_ERR_INVALID; }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c.stream));
+  return BCI_OK;
+}
+
+int bci_d2h(void* dst_host, const void* src_dev, size_t bytes) {
+  BCI_REQUIRE_INIT();
+  if (bytes == 0) return BCI_OK;
+  if (!dst_host || !src_dev) { set_error("bci_d2h: NULL pointer"); return BCI_ERR_INVALID; }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+  BCI_CUDA(cudaStreamSynchronize(c.stream));
+  return BCI_OK;
+}
+
+int bci_d2d(void* dst_dev, const void* src_dev, size_t bytes) {
+  BCI_REQUIRE_INIT();
+  if (bytes == 0) return BCI_OK;
+  if (!dst_dev || !src_dev) { set_error("bci_d2d: NULL pointer"); return BCI_ERR_INVALID; }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaMemcpyAsync(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice, c.stream));
+  return BCI_OK;
+}
+
+int bci_memset(void* dst_dev, int byte, size_t bytes) {
+  BCI_REQUIRE_INIT();
+  if (bytes == 0) return BCI_OK;
+  if (!dst_dev) { set_error("bci_memset: NULL pointer"); return BCI_ERR_INVALID; }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaMemsetAsync(dst_dev, byte, bytes, c.stream));
+  return BCI_OK;
+}
+
+int bci_sync(void) {
+  BCI_REQUIRE_INIT();
+  Ctx& c = ctx();
+  BCI_CUDA(cudaStreamSynchronize(c.stream));
+  return BCI_OK;
+}
+
+int bci_timer_begin(void) {
+  BCI_REQUIRE_INIT();
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaEventRecord(c.ev0, c.stream));
+  return BCI_OK;
+}
+
+int bci_timer_end(float* elapsed_ms) {
+  BCI_REQUIRE_INIT();
+  if (!elapsed_ms) { set_error("elapsed_ms is NULL"); return BCI_ERR_INVALID; }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaEventRecord(c.ev1, c.stream));
+  BCI_CUDA(cudaEventSynchronize(c.ev1));
+  BCI_CUDA(cudaEventElapsedTime(elapsed_ms, c.ev0, c.ev1));
+  return BCI_OK;
+}
+
+static cudaEvent_t g_slots[64];
+static bool g_slot_made[64];
+
+int bci_event_record(int slot) {
+  BCI_REQUIRE_INIT();
+  if (slot < 0 || slot >= 64) { set_error("bci_event_record: slot %d out of range", slot); return BCI_ERR_INVALID; }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  if (!g_slot_made[slot]) {
+    BCI_CUDA(cudaEventCreate(&g_slots[slot]));
+    g_slot_made[slot] = true;
+  }
+  BCI_CUDA(cudaEventRecord(g_slots[slot], c.stream));
+  return BCI_OK;
+}
+
+int bci_event_elapsed(int slot_begin, int slot_end, float* elapsed_ms) {
+  BCI_REQUIRE_INIT();
+  if (slot_begin < 0 || slot_begin >= 64 || slot_end < 0 || slot_end >= 64 || !elapsed_ms ||
+      !g_slot_made[slot_begin] || !g_slot_made[slot_end]) {
+    set_error("bci_event_elapsed: bad slots");
+    return BCI_ERR_INVALID;
+  }
+  BCI_CUDA(cudaEventSynchronize(g_slots[slot_end]));
+  BCI_CUDA(cudaEventElapsedTime(elapsed_ms, g_slots[slot_begin], g_slots[slot_end]));
+  return BCI_OK;
+}
+
+uint64_t bci_launch_count(void) { return ctx().launches.load(); }
+
+int bci_flush_l2(void) {
+  BCI_REQUIRE_INIT();
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  const size_t want = 256u << 20;  // 2x the 126 MB L2
+  if (!c.flush) {
+    BCI_CUDA(cudaMalloc((void**)&c.flush, want));
+    c.flush_bytes = want;
+  }
+  BCI_CUDA(cudaMemsetAsync(c.flush, 0x5a, c.flush_bytes, c.stream));
+  return BCI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+"""Batch-first host API over the C ABI (include/bci.h): one call = one launch per op class
+for B independent requests.  Everything here is thin marshalling; the work happens in the
+sm_100a kernels.  No CPU fallback: errors propagate as `BciError`."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BciError, Unsupported  # noqa: F401  (re-exported)
+
+DTYPE_CODE = {
+    np.dtype(np.float32): _lib.F32,
+    np.dtype(np.float64): _lib.F64,
+    np.dtype(np.int32): _lib.I32,
+    np.dtype(np.int64): _lib.I64,
+}
+CODE_DTYPE = {v: k for k, v in DTYPE_CODE.items()}
+
+_initialised_device: int | None = None
+
+
+def dtype_code(dtype) -> int:
+    try:
+        return DTYPE_CODE[np.dtype(dtype)]
+    except KeyError:
+        raise Unsupported(_lib.ERR_UNSUPPORTED, f"dtype {dtype} is not handled on the device") from None
+
+
+def default_device() -> int:
+    for var in ("BCI_DEVICE", "LOCAL_RANK"):
+        v = os.environ.get(var)
+        if v not in (None, ""):
+            return int(v)
+    return 0
+
+
+def init(device: int | None = None) -> int:
+    """Binds this process to one GPU (one process per GPU).  Idempotent."""
+    global _initialised_device
+    lib = _lib.load()
+    dev = default_device() if device is None else int(device)
+    _lib.check(lib.bci_init(dev))
+    _initialised_device = dev
+    return dev
+
+
+def is_initialised() -> bool:
+    return _initialised_device is not None
+
+
+def shutdown() -> None:
+    global _initialised_device
+    _lib.load().bci_shutdown()
+    _initialised_device = None
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _lib.check(_lib.load().bci_device_count(C.byref(n)))
+    return n.value
+
+
+def device_info() -> dict:
+    info = _lib.DevInfo()
+    _lib.check(_lib.load().bci_device_info(C.byref(info)))
+    return {
+        "device": info.device,
+        "sm_count": info.sm_count,
+        "cc": (info.cc_major, info.cc_minor),
+        "total_mem": info.total_mem,
+        "name": info.name.decode(),
+    }
+
+
+def mem_info() -> tuple[int, int]:
+    f, t = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(_lib.load().bci_mem_info(C.byref(f), C.byref(t)))
+    return f.value, t.value
+
+
+def alloc(nbytes: int) -> int:
+    p = C.c_void_p(0)
+    _lib.check(_lib.load().bci_alloc(int(nbytes), C.byref(p)))
+    return int(p.value)
+
+
+def free(ptr: int) -> None:
+    if ptr:
+        _lib.check(_lib.load().bci_free(C.c_void_p(ptr)))
+
+
+def sync() -> None:
+    _lib.check(_lib.load().bci_sync())
+
+
+def flush_l2() -> None:
+    _lib.check(_lib.load().bci_flush_l2())
+
+
+def launch_count() -> int:
+    return int(_lib.load().bci_launch_count())
+
+
+def timer_begin() -> None:
+    _lib.check(_lib.load().bci_timer_begin())
+
+
+def timer_end() -> float:
+    ms = C.c_float(0.0)
+    _lib.check(_lib.load().bci_timer_end(C.byref(ms)))
+    return float(ms.value)
+
+
+def event_record(slot: int) -> None:
+    _lib.check(_lib.load().bci_event_record(int(slot)))
+
+
+def event_elapsed(slot_begin: int, slot_end: int) -> float:
+    ms = C.c_float(0.0)
+    _lib.check(_lib.load().bci_event_elapsed(int(slot_begin), int(slot_end), C.byref(ms)))
+    return float(ms.value)
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy uint8 array (for H2D/D2H staging)."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p(0)
+        _lib.check(_lib.load().bci_host_alloc(int(nbytes), C.byref(p)))
+        self.ptr = int(p.value)
+        self.nbytes = int(nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(1, self.nbytes)).from_address(self.ptr))[: self.nbytes]
+
+    def close(self) -> None:
+        if self.ptr:
+            self.array = None
+            _lib.load().bci_host_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def h2d(dst_ptr: int, src: np.ndarray) -> None:
+    src = np.ascontiguousarray(src)
+    _lib.check(_lib.load().bci_h2d(C.c_void_p(dst_ptr), C.c_void_p(src.ctypes.data), src.nbytes))
+    # pageable sources are staged by the runtime before the call returns; pinned ones must
+    # stay alive until the next sync — callers that pass pinned memory sync themselves.
+
+
+def d2h(dst: np.ndarray, src_ptr: int) -> None:
+    assert dst.flags["C_CONTIGUOUS"]
+    _lib.check(_lib.load().bci_d2h(C.c_void_p(dst.ctypes.data), C.c_void_p(src_ptr), dst.nbytes))
+
+
+def d2d(dst_ptr: int, src_ptr: int, nbytes: int) -> None:
+    _lib.check(_lib.load().bci_d2d(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(nbytes)))
+
+
+def upload(arr: np.ndarray) -> int:
+    """Allocates a device buffer and copies `arr` into it; returns the device pointer."""
+    arr = np.ascontiguousarray(arr)
+    p = alloc(arr.nbytes)
+    if arr.nbytes:
+        h2d(p, arr)
+    return p
+
+
+def download(ptr: int, n: int, dtype) -> np.ndarray:
+    out = np.empty(int(n), dtype=dtype)
+    if out.nbytes:
+        d2h(out, ptr)
+    return out
+
+
+# ---- batched ops ---------------------------------------------------------------------
+def _scalars(values: Sequence | None, code: int, B: int):
+    if values is None:
+        return None
+    arr = (_lib.Scalar * B)()
+    is_float = code in (_lib.F32, _lib.F64)
+    for i, v in enumerate(values):
+        if is_float:
+            arr[i].f = float(v)
+        else:
+            arr[i].i = int(v)
+    return arr
+
+
+def ewise(op: int, dtype, in0: Sequence[int], in1: Sequence[int] | None, scalars: Sequence | None,
+          out: Sequence[int], ns: Sequence[int]) -> None:
+    code = dtype_code(dtype)
+    B = len(in0)
+    _lib.check(_lib.load().bci_ewise(
+        op, code, B, _lib.ptr_array(in0), _lib.ptr_array(in1) if in1 is not None else None,
+        _scalars(scalars, code, B), _lib.ptr_array(out), _lib.size_array(ns)))
+
+
+def _decode_results(raw: np.ndarray, op: int, code: int) -> np.ndarray:
+    if op == _lib.RED_MEAN:
+        res_code = _lib.F32 if code == _lib.F32 else _lib.F64
+    elif op == _lib.RED_SUM:
+        res_code = _lib.I64 if code == _lib.I32 else code
+    else:
+        res_code = code
+    dt = CODE_DTYPE[res_code]
+    if dt.itemsize == 8:
+        return raw.view(dt).copy()
+    return raw.view(np.uint32)[::2].view(dt).copy()
+
+
+def reduce(op: int, dtype, in_ptrs: Sequence[int], ns: Sequence[int], pre: int = _lib.PRE_NONE) -> np.ndarray:
+    code = dtype_code(dtype)
+    B = len(in_ptrs)
+    raw = np.zeros(B, dtype=np.uint64)
+    _lib.check(_lib.load().bci_reduce(op, pre, code, B, _lib.ptr_array(in_ptrs), _lib.size_array(ns),
+                                      C.c_void_p(raw.ctypes.data)))
+    return _decode_results(raw, op, code)
+
+
+def reduce_fused(op: int, ew_op: int, dtype, in0: Sequence[int], in1: Sequence[int] | None,
+                 scalars: Sequence | None, ns: Sequence[int], pre: int = _lib.PRE_NONE,
+                 addends: Sequence | None = None) -> np.ndarray:
+    code = dtype_code(dtype)
+    B = len(in0)
+    raw = np.zeros(B, dtype=np.uint64)
+    _lib.check(_lib.load().bci_reduce_fused(
+        op, pre, ew_op, code, B, _lib.ptr_array(in0), _lib.ptr_array(in1) if in1 is not None else None,
+        _scalars(scalars, code, B), _scalars(addends, code, B), _lib.size_array(ns),
+        C.c_void_p(raw.ctypes.data)))
+    return _decode_results(raw, op, code)
+
+
+def argext(op: int, dtype, in_ptrs: Sequence[int], ns: Sequence[int]) -> np.ndarray:
+    code = dtype_code(dtype)
+    B = len(in_ptrs)
+    out = np.zeros(B, dtype=np.int64)
+    _lib.check(_lib.load().bci_argext(op, code, B, _lib.ptr_array(in_ptrs), _lib.size_array(ns),
+                                      out.ctypes.data_as(C.POINTER(C.c_int64))))
+    return out
+
+
+def cumsum_out_dtype(dtype) -> np.dtype:
+    dtype = np.dtype(dtype)
+    return np.dtype(np.int64) if dtype == np.int32 else dtype
+
+
+def cumsum(dtype, in_ptrs: Sequence[int], out_ptrs: Sequence[int], ns: Sequence[int]) -> None:
+    code = dtype_code(dtype)
+    _lib.check(_lib.load().bci_cumsum(code, len(in_ptrs), _lib.ptr_array(in_ptrs), _lib.ptr_array(out_ptrs),
+                                      _lib.size_array(ns)))
+
+
+def sort(dtype, in_ptrs: Sequence[int], out_ptrs: Sequence[int], ns: Sequence[int]) -> None:
+    code = dtype_code(dtype)
+    _lib.check(_lib.load().bci_sort(code, len(in_ptrs), _lib.ptr_array(in_ptrs), _lib.ptr_array(out_ptrs),
+                                    _lib.size_array(ns)))
+
+
+def argsort(dtype, in_ptrs: Sequence[int], out_idx_ptrs: Sequence[int], ns: Sequence[int]) -> None:
+    code = dtype_code(dtype)
+    _lib.check(_lib.load().bci_argsort(code, len(in_ptrs), _lib.ptr_array(in_ptrs),
+                                       _lib.ptr_array(out_idx_ptrs), _lib.size_array(ns)))
+
+
+def rand_f64(out_ptrs: Sequence[int], ns: Sequence[int], seeds: Iterable[int]) -> None:
+    seeds = [int(s) & 0xFFFFFFFFFFFFFFFF for s in seeds]
+    arr = (C.c_uint64 * len(seeds))(*seeds)
+    _lib.check(_lib.load().bci_rand_f64(len(out_ptrs), _lib.ptr_array(out_ptrs), _lib.size_array(ns), arr))
+
+
+def matmul_f32(a_ptrs: Sequence[int], b_ptrs: Sequence[int], c_ptrs: Sequence[int], M: int, N: int, K: int) -> None:
+    _lib.check(_lib.load().bci_matmul_f32(len(a_ptrs), _lib.ptr_array(a_ptrs), _lib.ptr_array(b_ptrs),
+                                          _lib.ptr_array(c_ptrs), int(M), int(N), int(K)))
+
+
+def sha256_device(ptrs: Sequence[int], lens: Sequence[int]) -> list[bytes]:
+    """SHA-256 of B device-resident messages, one launch."""
+    B = len(ptrs)
+    out = np.zeros(B * 32, dtype=np.uint8)
+    _lib.check(_lib.load().bci_sha256(B, _lib.ptr_array(ptrs), _lib.size_array(lens), 1,
+                                      C.c_void_p(out.ctypes.data)))
+    return [out[32 * i: 32 * i + 32].tobytes() for i in range(B)]
+
+
+def sha256_host(buffers: Sequence[bytes | bytearray | memoryview | np.ndarray]) -> list[bytes]:
+    """SHA-256 of B host buffers: copied to the device and hashed in one launch."""
+    B = len(buffers)
+    arrs = [np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b.view(np.uint8).reshape(-1)
+            for b in buffers]
+    ptrs = [a.ctypes.data if a.size else 0 for a in arrs]
+    out = np.zeros(B * 32, dtype=np.uint8)
+    _lib.check(_lib.load().bci_sha256(B, _lib.ptr_array(ptrs), _lib.size_array([a.size for a in arrs]), 0,
+                                      C.c_void_p(out.ctypes.data)))
+    return [out[32 * i: 32 * i + 32].tobytes() for i in range(B)]
+
+
+class Sha256Stream:
+    """Incremental hasher state for one ObjectWriter; chunks from many writers are
+    absorbed together with `sha256_update_many` (one launch per round of chunks)."""
+
+    def __init__(self):
+        self.state = _lib.Sha256State()
+        _lib.check(_lib.load().bci_sha256_init(C.byref(self.state)))
+
+
+def sha256_update_many(streams: Sequence[Sha256Stream], chunks: Sequence[bytes]) -> None:
+    B = len(streams)
+    st = (C.POINTER(_lib.Sha256State) * B)(*[C.pointer(s.state) for s in streams])
+    arrs = [np.frombuffer(c, dtype=np.uint8) for c in chunks]
+    ptrs = [a.ctypes.data if a.size else 0 for a in arrs]
+    _lib.check(_lib.load().bci_sha256_update_batch(B, st, _lib.ptr_array(ptrs),
+                                                   _lib.size_array([a.size for a in arrs])))
+
+
+def sha256_final_many(streams: Sequence[Sha256Stream]) -> list[bytes]:
+    B = len(streams)
+    st = (C.POINTER(_lib.Sha256State) * B)(*[C.pointer(s.state) for s in streams])
+    out = np.zeros(B * 32, dtype=np.uint8)
+    _lib.check(_lib.load().bci_sha256_final_batch(B, st, C.c_void_p(out.ctypes.data)))
+    return [out[32 * i: 32 * i + 32].tobytes() for i in range(B)]

@@ -1,0 +1,373 @@
+"""Parity of every CUDA kernel (through the C ABI) against the oracle on seeded inputs.
+Bars: bit-exact for integer/index/byte work and for correctly rounded float
+ufuncs; <= 1e-5 relative for float32 reductions, <= 1e-12 for float64."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from bee_code_interpreter_b200 import _lib as L
+from oracle import numpy_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.float64, np.int32, np.int64]
+SIZES = [1, 7, 255, 4096, 8193, 65536 + 3, 1_000_003]
+
+
+def gen(rng, n, dtype, lo=-100, hi=100):
+    if np.issubdtype(dtype, np.floating):
+        return ((rng.random(n) - 0.5) * 200).astype(dtype)
+    return rng.integers(lo, hi, n, dtype=dtype)
+
+
+class Bufs:
+    """Tracks device allocations of one test and frees them."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.ptrs = []
+
+    def up(self, arr, misalign=0):
+        arr = np.ascontiguousarray(arr)
+        p = self.dev.alloc(arr.nbytes + 64)
+        self.ptrs.append(p)
+        q = p + misalign * arr.itemsize
+        if arr.nbytes:
+            self.dev.h2d(q, arr)
+        return q
+
+    def new(self, nbytes):
+        p = self.dev.alloc(nbytes + 64)
+        self.ptrs.append(p)
+        return p
+
+    def close(self):
+        for p in self.ptrs:
+            self.dev.free(p)
+        self.dev.sync()
+
+
+@pytest.fixture
+def bufs(dev):
+    b = Bufs(dev)
+    yield b
+    b.close()
+
+
+BINARY = [(L.EW_ADD, "add"), (L.EW_SUB, "subtract"), (L.EW_MUL, "multiply"), (L.EW_MAXIMUM, "maximum"),
+          (L.EW_MINIMUM, "minimum")]
+UNARY = [(L.EW_SQUARE, "square"), (L.EW_ABS, "absolute"), (L.EW_NEG, "negative")]
+FLOAT_BINARY = [(L.EW_DIV, "divide")]
+FLOAT_UNARY_EXACT = [(L.EW_SQRT, "sqrt")]
+FLOAT_UNARY_ULP = [(L.EW_EXP, "exp"), (L.EW_LOG, "log")]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ewise_batched_ragged_bit_exact(dev, bufs, dtype):
+    rng = np.random.default_rng(11)
+    xs = [gen(rng, n, dtype) for n in SIZES]
+    ys = [gen(rng, n, dtype) for n in SIZES]
+    if np.issubdtype(dtype, np.floating):
+        xs[2][:5] = [np.nan, np.inf, -np.inf, 0.0, -0.0]
+        ys[2][:5] = [1.0, np.nan, np.inf, -0.0, 0.0]
+    ns = [x.size for x in xs]
+    px = [bufs.up(x) for x in xs]
+    py = [bufs.up(y) for y in ys]
+    po = [bufs.new(x.nbytes) for x in xs]
+    ops = BINARY + (FLOAT_BINARY if np.issubdtype(dtype, np.floating) else [])
+    for code, name in ops:
+        dev.ewise(code, dtype, px, py, None, po, ns)
+        for x, y, p in zip(xs, ys, po):
+            got = dev.download(p, x.size, dtype)
+            want = O.ewise(name, x, y)
+            assert got.tobytes() == want.tobytes() or np.array_equal(got, want, equal_nan=True), name
+    uops = UNARY + (FLOAT_UNARY_EXACT if np.issubdtype(dtype, np.floating) else [])
+    for code, name in uops:
+        dev.ewise(code, dtype, px, None, None, po, ns)
+        for x, p in zip(xs, po):
+            got = dev.download(p, x.size, dtype)
+            want = O.ewise(name, x)
+            assert np.array_equal(got, want, equal_nan=True), name
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ewise_scalar_and_misaligned(dev, bufs, dtype):
+    rng = np.random.default_rng(12)
+    x = gen(rng, 50_001, dtype)
+    p = bufs.up(x, misalign=1)  # not 32-byte aligned: scalar path
+    o = bufs.new(x.nbytes)
+    s = 3 if np.issubdtype(dtype, np.integer) else 1.5
+    for code, fn in [(L.EW_ADD, lambda a: a + dtype(s)), (L.EW_MUL, lambda a: a * dtype(s)),
+                     (L.EW_SUB, lambda a: a - dtype(s)), (L.EW_RSUB, lambda a: dtype(s) - a)]:
+        dev.ewise(code, dtype, [p], None, [s], [o], [x.size])
+        assert np.array_equal(dev.download(o, x.size, dtype), fn(x))
+    if np.issubdtype(dtype, np.floating):
+        dev.ewise(L.EW_RDIV, dtype, [p], None, [s], [o], [x.size])
+        assert np.array_equal(dev.download(o, x.size, dtype), dtype(s) / x)
+        dev.ewise(L.EW_DIV, dtype, [p], None, [s], [o], [x.size])
+        assert np.array_equal(dev.download(o, x.size, dtype), x / dtype(s))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_ewise_exp_log_within_2ulp(dev, bufs, dtype):
+    rng = np.random.default_rng(13)
+    x = (rng.random(100_000) * 20 + 1e-3).astype(dtype)
+    p = bufs.up(x)
+    o = bufs.new(x.nbytes)
+    for code, name in FLOAT_UNARY_ULP:
+        dev.ewise(code, dtype, [p], None, None, [o], [x.size])
+        got = dev.download(o, x.size, dtype)
+        want = O.ewise(name, x)
+        ulp = np.abs(got.astype(np.float64) - want.astype(np.float64)) / np.spacing(np.abs(want)).astype(np.float64)
+        assert ulp.max() <= 2.0, (name, ulp.max())
+
+
+def test_int_wraparound_matches_numpy(dev, bufs):
+    x = np.array([2**31 - 1, -2**31, 46341, -46341, 7], dtype=np.int32)
+    p = bufs.up(x)
+    o = bufs.new(x.nbytes)
+    with np.errstate(all="ignore"):
+        for code, want in [(L.EW_SQUARE, np.square(x)), (L.EW_ABS, np.abs(x)), (L.EW_NEG, np.negative(x))]:
+            dev.ewise(code, np.int32, [p], None, None, [o], [x.size])
+            assert np.array_equal(dev.download(o, x.size, np.int32), want)
+
+
+REL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_reduce_batched(dev, bufs, dtype):
+    rng = np.random.default_rng(21)
+    xs = [gen(rng, n, dtype) for n in SIZES + [3_000_001]]
+    ns = [x.size for x in xs]
+    px = [bufs.up(x) for x in xs]
+    for code, name in [(L.RED_SUM, "sum"), (L.RED_MEAN, "mean"), (L.RED_MAX, "max"), (L.RED_MIN, "min")]:
+        got = dev.reduce(code, dtype, px, ns)
+        for g, x in zip(got, xs):
+            want = O.reduce(name, x)
+            assert g.dtype == np.asarray(want).dtype, (name, g.dtype, np.asarray(want).dtype)
+            if name in ("max", "min") or (np.issubdtype(dtype, np.integer) and name == "sum"):
+                assert g == want, name
+            else:
+                # conditioning-aware bar: error relative to sum(|x|) (mixed-sign data)
+                tol = REL.get(np.dtype(dtype), 1e-12)
+                mag = np.abs(x.astype(np.float64)).sum() / (x.size if name == "mean" else 1)
+                assert abs(float(g) - float(want)) <= tol * mag, (name, g, want)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_reduce_nan_propagation_and_misaligned(dev, bufs, dtype):
+    x = np.arange(100_000, dtype=dtype)
+    x[77_777] = np.nan
+    p = bufs.up(x, misalign=3)
+    for code in (L.RED_MAX, L.RED_MIN, L.RED_SUM):
+        assert np.isnan(dev.reduce(code, dtype, [p], [x.size])[0])
+    y = np.arange(100_000, dtype=dtype)
+    q = bufs.up(y, misalign=3)
+    assert dev.reduce(L.RED_MAX, dtype, [q], [y.size])[0] == 99_999
+    assert dev.reduce(L.RED_MIN, dtype, [q], [y.size])[0] == 0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_sum_of_squares_fused(dev, bufs, dtype):
+    """numpy.sum(numpy.square(x)) — examples/benchmark-numpy.py:21 — as one kernel."""
+    rng = np.random.default_rng(22)
+    xs = [gen(rng, n, dtype, -30000, 30000) for n in SIZES]
+    px = [bufs.up(x) for x in xs]
+    got = dev.reduce(L.RED_SUM, dtype, px, [x.size for x in xs], pre=L.PRE_SQUARE)
+    for g, x in zip(got, xs):
+        with np.errstate(all="ignore"):
+            want = O.benchmark_numpy_body(x)
+        if np.issubdtype(dtype, np.integer):
+            assert g == want
+        else:
+            assert abs(float(g) - float(want)) <= REL[np.dtype(dtype)] * abs(float(want))
+
+
+def test_fused_c3_program(dev, bufs):
+    """C3 request mix: r1=sum(square(x)), r2=mean(x*y+1.0), r3=max(abs(x-y)) on float32."""
+    B, n = 5, 2**20
+    xs = [np.random.default_rng(2000 + i).random(n, dtype=np.float32) for i in range(B)]
+    ys = [np.random.default_rng(7000 + i).random(n, dtype=np.float32) for i in range(B)]
+    px = [bufs.up(x) for x in xs]
+    py = [bufs.up(y) for y in ys]
+    ns = [n] * B
+    r1 = dev.reduce(L.RED_SUM, np.float32, px, ns, pre=L.PRE_SQUARE)
+    r2 = dev.reduce_fused(L.RED_MEAN, L.EW_MUL, np.float32, px, py, None, ns, addends=[1.0] * B)
+    r3 = dev.reduce_fused(L.RED_MAX, L.EW_SUB, np.float32, px, py, None, ns, pre=L.PRE_ABS)
+    for i in range(B):
+        w1 = np.sum(np.square(xs[i]))
+        w2 = np.mean(xs[i] * ys[i] + 1.0)
+        w3 = np.max(np.abs(xs[i] - ys[i]))
+        assert abs(r1[i] - w1) <= 1e-5 * abs(w1)
+        assert abs(r2[i] - w2) <= 1e-5 * abs(w2)
+        assert r3[i] == w3  # max of bit-exact elements is exact
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_argext(dev, bufs, dtype):
+    rng = np.random.default_rng(31)
+    xs = [gen(rng, n, dtype, -5, 5) for n in SIZES + [2_500_000]]  # many ties
+    px = [bufs.up(x) for x in xs]
+    ns = [x.size for x in xs]
+    for code, name in [(L.ARGMAX, "argmax"), (L.ARGMIN, "argmin")]:
+        got = dev.argext(code, dtype, px, ns)
+        for g, x in zip(got, xs):
+            assert int(g) == O.argext(name, x), name
+    if np.issubdtype(dtype, np.floating):
+        x = gen(rng, 300_000, dtype)
+        x[[250_000, 123_456]] = np.nan
+        p = bufs.up(x)
+        assert dev.argext(L.ARGMAX, dtype, [p], [x.size])[0] == 123_456
+        assert dev.argext(L.ARGMIN, dtype, [p], [x.size])[0] == 123_456
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_cumsum(dev, bufs, dtype):
+    rng = np.random.default_rng(41)
+    xs = [gen(rng, n, dtype) for n in SIZES + [2_000_003]]
+    ns = [x.size for x in xs]
+    px = [bufs.up(x) for x in xs]
+    odt = dev.cumsum_out_dtype(dtype)
+    po = [bufs.new(x.size * odt.itemsize) for x in xs]
+    dev.cumsum(dtype, px, po, ns)
+    for x, p in zip(xs, po):
+        got = dev.download(p, x.size, odt)
+        want = O.cumsum(x)
+        assert got.dtype == want.dtype
+        if np.issubdtype(dtype, np.integer):
+            assert np.array_equal(got, want)
+        elif dtype == np.float64:
+            scale = np.maximum.accumulate(np.abs(want)) + np.cumsum(np.abs(x)) * 1e-3
+            assert np.all(np.abs(got - want) <= 1e-12 * scale)
+        else:
+            # float32: device = float64 prefix sums rounded once (oracle states the same)
+            assert np.all(np.abs(got.astype(np.float64) - want.astype(np.float64))
+                          <= 2 * np.spacing(np.abs(want)).astype(np.float64) + 1e-30)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_sort_and_argsort(dev, bufs, dtype):
+    rng = np.random.default_rng(51)
+    xs = [gen(rng, n, dtype, -1000, 1000) for n in SIZES + [1_500_001]]
+    if np.issubdtype(dtype, np.floating):
+        xs[3][:6] = [np.nan, -np.nan, np.inf, -np.inf, 0.0, -0.0]
+        xs[5][100:110] = np.nan
+    else:
+        info = np.iinfo(dtype)
+        xs[3][:4] = [info.min, info.max, 0, -1]
+    ns = [x.size for x in xs]
+    px = [bufs.up(x) for x in xs]
+    po = [bufs.new(x.nbytes) for x in xs]
+    dev.sort(dtype, px, po, ns)
+    for x, p in zip(xs, po):
+        got = dev.download(p, x.size, dtype)
+        assert np.array_equal(got, O.sort(x), equal_nan=True)
+    pi = [bufs.new(x.size * 8) for x in xs]
+    dev.argsort(dtype, px, pi, ns)
+    for x, p in zip(xs, pi):
+        got = dev.download(p, x.size, np.int64)
+        want = O.argsort_stable(x)
+        if np.issubdtype(dtype, np.floating) and (np.isnan(x).any() or (x == 0).any()):
+            # -0.0/+0.0 and NaN sign order are value-equal: compare through the values
+            assert np.array_equal(x[got], x[want], equal_nan=True)
+            assert np.array_equal(np.sort(got), np.arange(x.size))
+        else:
+            assert np.array_equal(got, want)
+
+
+def test_rand_matches_oracle_stream_and_distribution(dev, bufs):
+    ns = [1, 2, 3, 4097, 1_000_001]
+    seeds = [0, 1, 2**63 + 12345, 42, 0xDEADBEEFCAFEF00D]
+    po = [bufs.new(n * 8) for n in ns]
+    dev.rand_f64(po, ns, seeds)
+    for n, s, p in zip(ns, seeds, po):
+        got = dev.download(p, n, np.float64)
+        assert np.array_equal(got, O.rand_f64(n, s))
+    big = dev.download(po[-1], ns[-1], np.float64)
+    assert big.min() >= 0.0 and big.max() < 1.0
+    n = big.size
+    assert abs(big.mean() - 0.5) < 5 * np.sqrt(1 / 12 / n)
+    assert abs(np.sum(np.square(big)) / n - 1 / 3) < 5 * np.sqrt(4 / 45 / n)
+    # misaligned output takes the scalar path and must give the same stream
+    q = bufs.new(5000 * 8 + 64) + 8
+    dev.rand_f64([q], [5000], [77])
+    assert np.array_equal(dev.download(q, 5000, np.float64), O.rand_f64(5000, 77))
+
+
+KATS = [
+    (b"", "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"),
+    (b"abc", "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"),
+    (b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq",
+     "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1"),
+    (b"abcdefghbcdefghicdefghijdefghijkefghijklfghijklmghijklmnhijklmnoijklmnopjklmnopqklmnopqrlmnopqrsmnopqrstnopqrstu",
+     "cf5b16a778af8380036ce59e7b0492370b249b11e8f07a51afac45037afee9d1"),
+    (b"Hello, World!", "dffd6021bb2bd5b0af676290809ec3a53191dd81c7f70a4b28688a362182986f"),
+    (b"a" * 1_000_000, "cdc76e5c9914fb9281a1c7e284d73e67f1809a48a497200e046d39ccc7112cd0"),
+]
+
+
+def test_sha256_known_answers_and_length_sweep(dev):
+    msgs = [m for m, _ in KATS] + [bytes((i * 7 + j) & 0xFF for j in range(i)) for i in range(0, 260)]
+    msgs += [bytes(range(256)) * k + b"z" * r for k, r in [(1, 55), (1, 56), (2, 63), (2, 64), (4, 119), (4, 120)]]
+    got = dev.sha256_host(msgs)
+    for (m, hexd) in KATS:
+        assert got[msgs.index(m)].hex() == hexd
+    for m, g in zip(msgs, got):
+        assert g == hashlib.sha256(m).digest() == O.sha256_c(m)
+
+
+def test_sha256_many_small_messages_thread_kernel(dev):
+    rng = np.random.default_rng(61)
+    msgs = [rng.bytes(int(rng.integers(0, 700))) for _ in range(3000)]  # > 2*4*SMs -> thread kernel
+    got = dev.sha256_host(msgs)
+    for m, g in zip(msgs, got):
+        assert g == hashlib.sha256(m).digest()
+
+
+def test_sha256_device_resident_large_and_unaligned(dev, bufs):
+    rng = np.random.default_rng(62)
+    lens = [64 * 2**10 * 33 + 1, 3 * 2**20, 2**20 - 1, 5]
+    datas = [np.frombuffer(rng.bytes(n), dtype=np.uint8) for n in lens]
+    ptrs = [bufs.up(d) for d in datas]
+    got = dev.sha256_device(ptrs, lens)
+    for d, g in zip(datas, got):
+        assert g == hashlib.sha256(d.tobytes()).digest()
+    # pointer not 16-byte aligned: byte-wise loads
+    p = bufs.up(datas[0], misalign=3)
+    assert dev.sha256_device([p], [lens[0]])[0] == hashlib.sha256(datas[0].tobytes()).digest()
+
+
+def test_sha256_streaming_writers(dev):
+    rng = np.random.default_rng(63)
+    B = 7
+    payloads = [rng.bytes(int(rng.integers(0, 300_000))) for _ in range(B)]
+    streams = [dev.Sha256Stream() for _ in range(B)]
+    offs = [0] * B
+    while any(o < len(p) for o, p in zip(offs, payloads)):
+        chunks = []
+        for i in range(B):
+            step = int(rng.integers(1, 70_000))
+            chunks.append(payloads[i][offs[i]: offs[i] + step])
+            offs[i] += step
+        dev.sha256_update_many(streams, chunks)
+    got = dev.sha256_final_many(streams)
+    for p, g in zip(payloads, got):
+        assert g == hashlib.sha256(p).digest()
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 7, 3), (128, 128, 128), (130, 257, 65), (256, 512, 384), (1000, 300, 77)])
+def test_matmul_f32_vs_f64(dev, bufs, shape):
+    M, N, K = shape
+    B = 3
+    As = [np.random.default_rng(1000 + i).standard_normal((M, K), dtype=np.float32) for i in range(B)]
+    Bs = [np.random.default_rng(1100 + i).standard_normal((K, N), dtype=np.float32) for i in range(B)]
+    pa = [bufs.up(a) for a in As]
+    pb = [bufs.up(b) for b in Bs]
+    pc = [bufs.new(M * N * 4) for _ in range(B)]
+    dev.matmul_f32(pa, pb, pc, M, N, K)
+    for a, b, p in zip(As, Bs, pc):
+        got = dev.download(p, M * N, np.float32).reshape(M, N)
+        want = O.matmul_f64(a, b)
+        assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
