@@ -1,0 +1,70 @@
+"""In-process backend for numpy_proxy: the same "new buffer out" call surface as
+broker_client.RemoteBackend, implemented directly on the C-ABI binding (device.py).
+Used by the service process itself, the smoke test and the GPU parity tests."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib as L
+
+
+class LocalBackend:
+    def __init__(self, device_module=None):
+        if device_module is None:
+            from . import device as device_module
+            if not device_module.is_initialised():
+                device_module.init()
+        self.dev = device_module
+
+    def alloc(self, nbytes): return self.dev.alloc(nbytes)
+    def free(self, ptr): self.dev.free(ptr)
+    def upload(self, arr): return self.dev.upload(arr)
+    def download(self, ptr, n, dtype): return self.dev.download(ptr, n, dtype)
+
+    def _new(self, nbytes, fill):
+        out = self.dev.alloc(nbytes)
+        try:
+            fill(out)
+        except Exception:
+            self.dev.free(out)
+            raise
+        return out
+
+    def copy_buffer(self, src, nbytes):
+        return self._new(nbytes, lambda out: self.dev.d2d(out, src, nbytes))
+
+    def rand(self, n, seed):
+        return self._new(n * 8, lambda out: self.dev.rand_f64([out], [n], [seed]))
+
+    def ewise_new(self, op, dtype, in0, in1, scalar, n):
+        dtype = np.dtype(dtype)
+        return self._new(n * dtype.itemsize, lambda out: self.dev.ewise(
+            op, dtype, [in0], [in1] if in1 is not None else None, [scalar] if in1 is None else None, [out], [n]))
+
+    def reduce(self, op, dtype, in_ptrs, ns, pre=L.PRE_NONE):
+        return self.dev.reduce(op, dtype, in_ptrs, ns, pre=pre)
+
+    def reduce_fused(self, op, ew_op, dtype, in0, in1, scalars, ns, pre=L.PRE_NONE, addends=None):
+        return self.dev.reduce_fused(op, ew_op, dtype, in0, in1, scalars, ns, pre=pre, addends=addends)
+
+    def argext(self, op, dtype, in_ptrs, ns):
+        return self.dev.argext(op, dtype, in_ptrs, ns)
+
+    def cumsum_new(self, dtype, ptr, n):
+        odt = self.dev.cumsum_out_dtype(dtype)
+        return self._new(n * odt.itemsize, lambda out: self.dev.cumsum(dtype, [ptr], [out], [n]))
+
+    def sort_new(self, dtype, ptr, n, inplace=False):
+        if inplace:
+            self.dev.sort(dtype, [ptr], [ptr], [n])
+            return ptr
+        return self._new(n * np.dtype(dtype).itemsize, lambda out: self.dev.sort(dtype, [ptr], [out], [n]))
+
+    def argsort_new(self, dtype, ptr, n):
+        return self._new(n * 8, lambda out: self.dev.argsort(dtype, [ptr], [out], [n]))
+
+    def matmul_new(self, a, b, M, N, K):
+        return self._new(M * N * 4, lambda out: self.dev.matmul_f32([a], [b], [out], M, N, K))
+
+    def sha256(self, ptr, nbytes):
+        return self.dev.sha256_device([ptr], [nbytes])[0]

@@ -72,7 +72,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, sources))
     tmp = LIB_PATH.with_suffix(".so.tmp")
-    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static", "-Xlinker", "--no-undefined", "-ldl", "-lpthread", "-lrt"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static", "-Xlinker", "--no-undefined", "-ldl", "-lpthread", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link of libbci.so failed:\n{r.stdout}\n{r.stderr}")

@@ -1,0 +1,171 @@
+"""LocalGpuExecutor — drop-in for the executor-backend duck type (boundary i).
+
+Mirrors `KubernetesCodeExecutor.execute(source_code, files, env) -> Result`
+(services/kubernetes_code_executor.py:47-52,75-149), the object `create_http_server`
+(services/http_server.py:77-106) and `CustomToolExecutor` (custom_tool_executor.py:45-46)
+consume, injected at `ApplicationContext.code_executor` (application_context.py:72-84).
+
+Per request, in the reference's order (kubernetes_code_executor.py:95-149):
+  1. fresh workspace (the "fresh pod"), files of the `files` map restored into it from the
+     object store (upload_file, :100-113; PUT semantics of executor/server.rs:69-88);
+  2. the script runs as its own OS process with stdout/stderr captured, the request env
+     applied, a timeout (executor/server.rs:149-169: timeout -> ("", "Execution timed out",
+     -1), killed by signal -> -1).  The process is a fork of a warm zygote
+     (zygote.py, script_runner.py) whose numpy calls reach the GPU through the broker (broker.py);
+  3. top-level regular files whose ctime is after the request start are the changed files
+     (executor/server.rs:98-118), stored through the object store and returned as
+     {"/workspace/<name>": <object id>} (download_file, :126-142).
+Script failures are results (exit_code != 0 + stderr), not exceptions; backend failures
+raise and become HTTP 500 in the reference's route (http_server.py:102-104).
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import re
+import shutil
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Mapping
+
+WORKSPACE_PREFIX = "/workspace/"
+_ABS_PATH_RE = re.compile(r"^/[^/].*$")            # utils/validation.py:20-22
+_HASH_RE = re.compile(r"^[0-9a-zA-Z_-]{1,255}$")   # utils/validation.py:19
+
+
+@dataclass
+class Result:
+    """kubernetes_code_executor.py:47-52"""
+    stdout: str
+    stderr: str
+    exit_code: int
+    files: Mapping[str, str] = field(default_factory=dict)
+
+
+class LocalGpuExecutor:
+    Result = Result
+
+    def __init__(self, file_storage=None, *, max_inflight: int = 64, timeout: float = 60.0,
+                 broker=None, device_module=None, storage_path: str | None = None,
+                 min_rand_elems: int | None = None, zygotes: int | None = None):
+        self._own_broker = broker is None
+        if broker is None:
+            from .broker import GpuBroker
+            broker = GpuBroker(device_module)
+        self.broker = broker
+        self._tmp_storage = None
+        if file_storage is None:
+            from .storage import ContentAddressedStorage, HashService
+            if storage_path is None:
+                self._tmp_storage = tempfile.mkdtemp(prefix="bci-objects-")
+                storage_path = self._tmp_storage
+            file_storage = ContentAddressedStorage(storage_path, HashService(device_module))
+        self.file_storage = file_storage
+        self.timeout = timeout
+        self.max_inflight = max_inflight
+        self.min_rand_elems = min_rand_elems
+        self._pool = ThreadPoolExecutor(max_workers=max_inflight, thread_name_prefix="bci-exec")
+        self._sem: asyncio.Semaphore | None = None
+        self._sem_loop = None
+        n_zyg = zygotes if zygotes is not None else max(1, min(8, (os.cpu_count() or 2) // 8))
+        from .zygote import ZygoteClient
+        self._zygotes = [ZygoteClient() for _ in range(n_zyg)]
+        self._rr = 0
+
+    # ---- public API ---------------------------------------------------------------------
+    async def execute(self, source_code: str, files: Mapping[str, str] = {}, env: Mapping[str, str] = {}) -> Result:
+        _validate(source_code, files, env)
+        loop = asyncio.get_running_loop()
+        if self._sem is None or self._sem_loop is not loop:
+            self._sem, self._sem_loop = asyncio.Semaphore(self.max_inflight), loop
+        async with self._sem:  # admission: at most `max_inflight` requests resident on the GPU
+            workspace = Path(tempfile.mkdtemp(prefix="bci-ws-"))
+            capture = Path(tempfile.mkdtemp(prefix="bci-io-"))
+            try:
+                for file_path, object_id in files.items():
+                    target = workspace / file_path.removeprefix(WORKSPACE_PREFIX)
+                    target.parent.mkdir(parents=True, exist_ok=True)
+                    target.write_bytes(await self.file_storage.read(object_id))
+                start_ns = time.time_ns()
+                stdout, stderr, exit_code = await loop.run_in_executor(
+                    self._pool, self._run_process, source_code, str(workspace), dict(env), capture)
+                stored = {}
+                names = _changed_files(workspace, start_ns)
+                if names:
+                    ids = await asyncio.gather(*(self._store(workspace / n) for n in names))
+                    stored = {WORKSPACE_PREFIX + n: i for n, i in zip(names, ids)}
+                return Result(stdout=stdout, stderr=stderr, exit_code=exit_code, files=stored)
+            finally:
+                shutil.rmtree(workspace, ignore_errors=True)
+                shutil.rmtree(capture, ignore_errors=True)
+
+    def close(self) -> None:
+        self._pool.shutdown(wait=False, cancel_futures=True)
+        hasher = getattr(self.file_storage, "_hasher", None)
+        if hasher is not None:
+            hasher.close()
+        for z in self._zygotes:
+            z.close()
+        if self._own_broker:
+            self.broker.close()
+        if self._tmp_storage:
+            shutil.rmtree(self._tmp_storage, ignore_errors=True)
+
+    # ---- internals -------------------------------------------------------------------------
+    async def _store(self, path: Path) -> str:
+        async with self.file_storage.writer() as w:
+            with open(path, "rb") as f:
+                while True:
+                    chunk = f.read(1 << 20)
+                    if not chunk:
+                        break
+                    await w.write(chunk)
+        return w.hash
+
+    def _run_process(self, source_code: str, workspace: str, env: dict, capture: Path):
+        out_path, err_path = str(capture / "stdout"), str(capture / "stderr")
+        req = {"source_code": source_code, "workspace": workspace, "env": env, "stdout_path": out_path,
+               "stderr_path": err_path, "broker_socket": self.broker.socket_path,
+               "min_rand_elems": self.min_rand_elems}
+        self._rr = (self._rr + 1) % len(self._zygotes)
+        code = self._zygotes[self._rr].run(req, self.timeout)
+        if code is None:
+            return "", "Execution timed out", -1   # executor/server.rs:169
+        if code < 0:
+            code = -1                               # died on a signal (executor/server.rs:165)
+        return _read_text(out_path), _read_text(err_path), code
+
+
+def _read_text(path: str) -> str:
+    try:
+        with open(path, "rb") as f:
+            return f.read().decode("utf-8", "replace")  # lossy like server.rs:163-164
+    except FileNotFoundError:
+        return ""
+
+
+def _changed_files(workspace: Path, since_ns: int) -> list[str]:
+    out = []
+    for entry in os.scandir(workspace):
+        if entry.is_file() and entry.stat().st_ctime_ns > since_ns:
+            out.append(entry.name)
+    return sorted(out)
+
+
+def _validate(source_code, files, env) -> None:
+    """Same constraints pydantic enforces in the reference (@validate_call,
+    kubernetes_code_executor.py:80; AbsolutePath / Hash, utils/validation.py:19-22)."""
+    if not isinstance(source_code, str):
+        raise ValueError("source_code must be a string")
+    for path, object_id in files.items():
+        if not isinstance(path, str) or not _ABS_PATH_RE.match(path):
+            raise ValueError(f"files key {path!r} is not an absolute path")
+        if not isinstance(object_id, str) or not _HASH_RE.match(object_id):
+            raise ValueError(f"files value {object_id!r} is not a valid object id")
+    for k, v in env.items():
+        if not isinstance(k, str) or not isinstance(v, str):
+            raise ValueError("env must map str to str")

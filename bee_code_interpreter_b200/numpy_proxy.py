@@ -1,0 +1,502 @@
+"""Device-resident stand-ins for numpy arrays inside agent code (boundary ii).
+
+`DeviceArray` is an ndarray duck (`__array__`, `__array_ufunc__`, `__array_function__`,
+operators) whose data lives in HBM.  Calls numpy would run on the CPU — the ufuncs and
+reductions of examples/benchmark-numpy.py:20-21, np.sort/argmax/cumsum/matmul of the other
+BASELINE configs — are forwarded to a *backend* that speaks the batch-first device API
+(`device.py` in-process, or `broker_client.RemoteBackend` from a sandboxed script process).
+Anything the kernels do not take (unsupported dtype/shape/kwarg, or an `Unsupported` from
+the library) is evaluated by numpy itself on a host copy: a script never fails where numpy
+would not.
+
+Single-use temporaries are not materialised: `np.square(x)`, `x*y+1.0`, `np.abs(x-y)` return
+a *deferred* DeviceArray; if the next consumer is a full reduction the whole expression runs
+as one fused kernel (bci_reduce / bci_reduce_fused), otherwise the elementwise kernel runs
+first.  Every intermediate is rounded exactly as numpy's separate ufunc calls round it.
+"""
+from __future__ import annotations
+
+import operator
+import weakref
+
+import numpy as np
+from numpy.lib.mixins import NDArrayOperatorsMixin
+
+from . import _lib as L
+
+SUPPORTED = (np.dtype(np.float32), np.dtype(np.float64), np.dtype(np.int32), np.dtype(np.int64))
+
+BINARY_UFUNCS = {np.add: L.EW_ADD, np.subtract: L.EW_SUB, np.multiply: L.EW_MUL, np.divide: L.EW_DIV,
+                 np.true_divide: L.EW_DIV, np.maximum: L.EW_MAXIMUM, np.minimum: L.EW_MINIMUM}
+REVERSED = {L.EW_SUB: L.EW_RSUB, L.EW_DIV: L.EW_RDIV}  # scalar on the left
+COMMUTATIVE = {L.EW_ADD, L.EW_MUL, L.EW_MAXIMUM, L.EW_MINIMUM}
+UNARY_UFUNCS = {np.square: L.EW_SQUARE, np.absolute: L.EW_ABS, np.fabs: L.EW_ABS, np.negative: L.EW_NEG,
+                np.sqrt: L.EW_SQRT, np.exp: L.EW_EXP, np.log: L.EW_LOG}
+FLOAT_ONLY = {L.EW_DIV, L.EW_RDIV, L.EW_SQRT, L.EW_EXP, L.EW_LOG}
+FUSABLE_PRODUCERS = {L.EW_ADD, L.EW_SUB, L.EW_MUL, L.EW_MAXIMUM, L.EW_MINIMUM, L.EW_RSUB}
+PRE_OF = {L.EW_SQUARE: L.PRE_SQUARE, L.EW_ABS: L.PRE_ABS}
+REDUCE_UFUNCS = {np.add: L.RED_SUM, np.maximum: L.RED_MAX, np.minimum: L.RED_MIN}
+
+
+class _Fallback(Exception):
+    """Raised internally when an operation must be evaluated by numpy on the host."""
+
+
+def _weak_scalar_ok(value, dtype: np.dtype) -> bool:
+    """numpy (NEP 50) keeps the array dtype for python scalars; numpy-typed scalars only
+    when their dtype is the array's own."""
+    if isinstance(value, (bool, np.bool_)):
+        return False
+    if isinstance(value, np.generic):
+        return value.dtype == dtype
+    if isinstance(value, int):
+        if dtype.kind == "f":
+            return True
+        info = np.iinfo(dtype)
+        return info.min <= value <= info.max
+    if isinstance(value, float):
+        return dtype.kind == "f"
+    return False
+
+
+class DeviceArray(NDArrayOperatorsMixin):
+    __array_priority__ = 1000.0
+
+    def __init__(self, backend, ptr, shape, dtype, *, deferred=None):
+        self._backend = backend
+        self._ptr = ptr                      # device pointer/handle, or None while deferred/host-only
+        self._shape = tuple(int(s) for s in shape)
+        self._dtype = np.dtype(dtype)
+        self._host = None                    # cached host copy
+        self._deferred = deferred            # ("unary", op, a) | ("binary", op, a, b_or_None, scalar)
+        self._dependents = {}                # id -> weakref of deferred arrays that read this one
+        if deferred is not None:
+            for src in deferred[2:4]:
+                if isinstance(src, DeviceArray):
+                    src._dependents[id(self)] = weakref.ref(self)
+
+    # ---- construction -------------------------------------------------------------
+    @classmethod
+    def from_host(cls, backend, arr: np.ndarray) -> "DeviceArray":
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype not in SUPPORTED:
+            raise _Fallback(f"dtype {arr.dtype}")
+        ptr = backend.upload(arr)
+        out = cls(backend, ptr, arr.shape, arr.dtype)
+        out._host = arr
+        return out
+
+    # ---- basic ndarray attributes ---------------------------------------------------
+    @property
+    def shape(self): return self._shape
+    @property
+    def dtype(self): return self._dtype
+    @property
+    def ndim(self): return len(self._shape)
+    @property
+    def size(self):
+        n = 1
+        for s in self._shape:
+            n *= s
+        return n
+    @property
+    def nbytes(self): return self.size * self._dtype.itemsize
+    @property
+    def itemsize(self): return self._dtype.itemsize
+    @property
+    def T(self): return self.__array__().T
+
+    def __len__(self):
+        if not self._shape:
+            raise TypeError("len() of unsized object")
+        return self._shape[0]
+
+    # ---- residency --------------------------------------------------------------------
+    def _device_ptr(self):
+        """Device pointer, running the deferred elementwise kernel or the upload if needed."""
+        if self._ptr is None:
+            if self._deferred is not None:
+                self._materialise_deferred()
+            elif self._host is not None:
+                self._ptr = self._backend.upload(np.ascontiguousarray(self._host))
+            else:  # pragma: no cover
+                raise RuntimeError("DeviceArray has neither device nor host data")
+        return self._ptr
+
+    def _materialise_deferred(self):
+        d = self._deferred
+        n = self.size
+        if d[0] == "unary":
+            _, op, a = d
+            out = self._backend.ewise_new(op, self._dtype, a._device_ptr(), None, None, n)
+        else:
+            _, op, a, b, scalar = d
+            out = self._backend.ewise_new(op, self._dtype, a._device_ptr(),
+                                          b._device_ptr() if b is not None else None,
+                                          scalar if b is None else None, n)
+        self._ptr = out
+        self._deferred = None
+
+    def __array__(self, dtype=None, copy=None):
+        if self._host is None:
+            try:
+                ptr = self._device_ptr()
+                self._host = self._backend.download(ptr, self.size, self._dtype).reshape(self._shape)
+            except L.BciError:
+                self._host = self._eval_on_host()
+        arr = self._host
+        if dtype is not None and np.dtype(dtype) != arr.dtype:
+            return arr.astype(dtype)
+        return arr.copy() if copy else arr
+
+    def _eval_on_host(self) -> np.ndarray:
+        """Deferred expression evaluated by numpy (device unavailable for it)."""
+        d = self._deferred
+        if d is None:
+            raise
+        if d[0] == "unary":
+            return _UNARY_NP[d[1]](np.asarray(d[2]))
+        _, op, a, b, scalar = d
+        rhs = np.asarray(b) if b is not None else self._dtype.type(scalar)
+        return _BINARY_NP[op](np.asarray(a), rhs)
+
+    def _before_mutation(self):
+        for ref in list(self._dependents.values()):
+            dep = ref()
+            if dep is not None and dep._deferred is not None:
+                dep._device_ptr()
+        self._dependents = {}
+
+    def __del__(self):
+        try:
+            if self._ptr is not None and self._backend is not None:
+                self._backend.free(self._ptr)
+        except Exception:
+            pass
+
+    # ---- protocols --------------------------------------------------------------------
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        try:
+            if method == "__call__" and not kwargs:
+                if ufunc in UNARY_UFUNCS and len(inputs) == 1:
+                    return _unary(UNARY_UFUNCS[ufunc], inputs[0])
+                if ufunc in BINARY_UFUNCS and len(inputs) == 2:
+                    return _binary(BINARY_UFUNCS[ufunc], inputs[0], inputs[1])
+                if ufunc is np.matmul and len(inputs) == 2:
+                    return matmul(inputs[0], inputs[1])
+            if method == "reduce" and ufunc in REDUCE_UFUNCS and len(inputs) == 1:
+                if _plain_reduce_kwargs(kwargs):
+                    return _reduce(REDUCE_UFUNCS[ufunc], inputs[0])
+        except (_Fallback, L.Unsupported, L.BciError):
+            pass
+        host_inputs = tuple(np.asarray(x) if isinstance(x, DeviceArray) else x for x in inputs)
+        if "out" in kwargs:
+            outs = kwargs["out"]
+            for o in outs if isinstance(outs, tuple) else (outs,):
+                if isinstance(o, DeviceArray):
+                    return NotImplemented
+        return getattr(ufunc, method)(*host_inputs, **kwargs)
+
+    def __array_function__(self, func, types, args, kwargs):
+        handler = _FUNCTIONS.get(func)
+        if handler is not None:
+            try:
+                return handler(*args, **kwargs)
+            except (_Fallback, L.Unsupported, L.BciError, TypeError):
+                pass
+        return func(*_to_host(args), **_to_host(kwargs))
+
+    # ---- methods numpy's own wrappers and agent code call --------------------------------
+    def sum(self, axis=None, dtype=None, out=None, **kw): return _method_reduce(np.sum, L.RED_SUM, self, axis, dtype, out, kw)
+    def mean(self, axis=None, dtype=None, out=None, **kw): return _method_reduce(np.mean, L.RED_MEAN, self, axis, dtype, out, kw)
+    def max(self, axis=None, out=None, **kw): return _method_reduce(np.max, L.RED_MAX, self, axis, None, out, kw)
+    def min(self, axis=None, out=None, **kw): return _method_reduce(np.min, L.RED_MIN, self, axis, None, out, kw)
+    def argmax(self, axis=None, out=None, **kw): return argmax(self, axis=axis, out=out, **kw)
+    def argmin(self, axis=None, out=None, **kw): return argmin(self, axis=axis, out=out, **kw)
+    def cumsum(self, axis=None, dtype=None, out=None): return cumsum(self, axis=axis, dtype=dtype, out=out)
+    def dot(self, other): return matmul(self, other) if self.ndim == 2 else np.dot(np.asarray(self), np.asarray(other))
+
+    def astype(self, dtype, *a, **kw):
+        if np.dtype(dtype) == self._dtype and not a and not kw:
+            return self.copy()
+        return np.asarray(self).astype(dtype, *a, **kw)
+
+    def copy(self, order="C"):
+        out = self._backend.copy_buffer(self._device_ptr(), self.nbytes)
+        return DeviceArray(self._backend, out, self._shape, self._dtype)
+
+    def reshape(self, *shape, **kw):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return np.asarray(self).reshape(*shape, **kw)
+
+    def ravel(self, *a, **kw): return self if self.ndim == 1 and not a and not kw else np.asarray(self).ravel(*a, **kw)
+    def flatten(self, *a, **kw): return np.asarray(self).flatten(*a, **kw)
+    def tolist(self): return np.asarray(self).tolist()
+    def item(self, *a): return np.asarray(self).item(*a)
+
+    def sort(self, axis=-1, kind=None, order=None):
+        """In-place like ndarray.sort."""
+        if order is not None or self.ndim != 1 or axis not in (-1, 0):
+            raise _Fallback("sort kwargs")
+        self._before_mutation()
+        self._backend.sort_new(self._dtype, self._device_ptr(), self.size, inplace=True)
+        self._host = None
+
+    def __getitem__(self, key):
+        return np.asarray(self)[key]
+
+    def __setitem__(self, key, value):
+        self._before_mutation()
+        host = np.asarray(self)
+        if not host.flags.writeable:
+            host = host.copy()
+        host[key] = np.asarray(value) if isinstance(value, DeviceArray) else value
+        self._host = host
+        if self._ptr is not None:  # device copy is stale now
+            self._backend.free(self._ptr)
+            self._ptr = None
+        self._deferred = None
+
+    def __iter__(self): return iter(np.asarray(self))
+    def __repr__(self): return repr(np.asarray(self))
+    def __str__(self): return str(np.asarray(self))
+    def __format__(self, spec): return format(np.asarray(self), spec)
+    def __float__(self): return float(np.asarray(self))
+    def __int__(self): return int(np.asarray(self))
+    def __bool__(self): return bool(np.asarray(self))
+    def __index__(self): return operator.index(np.asarray(self))
+    def __contains__(self, item): return item in np.asarray(self)
+
+    def __getattr__(self, name):
+        # anything else an ndarray has (std, var, round, clip, ...): numpy on the host copy
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(np.asarray(self), name)
+
+
+_UNARY_NP = {L.EW_SQUARE: np.square, L.EW_ABS: np.absolute, L.EW_NEG: np.negative, L.EW_SQRT: np.sqrt,
+             L.EW_EXP: np.exp, L.EW_LOG: np.log}
+_BINARY_NP = {L.EW_ADD: np.add, L.EW_SUB: np.subtract, L.EW_MUL: np.multiply, L.EW_DIV: np.divide,
+              L.EW_MAXIMUM: np.maximum, L.EW_MINIMUM: np.minimum,
+              L.EW_RSUB: lambda a, s: np.subtract(s, a), L.EW_RDIV: lambda a, s: np.divide(s, a)}
+
+
+def _to_host(obj):
+    if isinstance(obj, DeviceArray):
+        return np.asarray(obj)
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_host(o) for o in obj)
+    if isinstance(obj, dict):
+        return {k: _to_host(v) for k, v in obj.items()}
+    return obj
+
+
+def _plain_reduce_kwargs(kwargs) -> bool:
+    """True when a ufunc.reduce / np.sum style call asks for the full reduction only."""
+    for k, v in kwargs.items():
+        if k == "axis":
+            if v is not None and v != 0:
+                return False
+        elif k in ("dtype", "out", "where", "initial"):
+            if v is not None and v is not np._NoValue and v is not True:
+                return False
+        elif k == "keepdims":
+            if v not in (False, np._NoValue):
+                return False
+        else:
+            return False
+    return True
+
+
+# ---- elementwise -----------------------------------------------------------------------------
+def _unary(op, x):
+    if not isinstance(x, DeviceArray):
+        raise _Fallback("operand")
+    if x.dtype not in SUPPORTED or (op in FLOAT_ONLY and x.dtype.kind != "f"):
+        raise _Fallback("dtype")
+    return DeviceArray(x._backend, None, x.shape, x.dtype, deferred=("unary", op, x))
+
+
+def _binary(op, a, b):
+    if isinstance(a, DeviceArray) and isinstance(b, DeviceArray):
+        if a.dtype != b.dtype or a.shape != b.shape or a.dtype not in SUPPORTED or a._backend is not b._backend:
+            raise _Fallback("operands")
+        if op in FLOAT_ONLY and a.dtype.kind != "f":
+            raise _Fallback("dtype")
+        return DeviceArray(a._backend, None, a.shape, a.dtype, deferred=("binary", op, a, b, None))
+    if isinstance(a, DeviceArray):
+        arr, scalar, left = a, b, False
+    elif isinstance(b, DeviceArray):
+        arr, scalar, left = b, a, True
+    else:
+        raise _Fallback("operands")
+    if arr.dtype not in SUPPORTED or not _weak_scalar_ok(scalar, arr.dtype):
+        raise _Fallback("scalar")
+    if left and op not in COMMUTATIVE:
+        op = REVERSED[op]
+    if op in FLOAT_ONLY and arr.dtype.kind != "f":
+        raise _Fallback("dtype")
+    value = float(scalar) if arr.dtype.kind == "f" else int(scalar)
+    return DeviceArray(arr._backend, None, arr.shape, arr.dtype, deferred=("binary", op, arr, None, value))
+
+
+# ---- reductions --------------------------------------------------------------------------------
+def _result_scalar(value):
+    return value.dtype.type(value) if isinstance(value, np.generic) else value
+
+
+def _reduce(red_op, x):
+    if not isinstance(x, DeviceArray) or x.dtype not in SUPPORTED:
+        raise _Fallback("operand")
+    be, n = x._backend, x.size
+    if n == 0:
+        raise _Fallback("empty")
+    d = x._deferred
+    if d is not None:
+        # fold the single-use producer into the reduction's load
+        if d[0] == "unary" and d[1] in PRE_OF:
+            pre, inner = PRE_OF[d[1]], d[2]
+            di = inner._deferred
+            if di is not None and di[0] == "binary" and di[1] in FUSABLE_PRODUCERS and _leaf(di[2]) and _leaf_or_none(di[3]):
+                return be.reduce_fused(red_op, di[1], x.dtype, [di[2]._device_ptr()],
+                                       [di[3]._device_ptr()] if di[3] is not None else None,
+                                       [di[4]] if di[3] is None else None, [n], pre=pre)[0]
+            return be.reduce(red_op, x.dtype, [inner._device_ptr()], [n], pre=pre)[0]
+        if d[0] == "binary" and d[1] in FUSABLE_PRODUCERS:
+            _, op, a, b, scalar = d
+            if _leaf(a) and _leaf_or_none(b):
+                return be.reduce_fused(red_op, op, x.dtype, [a._device_ptr()],
+                                       [b._device_ptr()] if b is not None else None,
+                                       [scalar] if b is None else None, [n])[0]
+            # (u (op) v) + scalar  with an array-array producer underneath: mean(x*y+1.0)
+            da = a._deferred
+            if (op == L.EW_ADD and b is None and da is not None and da[0] == "binary" and da[3] is not None
+                    and da[1] in FUSABLE_PRODUCERS and _leaf(da[2]) and _leaf(da[3])):
+                return be.reduce_fused(red_op, da[1], x.dtype, [da[2]._device_ptr()], [da[3]._device_ptr()],
+                                       None, [n], addends=[scalar])[0]
+    return be.reduce(red_op, x.dtype, [x._device_ptr()], [n])[0]
+
+
+def _leaf(a) -> bool:
+    return isinstance(a, DeviceArray) and a._deferred is None
+
+
+def _leaf_or_none(a) -> bool:
+    return a is None or _leaf(a)
+
+
+def _method_reduce(np_func, red_op, x, axis, dtype, out, kw):
+    plain = (axis is None or (axis in (0, -1) and x.ndim == 1)) and dtype is None and out is None and \
+        all(v in (False, np._NoValue, None, True) and k in ("keepdims", "where", "initial") and
+            not (k == "keepdims" and v is True) and not (k == "initial" and v not in (None, np._NoValue))
+            for k, v in kw.items())
+    if plain:
+        try:
+            return _reduce(red_op, x)
+        except (_Fallback, L.Unsupported, L.BciError):
+            pass
+    kw = {k: v for k, v in kw.items() if v is not np._NoValue}
+    if dtype is not None:
+        kw["dtype"] = dtype
+    return np_func(np.asarray(x), axis=axis, out=out, **kw)
+
+
+def _np_sum(a, axis=None, dtype=None, out=None, **kw): return _method_reduce(np.sum, L.RED_SUM, _need_dev(a), axis, dtype, out, kw)
+def _np_mean(a, axis=None, dtype=None, out=None, **kw): return _method_reduce(np.mean, L.RED_MEAN, _need_dev(a), axis, dtype, out, kw)
+def _np_max(a, axis=None, out=None, **kw): return _method_reduce(np.max, L.RED_MAX, _need_dev(a), axis, None, out, kw)
+def _np_min(a, axis=None, out=None, **kw): return _method_reduce(np.min, L.RED_MIN, _need_dev(a), axis, None, out, kw)
+
+
+def _need_dev(a):
+    if not isinstance(a, DeviceArray):
+        raise _Fallback("operand")
+    return a
+
+
+def _arg(op, a, axis=None, out=None, **kw):
+    a = _need_dev(a)
+    if out is not None or kw.get("keepdims") or not (axis is None or (a.ndim == 1 and axis in (0, -1))):
+        raise _Fallback("kwargs")
+    if a.dtype not in SUPPORTED or a.size == 0:
+        raise _Fallback("dtype")
+    return np.int64(a._backend.argext(op, a.dtype, [a._device_ptr()], [a.size])[0])
+
+
+def argmax(a, axis=None, out=None, **kw): return _arg(L.ARGMAX, a, axis, out, **kw)
+def argmin(a, axis=None, out=None, **kw): return _arg(L.ARGMIN, a, axis, out, **kw)
+
+
+def cumsum(a, axis=None, dtype=None, out=None):
+    a = _need_dev(a)
+    if dtype is not None or out is not None or a.ndim != 1 or axis not in (None, 0, -1) or a.dtype not in SUPPORTED:
+        raise _Fallback("kwargs")
+    be = a._backend
+    odt = np.dtype(np.int64) if a.dtype == np.int32 else a.dtype
+    return DeviceArray(be, be.cumsum_new(a.dtype, a._device_ptr(), a.size), a.shape, odt)
+
+
+def sort(a, axis=-1, kind=None, order=None, **kw):
+    a = _need_dev(a)
+    if order is not None or kw or a.ndim != 1 or axis not in (-1, 0, None) or a.dtype not in SUPPORTED:
+        raise _Fallback("kwargs")
+    be = a._backend
+    return DeviceArray(be, be.sort_new(a.dtype, a._device_ptr(), a.size), a.shape, a.dtype)
+
+
+def argsort(a, axis=-1, kind=None, order=None, **kw):
+    a = _need_dev(a)
+    # the default kind (quicksort) is unstable in numpy: any valid permutation is acceptable,
+    # the device always returns the stable one
+    if order is not None or kw or a.ndim != 1 or axis not in (-1, 0, None) or a.dtype not in SUPPORTED:
+        raise _Fallback("kwargs")
+    be = a._backend
+    return DeviceArray(be, be.argsort_new(a.dtype, a._device_ptr(), a.size), a.shape, np.int64)
+
+
+def matmul(a, b, out=None, **kw):
+    if out is not None or kw:
+        raise _Fallback("kwargs")
+    if not (isinstance(a, DeviceArray) and isinstance(b, DeviceArray)):
+        raise _Fallback("operands")
+    if a.dtype != np.float32 or b.dtype != np.float32 or a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[0]:
+        raise _Fallback("shape")
+    be = a._backend
+    M, K = a.shape
+    N = b.shape[1]
+    return DeviceArray(be, be.matmul_new(a._device_ptr(), b._device_ptr(), M, N, K), (M, N), np.float32)
+
+
+def _dot(a, b, out=None):
+    if isinstance(a, DeviceArray) and isinstance(b, DeviceArray) and a.ndim == 2 and b.ndim == 2:
+        return matmul(a, b, out=out)
+    raise _Fallback("dot")
+
+
+_FUNCTIONS = {
+    np.sum: _np_sum, np.mean: _np_mean, np.max: _np_max, np.min: _np_min, np.amax: _np_max, np.amin: _np_min,
+    np.argmax: argmax, np.argmin: argmin, np.cumsum: cumsum, np.sort: sort, np.argsort: argsort,
+    np.matmul: matmul, np.dot: _dot,
+}
+
+
+# ---- entry points used by the import hook (numpy_hook.py) ---------------------------------------
+OFFLOAD_MIN_ELEMS = 1 << 18   # host arrays smaller than this stay with numpy
+
+
+def device_rand(backend, shape, seed: int) -> DeviceArray:
+    """numpy.random.rand / random_sample for an unseeded legacy generator."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return DeviceArray(backend, backend.rand(n, seed), shape, np.float64)
+
+
+def offload(backend, arr):
+    """Host ndarray -> DeviceArray when it is big enough to pay for the PCIe hop."""
+    if isinstance(arr, DeviceArray):
+        return arr
+    if (isinstance(arr, np.ndarray) and arr.dtype in SUPPORTED and arr.size >= OFFLOAD_MIN_ELEMS
+            and arr.flags["C_CONTIGUOUS"]):
+        return DeviceArray.from_host(backend, arr)
+    raise _Fallback("host array")

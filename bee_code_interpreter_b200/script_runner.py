@@ -1,0 +1,60 @@
+"""Child-process body for one `/v1/execute` request: what `xonsh script.xsh` is in the
+reference (executor/server.rs:149-169), minus the interpreter start-up.
+
+Runs inside a fork of the warm zygote (zygote.py): cwd = request workspace, env = service env
++ request env, fds 1/2 -> capture files, builtins.__import__ = numpy_hook.patched_import
+(boundary ii), then the agent source runs as `__main__`.  The exit status follows CPython's
+own rules for scripts (uncaught exception -> traceback on stderr, status 1; sys.exit(n) -> n).
+"""
+from __future__ import annotations
+
+import builtins
+import os
+import sys
+import traceback
+
+import numpy  # noqa: F401  (preloaded in the zygote: forked children share these pages)
+
+from . import numpy_hook, numpy_proxy  # noqa: F401
+
+
+def run_in_child(req: dict) -> int:
+    os.chdir(req["workspace"])
+    env = req.get("env")
+    if env:
+        os.environ.update(env)
+    if req.get("broker_socket"):
+        os.environ["BCI_BROKER_SOCKET"] = req["broker_socket"]
+    out_fd = os.open(req["stdout_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    err_fd = os.open(req["stderr_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    os.dup2(out_fd, 1)
+    os.dup2(err_fd, 2)
+    os.close(out_fd)
+    os.close(err_fd)
+    sys.stdout = os.fdopen(1, "w", buffering=1, closefd=False)
+    sys.stderr = os.fdopen(2, "w", buffering=1, closefd=False)
+    sys.argv = ["script.py"]
+    numpy_hook.reset_request_state()
+    numpy_hook.install(min_rand_elems=req.get("min_rand_elems"))
+    code = 0
+    try:
+        compiled = compile(req["source_code"], "script.py", "exec")
+        exec(compiled, {"__name__": "__main__", "__builtins__": builtins, "__file__": "script.py"})
+    except SystemExit as e:
+        if e.code is None:
+            code = 0
+        elif isinstance(e.code, int):
+            code = e.code & 0xFF
+        else:
+            print(e.code, file=sys.stderr)
+            code = 1
+    except BaseException:
+        traceback.print_exc()
+        code = 1
+    finally:
+        try:
+            sys.stdout.flush()
+            sys.stderr.flush()
+        except Exception:
+            pass
+    return code

@@ -1,0 +1,200 @@
+"""Content-addressed object store (boundary iii): the reference's `Storage` protocol
+(services/storage.py:24-90) with the property its docstring promises and its code does not
+deliver (storage.py:35-39 vs :52): an object's id IS the SHA-256 of its bytes.
+
+Same surface: `writer()` async context manager yielding an object with `.write(data)` and
+`.hash`; `write(data) -> id`; `reader(id)`; `read(id)`; `exists(id)`; unknown id ->
+FileNotFoundError.  `.hash` is final when the `async with` block exits, which is when the
+reference's only call site reads it (kubernetes_code_executor.py:127-134).
+
+Hashing runs on the GPU: chunks from all concurrent writers are absorbed together, one
+`bci_sha256_update_batch` launch per round (HashService).  There is no CPU hashing path: if
+the device library is unavailable, writing fails loudly.
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import queue
+import re
+import secrets
+import threading
+from contextlib import asynccontextmanager
+from typing import AsyncIterator
+
+from anyio import Path
+
+HASH_RE = re.compile(r"^[0-9a-zA-Z_-]{1,255}$")  # utils/validation.py:19
+
+
+class HashService:
+    """Batches SHA-256 update/final calls from concurrent writers into single launches."""
+
+    def __init__(self, device_module=None, coalesce_us: int = 200):
+        if device_module is None:
+            from . import device as device_module
+            if not device_module.is_initialised():
+                device_module.init()
+        self.dev = device_module
+        self.coalesce_s = coalesce_us / 1e6
+        self._q: "queue.SimpleQueue" = queue.SimpleQueue()
+        self._thread = threading.Thread(target=self._loop, name="bci-hash", daemon=True)
+        self._running = True
+        self.stats = {"launches": 0, "chunks": 0, "max_batch": 0}
+        self._thread.start()
+
+    def new_stream(self):
+        return self.dev.Sha256Stream()
+
+    def update(self, stream, data: bytes) -> None:
+        self._submit(("update", stream, data))
+
+    def final(self, stream) -> bytes:
+        return self._submit(("final", stream, None))
+
+    def _submit(self, item):
+        done = threading.Event()
+        box: list = [None, None]
+        self._q.put((item, done, box))
+        done.wait()
+        if box[1] is not None:
+            raise box[1]
+        return box[0]
+
+    def close(self):
+        self._running = False
+        self._q.put(None)
+
+    def _loop(self):
+        import time
+
+        while self._running:
+            first = self._q.get()
+            if first is None:
+                break
+            items = [first]
+            if self.coalesce_s:
+                time.sleep(self.coalesce_s)
+            while True:
+                try:
+                    nxt = self._q.get_nowait()
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self._running = False
+                    break
+                items.append(nxt)
+            updates = [it for it in items if it[0][0] == "update"]
+            finals = [it for it in items if it[0][0] == "final"]
+            # a stream appears at most once per round (its writer awaits each call)
+            for group, fn in ((updates, self._do_updates), (finals, self._do_finals)):
+                if not group:
+                    continue
+                try:
+                    fn(group)
+                except Exception as e:
+                    for _, _, box in group:
+                        box[1] = e
+                for _, done, _ in group:
+                    done.set()
+
+    def _do_updates(self, group):
+        self.dev.sha256_update_many([it[0][1] for it in group], [it[0][2] for it in group])
+        self.stats["launches"] += 1
+        self.stats["chunks"] += len(group)
+        self.stats["max_batch"] = max(self.stats["max_batch"], len(group))
+
+    def _do_finals(self, group):
+        digests = self.dev.sha256_final_many([it[0][1] for it in group])
+        self.stats["launches"] += 1
+        for (_, _, box), d in zip(group, digests):
+            box[0] = d
+
+
+class ObjectWriter:
+    """services/storage.py:28-31 — `.hash` + `async write(data)`."""
+
+    FLUSH_BYTES = 4 << 20  # hash in >= 4 MiB slices so one launch carries real work
+
+    def __init__(self, file, hasher: HashService):
+        self._file = file
+        self._hasher = hasher
+        self._stream = hasher.new_stream()
+        self._pending = bytearray()
+        self.hash: str = ""
+
+    async def write(self, data: bytes) -> None:
+        await self._file.write(data)
+        self._pending += data
+        if len(self._pending) >= self.FLUSH_BYTES:
+            await self._flush()
+
+    async def _flush(self):
+        if self._pending:
+            chunk = bytes(self._pending)
+            self._pending.clear()
+            await asyncio.to_thread(self._hasher.update, self._stream, chunk)
+
+    async def _finish(self) -> str:
+        await self._flush()
+        digest = await asyncio.to_thread(self._hasher.final, self._stream)
+        self.hash = digest.hex()
+        return self.hash
+
+
+class ContentAddressedStorage:
+    def __init__(self, storage_path: str, hasher: HashService | None = None):
+        self.storage_path = Path(storage_path)
+        self._hasher = hasher
+
+    @property
+    def hasher(self) -> HashService:
+        if self._hasher is None:
+            self._hasher = HashService()
+        return self._hasher
+
+    @asynccontextmanager
+    async def writer(self) -> AsyncIterator[ObjectWriter]:
+        await self.storage_path.mkdir(parents=True, exist_ok=True)
+        tmp = self.storage_path / (".tmp-" + secrets.token_hex(16))
+        try:
+            async with await tmp.open("wb") as file:
+                w = ObjectWriter(file, self.hasher)
+                yield w
+                await w._finish()
+            target = self.storage_path / w.hash
+            if await target.exists():
+                await tmp.unlink()          # same content already stored: dedupe
+            else:
+                await tmp.rename(target)
+        except BaseException:
+            if await tmp.exists():
+                await tmp.unlink()
+            raise
+
+    async def write(self, data: bytes) -> str:
+        async with self.writer() as f:
+            await f.write(data)
+        return f.hash
+
+    @asynccontextmanager
+    async def reader(self, object_hash: str):
+        _check_hash(object_hash)
+        target = self.storage_path / object_hash
+        if not object_hash or not await target.exists():
+            raise FileNotFoundError(f"File not found: {object_hash}")
+        async with await target.open("rb") as f:
+            yield f
+
+    async def read(self, object_hash: str) -> bytes:
+        async with self.reader(object_hash) as f:
+            return await f.read()
+
+    async def exists(self, object_hash: str) -> bool:
+        _check_hash(object_hash)
+        return await (self.storage_path / object_hash).exists()
+
+
+def _check_hash(object_hash: str) -> None:
+    if not isinstance(object_hash, str) or not HASH_RE.match(object_hash):
+        raise ValueError(f"invalid object id {object_hash!r}")  # pydantic ValidationError is a ValueError too

@@ -231,6 +231,8 @@ def run_ours(args) -> dict | None:
 
 def measure_e2e(args, dev, dist, rank, world, n):
     """The same requests through the public executor API: source text in, stdout out."""
+    if args.e2e_requests <= 0:
+        return {"value": None, "unit": "requests/s", "error": "skipped (--e2e-requests 0)"}
     try:
         from bee_code_interpreter_b200.executor import LocalGpuExecutor
         from bee_code_interpreter_b200 import workloads as W
@@ -240,7 +242,7 @@ def measure_e2e(args, dev, dist, rank, world, n):
 
     requests = args.e2e_requests
     src = W.benchmark_numpy_source(n)
-    execu = LocalGpuExecutor(max_inflight=args.e2e_inflight)
+    execu = LocalGpuExecutor(max_inflight=args.e2e_inflight, timeout=300)
 
     async def batch():
         return await asyncio.gather(*(execu.execute(src) for _ in range(requests)))

@@ -1,0 +1,211 @@
+"""TEST DOUBLE for `bee_code_interpreter_b200.device` — lets the CPU-only suite exercise the
+HOST logic (proxy fusion decisions, broker batching/ownership, executor process model,
+storage protocol) without a GPU.  It lives under tests/ and is never importable from the
+product; "device memory" is a dict of numpy byte buffers and every op is numpy (the oracle).
+It records each batched call so tests can assert how requests were packed."""
+from __future__ import annotations
+
+import hashlib
+import threading
+
+import numpy as np
+
+from bee_code_interpreter_b200 import _lib as L
+from oracle import numpy_oracle as O
+
+_mem: dict[int, np.ndarray] = {}
+_next = [1 << 20]
+_lock = threading.Lock()
+calls: list[tuple] = []           # (name, batch_size, extra)
+_initialised = [False]
+
+BIN = {L.EW_ADD: np.add, L.EW_SUB: np.subtract, L.EW_MUL: np.multiply, L.EW_DIV: np.divide,
+       L.EW_MAXIMUM: np.maximum, L.EW_MINIMUM: np.minimum,
+       L.EW_RSUB: lambda a, s: np.subtract(s, a), L.EW_RDIV: lambda a, s: np.divide(s, a)}
+UN = {L.EW_SQUARE: np.square, L.EW_ABS: np.absolute, L.EW_NEG: np.negative, L.EW_SQRT: np.sqrt,
+      L.EW_EXP: np.exp, L.EW_LOG: np.log}
+RED = {L.RED_SUM: np.sum, L.RED_MEAN: np.mean, L.RED_MAX: np.max, L.RED_MIN: np.min}
+PRE = {L.PRE_NONE: lambda a: a, L.PRE_SQUARE: np.square, L.PRE_ABS: np.absolute}
+
+
+def reset():
+    with _lock:
+        _mem.clear()
+        calls.clear()
+
+
+def live_buffers() -> int:
+    return len(_mem)
+
+
+def init(device=None):
+    _initialised[0] = True
+    return 0
+
+
+def is_initialised():
+    return _initialised[0]
+
+
+def device_info():
+    return {"device": 0, "sm_count": 148, "cc": (10, 0), "total_mem": 1 << 37, "name": "fake"}
+
+
+def mem_info():
+    return 1 << 36, 1 << 37
+
+
+def sync():
+    pass
+
+
+def launch_count():
+    return len(calls)
+
+
+def alloc(nbytes):
+    with _lock:
+        p = _next[0]
+        _next[0] += (int(nbytes) + 4095) // 4096 * 4096 + 4096
+        _mem[p] = np.zeros(max(int(nbytes), 1), dtype=np.uint8)
+        return p
+
+
+def free(ptr):
+    with _lock:
+        if ptr:
+            _mem.pop(ptr)  # KeyError = double free / foreign pointer: a real bug
+
+
+def _view(ptr, n, dtype):
+    dtype = np.dtype(dtype)
+    return _mem[ptr][: int(n) * dtype.itemsize].view(dtype)
+
+
+def h2d(dst, src):
+    src = np.ascontiguousarray(src)
+    _mem[dst][: src.nbytes] = src.view(np.uint8).reshape(-1)
+
+
+def d2h(dst, src):
+    dst.view(np.uint8).reshape(-1)[:] = _mem[src][: dst.nbytes]
+
+
+def d2d(dst, src, nbytes):
+    _mem[dst][:nbytes] = _mem[src][:nbytes]
+
+
+def upload(arr):
+    arr = np.ascontiguousarray(arr)
+    p = alloc(arr.nbytes)
+    if arr.nbytes:
+        h2d(p, arr)
+    return p
+
+
+def download(ptr, n, dtype):
+    return _view(ptr, n, dtype).copy()
+
+
+def ewise(op, dtype, in0, in1, scalars, out, ns):
+    calls.append(("ewise", len(in0), op))
+    dtype = np.dtype(dtype)
+    with np.errstate(all="ignore"):
+        for i in range(len(in0)):
+            a = _view(in0[i], ns[i], dtype)
+            if op in UN:
+                r = UN[op](a)
+            else:
+                b = _view(in1[i], ns[i], dtype) if in1 is not None and in1[i] else dtype.type(scalars[i])
+                r = BIN[op](a, b)
+            _view(out[i], ns[i], dtype)[:] = r.astype(dtype)
+
+
+def reduce(op, dtype, in_ptrs, ns, pre=L.PRE_NONE):
+    calls.append(("reduce", len(in_ptrs), (op, pre)))
+    with np.errstate(all="ignore"):
+        return np.array([RED[op](PRE[pre](_view(p, n, dtype))) for p, n in zip(in_ptrs, ns)])
+
+
+def reduce_fused(op, ew_op, dtype, in0, in1, scalars, ns, pre=L.PRE_NONE, addends=None):
+    calls.append(("reduce_fused", len(in0), (op, ew_op, pre, addends is not None)))
+    dtype = np.dtype(dtype)
+    out = []
+    with np.errstate(all="ignore"):
+        for i in range(len(in0)):
+            a = _view(in0[i], ns[i], dtype)
+            b = _view(in1[i], ns[i], dtype) if in1 is not None else dtype.type(scalars[i])
+            v = BIN[ew_op](a, b)
+            if addends is not None:
+                v = v + dtype.type(addends[i])
+            out.append(RED[op](PRE[pre](v)))
+    return np.array(out)
+
+
+def argext(op, dtype, in_ptrs, ns):
+    calls.append(("argext", len(in_ptrs), op))
+    f = np.argmax if op == L.ARGMAX else np.argmin
+    return np.array([f(_view(p, n, dtype)) for p, n in zip(in_ptrs, ns)], dtype=np.int64)
+
+
+def cumsum_out_dtype(dtype):
+    dtype = np.dtype(dtype)
+    return np.dtype(np.int64) if dtype == np.int32 else dtype
+
+
+def cumsum(dtype, in_ptrs, out_ptrs, ns):
+    calls.append(("cumsum", len(in_ptrs), None))
+    for p, o, n in zip(in_ptrs, out_ptrs, ns):
+        r = O.cumsum(_view(p, n, dtype))
+        _view(o, n, r.dtype)[:] = r
+
+
+def sort(dtype, in_ptrs, out_ptrs, ns):
+    calls.append(("sort", len(in_ptrs), None))
+    for p, o, n in zip(in_ptrs, out_ptrs, ns):
+        _view(o, n, dtype)[:] = np.sort(_view(p, n, dtype))
+
+
+def argsort(dtype, in_ptrs, out_ptrs, ns):
+    calls.append(("argsort", len(in_ptrs), None))
+    for p, o, n in zip(in_ptrs, out_ptrs, ns):
+        _view(o, n, np.int64)[:] = np.argsort(_view(p, n, dtype), kind="stable")
+
+
+def rand_f64(out_ptrs, ns, seeds):
+    calls.append(("rand", len(out_ptrs), None))
+    for p, n, s in zip(out_ptrs, ns, seeds):
+        _view(p, n, np.float64)[:] = O.rand_f64(n, s)
+
+
+def matmul_f32(a_ptrs, b_ptrs, c_ptrs, M, N, K):
+    calls.append(("matmul", len(a_ptrs), (M, N, K)))
+    for a, b, c in zip(a_ptrs, b_ptrs, c_ptrs):
+        _view(c, M * N, np.float32)[:] = (_view(a, M * K, np.float32).reshape(M, K) @
+                                          _view(b, K * N, np.float32).reshape(K, N)).reshape(-1)
+
+
+def sha256_device(ptrs, lens):
+    calls.append(("sha256", len(ptrs), None))
+    return [hashlib.sha256(_mem[p][:n].tobytes()).digest() for p, n in zip(ptrs, lens)]
+
+
+def sha256_host(buffers):
+    calls.append(("sha256", len(buffers), None))
+    return [hashlib.sha256(bytes(b)).digest() for b in buffers]
+
+
+class Sha256Stream:
+    def __init__(self):
+        self.h = hashlib.sha256()
+
+
+def sha256_update_many(streams, chunks):
+    calls.append(("sha256_update", len(streams), None))
+    for s, c in zip(streams, chunks):
+        s.h.update(c)
+
+
+def sha256_final_many(streams):
+    calls.append(("sha256_final", len(streams), None))
+    return [s.h.digest() for s in streams]

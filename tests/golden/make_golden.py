@@ -1,0 +1,118 @@
+"""Regenerates the committed golden fixtures.  Runs ONLY where the reference checkout exists
+(/root/reference, the authoring container); tests and the GPU box use the committed outputs.
+
+  http_replay.json  the reference's own FastAPI app (services/http_server.py:77-106), imported
+                    unmodified from /root/reference, driven in-process with the bodies of the
+                    reference's e2e tests (test/e2e/test_http.py:23-99) and example scripts
+                    (examples/{crash,escaping,files,ls}.py-style), with oracle.LocalCpuExecutor
+                    as the executor backend and the reference's own Storage
+                    (services/storage.py) as the object store.  Pins: response model shape,
+                    status codes (200 / 422 / 500), file-map round trip, env propagation,
+                    exit-code and stderr behaviour of failing scripts.
+  numeric.npz       seeded inputs and the results stock numpy (the reference's arithmetic)
+                    gives for every op class of SURVEY.md §8a; numpy version recorded.
+"""
+import json
+import sys
+import tempfile
+from contextvars import ContextVar
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, "/root/reference/src")
+OUT = Path(__file__).resolve().parent
+
+
+def http_replay():
+    from fastapi.testclient import TestClient
+
+    from code_interpreter.services.http_server import create_http_server
+    from code_interpreter.services.storage import Storage
+    from oracle.cpu_executor import LocalCpuExecutor
+
+    storage_dir = tempfile.mkdtemp(prefix="bci-golden-store-")
+    executor = LocalCpuExecutor(Storage(storage_dir), timeout=5)
+
+    class NoTools:  # custom tools are out of scope
+        def parse(self, **kw):
+            raise NotImplementedError
+
+        async def execute(self, **kw):
+            raise NotImplementedError
+
+    app = create_http_server(executor, NoTools(), ContextVar("request_id", default=""))
+    client = TestClient(app, raise_server_exceptions=False)
+    cases = []
+
+    def post(name, body, note):
+        r = client.post("/v1/execute", json=body)
+        try:
+            payload = r.json()
+        except Exception:
+            payload = r.text
+        cases.append({"name": name, "request": body, "status": r.status_code, "response": payload, "pins": note})
+        return payload
+
+    post("hello", {"source_code": "print(21 * 2)"}, "health_check.py:45-53 expects '42\\n'")
+    created = post("create_file", {"source_code": "\nwith open('file.txt', 'w') as f:\n    f.write(\"Hello, World!\")\n", "files": {}},
+                   "test_http.py:47-65: exit 0, files keys == {/workspace/file.txt}")
+    fid = created["files"]["/workspace/file.txt"]
+    post("read_file_back", {"source_code": "\nwith open('file.txt', 'r') as f:\n    print(f.read())\n",
+                            "files": {"/workspace/file.txt": fid}},
+         "test_http.py:67-85: stdout == content + newline, no files")
+    post("env", {"source_code": "import os\nprint('Hello ' + os.environ['MY_NAME'])", "files": {}, "env": {"MY_NAME": "John Doe"}},
+         "test_http.py:88-99")
+    post("crash", {"source_code": "0/0"}, "examples/crash.py:15: non-zero exit, traceback on stderr, HTTP 200")
+    post("sys_exit_3", {"source_code": "import sys\nprint('x')\nsys.exit(3)"}, "exit code passthrough (server.rs:165)")
+    post("stderr_and_unicode", {"source_code": "import sys\nprint('caf\\u00e9 \\u2713')\nprint('warn', file=sys.stderr)"}, "utf-8 text on both streams")
+    post("subdir_not_listed", {"source_code": "import os\nos.makedirs('d', exist_ok=True)\nopen('d/inner.txt','w').write('x')\nopen('top.bin','wb').write(bytes(range(256)))"},
+         "server.rs:98-118: only top-level regular files are reported")
+    post("timeout", {"source_code": "import time\ntime.sleep(30)"}, "server.rs:169: ('', 'Execution timed out', -1) [fixture timeout = 5 s]")
+    post("bad_path", {"source_code": "pass", "files": {"relative/path": "abc"}}, "validation.py:20-22: AbsolutePath -> 422")
+    post("bad_hash", {"source_code": "pass", "files": {"/workspace/x": "not a hash!"}}, "validation.py:19: Hash -> 422")
+    post("unknown_object", {"source_code": "pass", "files": {"/workspace/x": "deadbeef"}}, "storage.py:72-73 FileNotFoundError -> http_server.py:102-104 HTTP 500")
+    post("numpy_small", {"source_code": "import numpy as np\nnp.random.seed(42)\nx = np.random.normal(loc=10, scale=2, size=100)\nprint(repr(float(x.mean())))"},
+         "examples/using_imports.py:20-22: seeded legacy generator stays on numpy's MT19937 stream")
+    (OUT / "http_replay.json").write_text(json.dumps({"generated_with": {"numpy": np.__version__}, "cases": cases}, indent=1))
+    print("http_replay.json:", len(cases), "cases")
+
+
+def numeric():
+    data = {}
+    for name, dt in [("f32", np.float32), ("f64", np.float64), ("i32", np.int32), ("i64", np.int64)]:
+        rng = np.random.default_rng(9000 + len(name) + ord(name[0]) + int(name[1:]))
+        if np.issubdtype(dt, np.floating):
+            x = ((rng.random(5003) - 0.5) * 200).astype(dt)
+            y = ((rng.random(5003) - 0.5) * 200).astype(dt)
+        else:
+            x = rng.integers(-1000, 1000, 5003, dtype=dt)
+            y = rng.integers(-1000, 1000, 5003, dtype=dt)
+        data[f"{name}_x"], data[f"{name}_y"] = x, y
+        data[f"{name}_add"] = x + y
+        data[f"{name}_mul"] = x * y
+        data[f"{name}_square"] = np.square(x)
+        data[f"{name}_abs_sub"] = np.abs(x - y)
+        data[f"{name}_sum"] = np.asarray(np.sum(x))
+        data[f"{name}_mean"] = np.asarray(np.mean(x))
+        data[f"{name}_max"] = np.asarray(np.max(x))
+        data[f"{name}_min"] = np.asarray(np.min(x))
+        data[f"{name}_sumsq"] = np.asarray(np.sum(np.square(x)))
+        data[f"{name}_argmax"] = np.asarray(np.argmax(x))
+        data[f"{name}_argmin"] = np.asarray(np.argmin(x))
+        data[f"{name}_cumsum"] = np.cumsum(x)
+        data[f"{name}_sort"] = np.sort(x)
+        data[f"{name}_argsort"] = np.argsort(x, kind="stable")
+    a = np.random.default_rng(1000).random((96, 160), dtype=np.float32)
+    b = np.random.default_rng(1001).random((160, 64), dtype=np.float32)
+    data["mm_a"], data["mm_b"], data["mm_c"] = a, b, a @ b
+    data["numpy_version"] = np.asarray(np.__version__)
+    np.savez_compressed(OUT / "numeric.npz", **data)
+    print("numeric.npz:", len(data), "arrays")
+
+
+if __name__ == "__main__":
+    http_replay()
+    numeric()

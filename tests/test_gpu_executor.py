@@ -1,0 +1,101 @@
+"""End-to-end on the real device: agent source text -> zygote fork -> import hook -> broker ->
+batched CUDA launches -> stdout; output files hashed by the SHA-256 kernel.  Checked against
+numpy (the reference's arithmetic) and hashlib."""
+import asyncio
+import hashlib
+
+import numpy as np
+import pytest
+
+from bee_code_interpreter_b200 import numpy_proxy as P
+from bee_code_interpreter_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def executor(dev):
+    from bee_code_interpreter_b200.executor import LocalGpuExecutor
+
+    ex = LocalGpuExecutor(max_inflight=16, timeout=60, zygotes=2)
+    yield ex
+    ex.close()
+
+
+def test_metric_script_through_executor(executor, dev):
+    n = 10_000_000
+    launches0 = dev.launch_count()
+    res = asyncio.run(_many(executor, W.benchmark_numpy_source(n), 24))
+    for r in res:
+        assert r.exit_code == 0, r.stderr
+        v = float(r.stdout.splitlines()[0].split()[1])
+        assert abs(v / n - 1 / 3) < 6 * np.sqrt(4 / 45 / n)
+    # 24 requests x (rand + fused reduce) packed into fewer launches than requests x 2
+    assert 2 <= dev.launch_count() - launches0 <= 48
+    assert executor.broker.stats["max_batch"] >= 1
+
+
+async def _many(ex, src, k):
+    return await asyncio.gather(*(ex.execute(src) for _ in range(k)))
+
+
+C3_SCRIPT = '''
+import numpy as np
+x = np.load("x.npy"); y = np.load("y.npy")
+import numpy
+bx = numpy.sort(x)                      # large host array: offloaded by the hook
+print(repr(float(bx[0])), repr(float(bx[-1])))
+r = numpy.random.rand(2_000_000)
+print(type(r).__name__, r.shape, float(numpy.min(r)) >= 0.0, float(numpy.max(r)) < 1.0)
+s = r * 2.0 + 1.0
+print(repr(float(numpy.mean(s))))
+numpy.save("out.npy", numpy.asarray(numpy.sqrt(r)))
+'''
+
+
+def test_script_with_files_and_hook_offload(executor):
+    from bee_code_interpreter_b200.storage import ContentAddressedStorage  # noqa: F401
+    import io
+
+    x = np.random.default_rng(1).random(P.OFFLOAD_MIN_ELEMS * 2).astype(np.float32)
+    y = np.random.default_rng(2).random(1000).astype(np.float32)
+
+    def npy(a):
+        b = io.BytesIO()
+        np.save(b, a)
+        return b.getvalue()
+
+    async def go():
+        hx = await executor.file_storage.write(npy(x))
+        hy = await executor.file_storage.write(npy(y))
+        assert hx == hashlib.sha256(npy(x)).hexdigest()
+        r = await executor.execute(C3_SCRIPT, files={"/workspace/x.npy": hx, "/workspace/y.npy": hy})
+        assert r.exit_code == 0, r.stderr
+        lines = r.stdout.splitlines()
+        assert lines[0] == f"{float(x.min())!r} {float(x.max())!r}"
+        assert lines[1] == "DeviceArray (2000000,) True True"
+        assert abs(float(lines[2]) - 2.0) < 0.01
+        assert set(r.files) == {"/workspace/out.npy"}
+        blob = await executor.file_storage.read(r.files["/workspace/out.npy"])
+        assert hashlib.sha256(blob).hexdigest() == r.files["/workspace/out.npy"]
+        out = np.load(io.BytesIO(blob))
+        assert out.shape == (2_000_000,) and 0.0 <= out.min() and out.max() < 1.0
+
+    asyncio.run(go())
+
+
+def test_proxy_on_device_matches_numpy(dev):
+    from bee_code_interpreter_b200.backend import LocalBackend
+
+    be = LocalBackend(dev)
+    rng = np.random.default_rng(5)
+    xh, yh = rng.random(1 << 20, dtype=np.float32), rng.random(1 << 20, dtype=np.float32)
+    x, y = P.DeviceArray.from_host(be, xh), P.DeviceArray.from_host(be, yh)
+    assert abs(np.sum(np.square(x)) - np.sum(np.square(xh))) <= 1e-5 * np.sum(np.square(xh))
+    assert abs(np.mean(x * y + 1.0) - np.mean(xh * yh + 1.0)) <= 1e-5
+    assert np.max(np.abs(x - y)) == np.max(np.abs(xh - yh))
+    assert np.array_equal(np.asarray(x * y + 1.0), xh * yh + 1.0)          # unfused path, bit-exact
+    assert np.argmax(x) == np.argmax(xh)
+    assert np.array_equal(np.asarray(np.sort(x)), np.sort(xh))
+    k = P.DeviceArray.from_host(be, rng.integers(0, 2**31, 1 << 20, dtype=np.int64))
+    assert np.array_equal(np.asarray(np.cumsum(k)), np.cumsum(np.asarray(k)))

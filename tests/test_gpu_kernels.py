@@ -110,7 +110,9 @@ def test_ewise_scalar_and_misaligned(dev, bufs, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_ewise_exp_log_within_2ulp(dev, bufs, dtype):
+def test_ewise_exp_log_within_4ulp(dev, bufs, dtype):
+    """exp/log are the only ufuncs not correctly rounded on either side (CUDA libm <= 2 ulp,
+    numpy/SVML <= 1 ulp): bar = 4 ulp, far inside the 1e-5 relative bar for float32."""
     rng = np.random.default_rng(13)
     x = (rng.random(100_000) * 20 + 1e-3).astype(dtype)
     p = bufs.up(x)
@@ -120,7 +122,8 @@ def test_ewise_exp_log_within_2ulp(dev, bufs, dtype):
         got = dev.download(o, x.size, dtype)
         want = O.ewise(name, x)
         ulp = np.abs(got.astype(np.float64) - want.astype(np.float64)) / np.spacing(np.abs(want)).astype(np.float64)
-        assert ulp.max() <= 2.0, (name, ulp.max())
+        assert ulp.max() <= 4.0, (name, ulp.max())
+        assert np.all(np.abs(got - want) <= 1e-5 * np.abs(want) + 1e-30)
 
 
 def test_int_wraparound_matches_numpy(dev, bufs):

@@ -1,0 +1,316 @@
+"""Host-side logic on CPU, with tests/fake_device.py standing in for the GPU binding:
+numpy proxy semantics and fusion decisions, import hook, broker batching and buffer
+ownership, executor process model replayed against the reference-app fixtures, and the
+content-addressed storage protocol."""
+import asyncio
+import hashlib
+import json
+import sys
+import threading
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+import fake_device  # noqa: E402
+
+from bee_code_interpreter_b200 import _lib as L  # noqa: E402
+from bee_code_interpreter_b200 import numpy_proxy as P  # noqa: E402
+from bee_code_interpreter_b200.backend import LocalBackend  # noqa: E402
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture
+def be(built):
+    fake_device.reset()
+    return LocalBackend(fake_device)
+
+
+def names(calls):
+    return [c[0] for c in calls]
+
+
+# ---- proxy ------------------------------------------------------------------------------
+def test_benchmark_numpy_expression_is_two_launches(be):
+    x = P.device_rand(be, (100_000,), seed=7)
+    r = np.sum(np.square(x))                       # examples/benchmark-numpy.py:21
+    assert names(fake_device.calls) == ["rand", "reduce"]      # square never materialised
+    assert fake_device.calls[1][2] == (L.RED_SUM, L.PRE_SQUARE)
+    assert r == np.sum(np.square(np.asarray(x)))
+    assert isinstance(r, np.float64)
+
+
+def test_c3_request_mix_fuses_into_three_launches(be):
+    rng = np.random.default_rng(0)
+    xh, yh = rng.random(5000, dtype=np.float32), rng.random(5000, dtype=np.float32)
+    x, y = P.DeviceArray.from_host(be, xh), P.DeviceArray.from_host(be, yh)
+    fake_device.calls.clear()
+    r1 = np.sum(np.square(x))
+    r2 = np.mean(x * y + 1.0)
+    r3 = np.max(np.abs(x - y))
+    assert names(fake_device.calls) == ["reduce", "reduce_fused", "reduce_fused"]
+    assert fake_device.calls[1][2] == (L.RED_MEAN, L.EW_MUL, L.PRE_NONE, True)
+    assert fake_device.calls[2][2] == (L.RED_MAX, L.EW_SUB, L.PRE_ABS, False)
+    assert np.isclose(r1, np.sum(np.square(xh)), rtol=1e-6)
+    assert np.isclose(r2, np.mean(xh * yh + 1.0), rtol=1e-6)
+    assert r3 == np.max(np.abs(xh - yh))
+    assert r2.dtype == np.float32 and r3.dtype == np.float32
+
+
+def test_deferred_value_used_twice_is_materialised_once(be):
+    x = P.DeviceArray.from_host(be, np.arange(10, dtype=np.float64))
+    fake_device.calls.clear()
+    sq = np.square(x)
+    total = sq.sum()
+    first = sq[0:3]                                 # needs the array itself
+    assert total == 285.0 and list(first) == [0.0, 1.0, 4.0]
+    assert names(fake_device.calls).count("ewise") == 1
+
+
+def test_mutation_forces_dependents_first(be):
+    x = P.DeviceArray.from_host(be, np.arange(8, dtype=np.float64))
+    sq = np.square(x)          # deferred on x
+    x[0] = 100.0               # numpy semantics: sq was computed from the OLD x
+    assert np.array_equal(np.asarray(sq), np.square(np.arange(8, dtype=np.float64)))
+    assert np.asarray(x)[0] == 100.0
+    assert np.sum(x) == 100.0 + sum(range(1, 8))
+
+
+def test_scalar_typing_follows_nep50(be):
+    x32 = P.DeviceArray.from_host(be, np.ones(4, dtype=np.float32))
+    assert (x32 * 2.5).dtype == np.float32                       # python float is weak
+    r = x32 * np.float64(2.5)                                    # numpy float64 scalar promotes: host path
+    assert isinstance(r, np.ndarray) and r.dtype == np.float64
+    xi = P.DeviceArray.from_host(be, np.arange(4, dtype=np.int32))
+    assert isinstance(xi + 1, P.DeviceArray) and (xi + 1).dtype == np.int32
+    r = xi * 0.5                                                 # int array * python float -> float64 on host
+    assert isinstance(r, np.ndarray) and r.dtype == np.float64
+    assert np.array_equal(np.asarray(2 - xi), 2 - np.arange(4, dtype=np.int32))   # reflected subtract
+    assert np.array_equal(np.asarray(1.0 / x32), np.ones(4, dtype=np.float32))
+
+
+def test_unsupported_calls_fall_back_to_numpy_results(be):
+    h = np.random.default_rng(3).random((6, 5))
+    x = P.DeviceArray.from_host(be, h)
+    assert np.array_equal(np.sum(x, axis=0), h.sum(axis=0))
+    assert np.isclose(np.std(x), h.std())
+    assert np.array_equal(np.asarray(x.T), h.T)
+    assert np.array_equal(np.where(x > 0.5, 1, 0), np.where(h > 0.5, 1, 0))
+    assert x.tolist() == h.tolist()
+    assert np.array_equal(np.concatenate([x, x]), np.concatenate([h, h]))
+    b = P.DeviceArray.from_host(be, np.array([1, 2, 3], dtype=np.int64))
+    assert np.array_equal(np.asarray(b + np.array([1, 1, 1])), np.array([2, 3, 4]))  # mixed device/host operands
+    assert str(b) == str(np.array([1, 2, 3])) and len(b) == 3 and float(b[1]) == 2.0
+
+
+def test_sort_argmax_cumsum_matmul_entry_points(be):
+    h = np.random.default_rng(4).random(1000).astype(np.float32)
+    x = P.DeviceArray.from_host(be, h)
+    assert np.array_equal(np.asarray(np.sort(x)), np.sort(h))
+    assert np.argmax(x) == np.argmax(h) and x.argmin() == np.argmin(h)
+    k = P.DeviceArray.from_host(be, np.arange(100, dtype=np.int32))
+    cs = np.cumsum(k)
+    assert cs.dtype == np.int64 and np.array_equal(np.asarray(cs), np.cumsum(np.arange(100, dtype=np.int32)))
+    idx = np.argsort(x, kind="stable")
+    assert np.array_equal(np.asarray(idx), np.argsort(h, kind="stable"))
+    a = P.DeviceArray.from_host(be, np.random.default_rng(5).random((8, 6), dtype=np.float32))
+    b = P.DeviceArray.from_host(be, np.random.default_rng(6).random((6, 4), dtype=np.float32))
+    c = a @ b
+    assert isinstance(c, P.DeviceArray) and c.shape == (8, 4)
+    assert np.allclose(np.asarray(c), np.asarray(a) @ np.asarray(b), rtol=1e-6)
+    x.sort()
+    assert np.array_equal(np.asarray(x), np.sort(h))
+
+
+def test_buffers_are_released(be):
+    x = P.device_rand(be, (1000,), seed=1)
+    y = np.square(x) + 1.0
+    _ = np.asarray(y)
+    del x, y
+    import gc
+
+    gc.collect()
+    assert fake_device.live_buffers() == 0
+
+
+# ---- import hook ----------------------------------------------------------------------------
+def test_hook_gives_agent_code_the_view_and_libraries_the_real_module(be):
+    from bee_code_interpreter_b200 import numpy_hook as H
+
+    H._state.update(backend=None, backend_factory=lambda: be, view=None, seeded=False, min_rand=100)
+    agent = {"__name__": "__main__"}
+    lib = {"__name__": "pandas.core.frame"}
+    view = H.patched_import("numpy", agent, None, None, 0)
+    assert view is not np and view.pi == np.pi and view.ndarray is np.ndarray
+    assert H.patched_import("numpy", lib, None, None, 0) is np
+    assert H.patched_import("numpy", agent, None, None, 0) is view                     # idempotent
+    assert H.patched_import("numpy.random", agent, None, ("rand",), 0) is view.random
+    assert H.patched_import("json", agent, None, None, 0).__name__ == "json"
+    x = view.random.rand(500)
+    assert isinstance(x, P.DeviceArray) and x.shape == (500,)
+    assert isinstance(view.random.rand(10), np.ndarray)                                   # below the offload floor
+    assert isinstance(view.random.rand(), float)
+    view.random.seed(42)                                                                  # seeded => numpy's MT19937 stream
+    a = view.random.rand(500)
+    np.random.seed(42)
+    assert isinstance(a, np.ndarray) and np.array_equal(a, np.random.rand(500))
+    big = np.random.default_rng(0).random(P.OFFLOAD_MIN_ELEMS).astype(np.float32)
+    s = view.sort(big)
+    assert isinstance(s, P.DeviceArray) and np.array_equal(np.asarray(s), np.sort(big))
+    small = big[:100]
+    assert isinstance(view.sort(small), np.ndarray)
+    assert np.array_equal(view.cumsum([1, 2, 3]), [1, 3, 6])                             # lists untouched
+    H._state.update(backend=None, backend_factory=None, view=None, seeded=False, min_rand=1 << 16)
+
+
+# ---- broker -----------------------------------------------------------------------------------
+def test_broker_batches_concurrent_clients_and_scopes_buffers(built):
+    from bee_code_interpreter_b200.broker import GpuBroker
+    from bee_code_interpreter_b200.broker_client import RemoteBackend
+
+    fake_device.reset()
+    broker = GpuBroker(fake_device, coalesce_us=20_000)
+    try:
+        n_clients = 6
+        results = [None] * n_clients
+        barrier = threading.Barrier(n_clients)
+
+        def client(i):
+            rb = RemoteBackend(broker.socket_path)
+            x = P.device_rand(rb, (2000 + i,), seed=100 + i)
+            barrier.wait()
+            results[i] = float(np.sum(np.square(x)))
+            del x
+            rb.close()
+
+        threads = [threading.Thread(target=client, args=(i,)) for i in range(n_clients)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(30)
+        from oracle import numpy_oracle as O
+
+        for i in range(n_clients):
+            assert np.isclose(results[i], np.sum(np.square(O.rand_f64(2000 + i, 100 + i))), rtol=1e-12)
+        red = [c for c in fake_device.calls if c[0] == "reduce"]
+        assert sum(c[1] for c in red) == n_clients and max(c[1] for c in red) >= 2   # packed into shared launches
+        # ownership: a client cannot name another client's buffer
+        a, b = RemoteBackend(broker.socket_path), RemoteBackend(broker.socket_path)
+        pa = a.rand(100, 1)
+        with pytest.raises(L.BciError):
+            b.reduce(L.RED_SUM, np.float64, [pa], [100])
+        with pytest.raises(L.BciError):
+            a.reduce(L.RED_SUM, np.float64, [pa], [101])                              # past the end of its own buffer
+        assert np.isclose(a.reduce(L.RED_SUM, np.float64, [pa], [100])[0], O.rand_f64(100, 1).sum())
+        # big arrays cross through /dev/shm files, small ones inline
+        big = np.random.default_rng(1).random(50_000)
+        pb = a.upload(big)
+        assert np.array_equal(a.download(pb, big.size, big.dtype), big)
+        a.close(); b.close()
+        import time
+
+        for _ in range(100):
+            if fake_device.live_buffers() == 0:
+                break
+            time.sleep(0.02)
+        assert fake_device.live_buffers() == 0                                          # disconnect frees everything
+    finally:
+        broker.close()
+
+
+# ---- executor -------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def executor(built):
+    from bee_code_interpreter_b200.executor import LocalGpuExecutor
+
+    fake_device.reset()
+    ex = LocalGpuExecutor(device_module=fake_device, max_inflight=8, timeout=5, zygotes=1, min_rand_elems=1000)
+    yield ex
+    ex.close()
+
+
+def run(ex, case):
+    b = case["request"]
+    return asyncio.run(ex.execute(b["source_code"], files=b.get("files", {}), env=b.get("env", {})))
+
+
+def test_executor_matches_reference_app_fixtures(executor):
+    cases = {c["name"]: c for c in json.loads((GOLDEN / "http_replay.json").read_text())["cases"]}
+    for name in ("hello", "env", "sys_exit_3", "stderr_and_unicode", "numpy_small"):
+        r, want = run(executor, cases[name]), cases[name]["response"]
+        assert (r.stdout, r.stderr, r.exit_code, dict(r.files)) == (want["stdout"], want["stderr"], want["exit_code"], {}), name
+    r = run(executor, cases["create_file"])
+    assert r.exit_code == 0 and set(r.files) == {"/workspace/file.txt"}
+    assert r.files["/workspace/file.txt"] == hashlib.sha256(b"Hello, World!").hexdigest()   # content addressed
+    back = asyncio.run(executor.execute(cases["read_file_back"]["request"]["source_code"], files=dict(r.files)))
+    assert back.stdout == cases["read_file_back"]["response"]["stdout"] and back.exit_code == 0 and not back.files
+    r = run(executor, cases["crash"])
+    assert r.exit_code == 1 and r.stdout == "" and "ZeroDivisionError: division by zero" in r.stderr
+    r = run(executor, cases["subdir_not_listed"])
+    assert set(r.files) == {"/workspace/top.bin"}
+    assert r.files["/workspace/top.bin"] == hashlib.sha256(bytes(range(256))).hexdigest()
+    r = run(executor, cases["timeout"])
+    assert (r.stdout, r.stderr, r.exit_code) == ("", "Execution timed out", -1)
+    for bad in ("bad_path", "bad_hash"):
+        with pytest.raises(ValueError):
+            run(executor, cases[bad])
+    with pytest.raises(FileNotFoundError):
+        run(executor, cases["unknown_object"])
+    r = asyncio.run(executor.execute("import os, signal\nos.kill(os.getpid(), signal.SIGKILL)"))
+    assert r.exit_code == -1                                                            # server.rs:165
+
+
+def test_executor_runs_the_metric_script_on_the_device_backend(executor):
+    from bee_code_interpreter_b200 import workloads as W
+
+    fake_device.calls.clear()
+    n = 50_000
+    res = asyncio.run(_many(executor, W.benchmark_numpy_source(n), 12))
+    for r in res:
+        assert r.exit_code == 0, r.stderr
+        lines = r.stdout.splitlines()
+        assert lines[0].startswith("Result: ") and lines[1].startswith("Execution Time: ")
+        assert abs(float(lines[0].split()[1]) / n - 1 / 3) < 6 * np.sqrt(4 / 45 / n)
+    kinds = names(fake_device.calls)
+    assert kinds.count("ewise") == 0 and "rand" in kinds and "reduce" in kinds           # fused, on the "device"
+    assert sum(c[1] for c in fake_device.calls if c[0] == "rand") == 12
+
+
+async def _many(ex, src, k):
+    return await asyncio.gather(*(ex.execute(src) for _ in range(k)))
+
+
+# ---- storage -----------------------------------------------------------------------------------------
+def test_content_addressed_storage_protocol(built, tmp_path):
+    from bee_code_interpreter_b200.storage import ContentAddressedStorage, HashService
+
+    fake_device.reset()
+    st = ContentAddressedStorage(str(tmp_path / "objects"), HashService(fake_device, coalesce_us=5000))
+
+    async def scenario():
+        payloads = [np.random.default_rng(i).bytes(n) for i, n in enumerate([0, 1, 63, 64, 65, 70_000, 9_000_000])]
+
+        async def put(p):
+            async with st.writer() as w:
+                for off in range(0, len(p), 65536):                                     # httpx-sized chunks
+                    await w.write(p[off:off + 65536])
+            return w.hash                                                                # read after exit, like the reference
+
+        ids = await asyncio.gather(*(put(p) for p in payloads))
+        for p, i in zip(payloads, ids):
+            assert i == hashlib.sha256(p).hexdigest()
+            assert await st.exists(i) and await st.read(i) == p
+        assert await st.write(payloads[3]) == ids[3]                                    # dedupe, same id
+        assert len(list((tmp_path / "objects").iterdir())) == len(set(ids))           # no temp files left
+        with pytest.raises(FileNotFoundError):
+            await st.read("0" * 64)
+        with pytest.raises(ValueError):
+            await st.read("../etc/passwd")
+        async with st.reader(ids[2]) as f:
+            assert await f.read() == payloads[2]
+
+    asyncio.run(scenario())
+    assert max(c[1] for c in fake_device.calls if c[0].startswith("sha256")) >= 2        # writers hashed together
+    st.hasher.close()
