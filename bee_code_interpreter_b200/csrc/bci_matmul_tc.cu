@@ -1,14 +1,365 @@
-// bci_matmul_tc.cu — tcgen05 / TMA path of K3 (see bci_matmul.cu).  Placeholder until the
-// 3xTF32 kernel lands: reports "unsupported" so every shape takes the SIMT fp32 kernel.
+// bci_matmul_tc.cu — tcgen05 / TMA path of K3 (numpy.matmul, 2-D float32).
+//
+// fp32 accuracy on the tf32 tensor pipe: every operand is split x = hi + lo with
+// hi = rna_tf32(x), lo = rna_tf32(x - hi) and the product is accumulated in fp32 (TMEM) as
+//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi            (3xTF32; the dropped lo*lo term is
+// 2^-22 relative), which keeps max|dC|/max|C| around 1e-7 where a single tf32 pass gives 3e-4
+// (SURVEY.md hard part 1).
+//
+// Two kernels per batch slice:
+//  1. split_kernel   : A -> A_hi, A_lo (row-major MxK, K contiguous); B -> Bt_hi, Bt_lo
+//                      TRANSPOSED to NxK so that both MMA operands are K-major.  HBM-bound,
+//                      (M*K + K*N) * 12 bytes per request.
+//  2. gemm3x_kernel  : one CTA per 128x128 output tile, K walked in 32-element (128-byte)
+//                      blocks through a 3-stage shared-memory ring:
+//        warp 0  (1 thread) TMA producer: 4 x cp.async.bulk.tensor (A_hi, A_lo, Bt_hi, Bt_lo
+//                 tiles of 128 rows x 128 B, SWIZZLE_128B) per stage, mbarrier complete_tx;
+//        warp 1  (1 thread) MMA issuer: 12 x tcgen05.mma.cta_group::1.kind::tf32 per stage
+//                 (3 products x 4 K-steps of 8), accumulator = 128 lanes x 128 columns of TMEM,
+//                 tcgen05.commit releases the stage / signals the epilogue;
+//        warps 2-5 epilogue: tcgen05.ld 32x32b.x32 -> registers -> 128-bit global stores.
+//      Tensor maps are 3-D (k, row, request) over the split planes, which this file lays
+//      out itself, so ONE launch covers every request of the slice (grid.z = request).
+// Tensor-pipe bound in principle (137.4 GFLOP algorithmic per 4096^3 request, x3 issued);
+// this first version is L2-bandwidth limited (64 KiB of operands per 128x128x32 step) — the
+// 2-CTA 256x256 tile with the split done in shared memory is the planned next step.
 #include "bci_common.cuh"
+#include <cuda.h>
+#include <vector>
+#include <cstring>
+#include <cstdlib>
 
 namespace bci {
 
-int matmul_tc_supported(int, int, int, const void* const*, const void* const*, void* const*, int) { return 0; }
+constexpr int TBM = 128, TBN = 128, TBK = 32;          // CTA tile; TBK * 4 B = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kTileBytes = TBM * TBK * 4;              // 16 KiB per operand plane per stage
+constexpr int kStageBytes = 4 * kTileBytes;            // A_hi, A_lo, Bt_hi, Bt_lo
+constexpr int kTmemCols = 128;
+constexpr int kGemmThreads = 192;
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
-int matmul_tc_launch(int, const void* const*, const void* const*, void* const*, int, int, int) {
-  set_error("tcgen05 matmul path is not built");
-  return BCI_ERR_UNSUPPORTED;
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  // bounded spin: a protocol bug must end in a trap, not in a hung GPU
+  for (unsigned long long spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spins > (1ull << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 UMMA format):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B
+//   (8 rows x 128 B per swizzle atom) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::tf32 instruction descriptor: D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------- kernel 1: split (+ transpose B)
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float r = __fsub_rn(x, hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+
+struct SplitReq { const float* A; const float* Bm; };
+
+// grid: (tiles, 1, nb).  tiles [0, ta) split A linearly; tiles [ta, ta+tb) transpose 32x32 blocks of B.
+__global__ void __launch_bounds__(256)
+split_kernel(const SplitReq* __restrict__ reqs, float* __restrict__ a_hi, float* __restrict__ a_lo,
+             float* __restrict__ bt_hi, float* __restrict__ bt_lo, int M, int N, int K, unsigned ta) {
+  __shared__ float th[32][33], tl[32][33];
+  const SplitReq q = reqs[blockIdx.z];
+  const size_t abase = (size_t)blockIdx.z * M * K, bbase = (size_t)blockIdx.z * N * K;
+  if (blockIdx.x < ta) {
+    // 256 threads x 4 float4 = 4096 elements per CTA
+    const size_t e0 = (size_t)blockIdx.x * 4096;
+    const size_t total = (size_t)M * K;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t e = e0 + ((size_t)u * 256 + threadIdx.x) * 4;
+      if (e + 3 < total) {
+        const float4 v = *reinterpret_cast<const float4*>(q.A + e);
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y);
+        split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<float4*>(a_hi + abase + e) = h;
+        *reinterpret_cast<float4*>(a_lo + abase + e) = l;
+      }
+    }
+  } else {
+    // B is K x N row-major; write Bt (N x K): 32x32 tile through padded smem
+    const unsigned t = blockIdx.x - ta;
+    const int tiles_n = N / 32;
+    const int k0 = (t / tiles_n) * 32, n0 = (t % tiles_n) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int kk = ty + r * 8;
+      float h, l;
+      split_tf32(q.Bm[(size_t)(k0 + kk) * N + n0 + tx], h, l);
+      th[kk][tx] = h;
+      tl[kk][tx] = l;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int nn = ty + r * 8;
+      bt_hi[bbase + (size_t)(n0 + nn) * K + k0 + tx] = th[tx][nn];
+      bt_lo[bbase + (size_t)(n0 + nn) * K + k0 + tx] = tl[tx][nn];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- kernel 2: 3xTF32 GEMM
+struct GemmOut { float* C; };
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const GemmOut* __restrict__ outs, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * kStageBytes);
+  uint64_t* full_bar = bars;                 // [kStages]
+  uint64_t* empty_bar = bars + kStages;      // [kStages]
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TBN, m0 = blockIdx.y * TBM, req = blockIdx.z;
+  const int num_kb = K / TBK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b_lo)) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* st = smem + (size_t)s * kStageBytes;
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        tma_load_3d(st + 0 * kTileBytes, &map_a_hi, &full_bar[s], kb * TBK, m0, req);
+        tma_load_3d(st + 1 * kTileBytes, &map_a_lo, &full_bar[s], kb * TBK, m0, req);
+        tma_load_3d(st + 2 * kTileBytes, &map_b_hi, &full_bar[s], kb * TBK, n0, req);
+        tma_load_3d(st + 3 * kTileBytes, &map_b_lo, &full_bar[s], kb * TBK, n0, req);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TBM, TBN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + (size_t)s * kStageBytes);
+        const uint64_t a_hi = umma_desc_sw128(st + 0 * kTileBytes), a_lo = umma_desc_sw128(st + 1 * kTileBytes);
+        const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < TBK / 8; ++k) {
+          const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K-step of 8, in 16-byte units
+          umma_tf32(tmem_base, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base, a_hi + adv, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);  // the stage is free once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);     // accumulator complete
+    }
+  } else {
+    // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+    const int quad = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float* __restrict__ C = outs[req].C;
+    const int row = m0 + quad * 32 + lane;
+    float* crow = C + (size_t)row * N + n0;
+#pragma unroll 1
+    for (int c = 0; c < TBN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+          "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        *reinterpret_cast<uint4*>(crow + c * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 3-D map over a [nb][rows][K] float plane: box = 32 (k) x 128 (rows) x 1, 128-byte swizzle
+static int make_map(CUtensorMap* map, float* base, int rows, int K, int nb) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return BCI_ERR_CUDA; }
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nb};
+  const cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)rows * K * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)TBM, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return BCI_ERR_CUDA; }
+  return BCI_OK;
+}
+
+int matmul_tc_supported(int M, int N, int K, const void* const* A, const void* const* Bm, void* const* C, int B) {
+  if (M % TBM || N % TBN || K % TBK || M <= 0 || N <= 0 || K <= 0) return 0;
+  for (int i = 0; i < B; ++i) {
+    if ((reinterpret_cast<uintptr_t>(A[i]) | reinterpret_cast<uintptr_t>(Bm[i]) | reinterpret_cast<uintptr_t>(C[i])) & 15) return 0;
+  }
+  return encode_fn() != nullptr;
+}
+
+int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* const* C, int M, int N, int K) {
+  Ctx& c = ctx();
+  static bool attr_set = false;
+  if (!attr_set) {
+    BCI_CUDA(cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    attr_set = true;
+  }
+  // slice the batch so the split planes (12 bytes per input element) stay within ~8 GiB of scratch
+  const size_t per_req = ((size_t)M * K + (size_t)N * K) * 8;
+  int slice = (int)((8ull << 30) / (per_req ? per_req : 1));
+  if (slice < 1) slice = 1;
+  if (slice > B) slice = B;
+  if (slice > 65535) slice = 65535;
+  void* sc = nullptr;
+  int rc = scratch_get(per_req * (size_t)slice + 4096, &sc);
+  if (rc != BCI_OK) return rc;
+  float* a_hi = reinterpret_cast<float*>(sc);
+  float* a_lo = a_hi + (size_t)slice * M * K;
+  float* bt_hi = a_lo + (size_t)slice * M * K;
+  float* bt_lo = bt_hi + (size_t)slice * N * K;
+  for (int b0 = 0; b0 < B; b0 += slice) {
+    const int nb = B - b0 < slice ? B - b0 : slice;
+    std::vector<SplitReq> sreq((size_t)nb);
+    std::vector<GemmOut> outs((size_t)nb);
+    for (int i = 0; i < nb; ++i) {
+      sreq[i].A = reinterpret_cast<const float*>(A[b0 + i]);
+      sreq[i].Bm = reinterpret_cast<const float*>(Bm[b0 + i]);
+      outs[i].C = reinterpret_cast<float*>(C[b0 + i]);
+    }
+    void *d_sreq = nullptr, *d_outs = nullptr;
+    rc = stage_upload(sreq.data(), sizeof(SplitReq) * (size_t)nb, &d_sreq);
+    if (rc != BCI_OK) return rc;
+    rc = stage_upload(outs.data(), sizeof(GemmOut) * (size_t)nb, &d_outs);
+    if (rc != BCI_OK) return rc;
+    const unsigned ta = (unsigned)(((size_t)M * K + 4095) / 4096);
+    const unsigned tb = (unsigned)((size_t)(K / 32) * (N / 32));
+    split_kernel<<<dim3(ta + tb, 1, (unsigned)nb), 256, 0, c.stream>>>(
+        reinterpret_cast<const SplitReq*>(d_sreq), a_hi, a_lo, bt_hi, bt_lo, M, N, K, ta);
+    BCI_CHECK_LAUNCH();
+    CUtensorMap m_ah, m_al, m_bh, m_bl;
+    if ((rc = make_map(&m_ah, a_hi, M, K, nb)) != BCI_OK) return rc;
+    if ((rc = make_map(&m_al, a_lo, M, K, nb)) != BCI_OK) return rc;
+    if ((rc = make_map(&m_bh, bt_hi, N, K, nb)) != BCI_OK) return rc;
+    if ((rc = make_map(&m_bl, bt_lo, N, K, nb)) != BCI_OK) return rc;
+    gemm3x_kernel<<<dim3((unsigned)(N / TBN), (unsigned)(M / TBM), (unsigned)nb), kGemmThreads, kGemmSmem, c.stream>>>(
+        m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K);
+    BCI_CHECK_LAUNCH();
+  }
+  return BCI_OK;
 }
 
 }  // namespace bci

@@ -374,3 +374,29 @@ def test_matmul_f32_vs_f64(dev, bufs, shape):
         got = dev.download(p, M * N, np.float32).reshape(M, N)
         want = O.matmul_f64(a, b)
         assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 32), (128, 256, 4096), (512, 384, 640), (4096, 4096, 4096)])
+def test_matmul_tcgen05_3xtf32_path(dev, bufs, shape, monkeypatch):
+    """Shapes the tcgen05 path takes (multiples of 128/128/32): 3xTF32 must stay at fp32-level
+    accuracy (a single TF32 pass would be ~3e-4 on normal inputs) and agree with the SIMT path."""
+    M, N, K = shape
+    B = 2
+    monkeypatch.setenv("BCI_MATMUL", "tc")
+    As = [np.random.default_rng(1000 + i).standard_normal((M, K), dtype=np.float32) for i in range(B)]
+    Bs = [np.random.default_rng(1100 + i).standard_normal((K, N), dtype=np.float32) for i in range(B)]
+    pa = [bufs.up(a) for a in As]
+    pb = [bufs.up(b) for b in Bs]
+    pc = [bufs.new(M * N * 4) for _ in range(B)]
+    dev.matmul_f32(pa, pb, pc, M, N, K)
+    monkeypatch.setenv("BCI_MATMUL", "simt")
+    ps = [bufs.new(M * N * 4) for _ in range(B)]
+    dev.matmul_f32(pa, pb, ps, M, N, K)
+    for a, b, p, q in zip(As, Bs, pc, ps):
+        got = dev.download(p, M * N, np.float32).reshape(M, N)
+        simt = dev.download(q, M * N, np.float32).reshape(M, N)
+        want = O.matmul_f64(a, b)
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 2e-6 * scale, np.abs(got - want).max() / scale
+        assert np.abs(simt - want).max() <= 1e-5 * scale
+        assert np.abs(got - simt).max() <= 1e-5 * scale
