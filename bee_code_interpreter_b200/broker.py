@@ -163,6 +163,14 @@ class GpuBroker:
             return [None] * len(argl)
         if kind == "sha256":
             return dev.sha256_device([a[0] for a in argl], [a[1] for a in argl])
+        if kind == "sha256_host":      # whole payloads (bytes or mmapped files) of many requests
+            return dev.sha256_host([a[0] for a in argl])
+        if kind == "sha256_update":    # one chunk per streaming writer
+            streams = [a[0] for a in argl]
+            dev.sha256_update_many(streams, [a[1] for a in argl])
+            return streams
+        if kind == "sha256_final":
+            return dev.sha256_final_many([a[0] for a in argl])
         raise ValueError(f"unknown op class {kind!r}")
 
     # ---- connections ------------------------------------------------------------------------
@@ -300,6 +308,19 @@ class GpuBroker:
         if op == "sha256":
             _, p, nbytes = msg
             return self.submit(("sha256",), (need(p, nbytes), nbytes))
+        if op == "sha256_file":        # executor output files: hashed where they lie (page cache -> GPU)
+            _, path = msg
+            size = os.path.getsize(path)
+            data = np.memmap(path, dtype=np.uint8, mode="r") if size else b""
+            return self.submit(("sha256_host",), (data,))
+        if op == "sha256_bytes":
+            return self.submit(("sha256_host",), (msg[1],))
+        if op == "sha256_update":      # streaming ObjectWriter: state travels with the message
+            _, state, chunk = msg
+            st = dev.Sha256Stream.from_bytes(state) if state is not None else dev.Sha256Stream()
+            return self.submit(("sha256_update",), (st, chunk)).to_bytes()
+        if op == "sha256_final":
+            return self.submit(("sha256_final",), (dev.Sha256Stream.from_bytes(msg[1]),))
         if op == "ping":
             return {"device": dev.device_info() if hasattr(dev, "device_info") else None, "stats": dict(self.stats)}
         raise ValueError(f"unknown message {op!r}")
@@ -315,18 +336,72 @@ def _payload_array(payload, dt, n):
 def main():  # standalone: python -m bee_code_interpreter_b200.broker --socket PATH [--device N]
     import argparse
     import signal
+    import sys
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--socket", required=True)
     ap.add_argument("--device", type=int, default=None)
+    ap.add_argument("--coalesce-us", type=int, default=150)
+    ap.add_argument("--fake-device", default=None, help="(tests only) python module path of a device double")
     args = ap.parse_args()
-    from . import device
+    if args.fake_device:
+        import importlib
 
-    device.init(args.device)
-    broker = GpuBroker(device, socket_path=args.socket)
-    print(f"bci broker on {broker.socket_path} (GPU {device.device_info()['device']})", flush=True)
-    signal.sigwait({signal.SIGINT, signal.SIGTERM})
-    broker.close()
+        device = importlib.import_module(args.fake_device)
+        device.init(args.device)
+    else:
+        from . import device
+
+        device.init(args.device)
+    broker = GpuBroker(device, socket_path=args.socket, coalesce_us=args.coalesce_us)
+    sys.stdout.write("ready\n")
+    sys.stdout.flush()
+    parent = os.getppid()
+    signal.signal(signal.SIGTERM, lambda *_: sys.exit(0))
+    try:
+        while os.getppid() == parent:   # do not outlive the service that started us
+            time.sleep(1.0)
+    finally:
+        broker.close()
+
+
+class BrokerProcess:
+    """The GPU owner as its own OS process (its Python threads do not share a GIL with the
+    service's request handling).  One per GPU."""
+
+    def __init__(self, device: int | None = None, coalesce_us: int = 150, fake_device: str | None = None,
+                 extra_pythonpath: str | None = None):
+        import subprocess
+        import sys
+
+        self._dir = tempfile.mkdtemp(prefix="bci-broker-")
+        self.socket_path = os.path.join(self._dir, "broker.sock")
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        env = dict(os.environ)
+        paths = [root] + ([extra_pythonpath] if extra_pythonpath else []) + ([env["PYTHONPATH"]] if env.get("PYTHONPATH") else [])
+        env["PYTHONPATH"] = os.pathsep.join(paths)
+        cmd = [sys.executable, "-m", "bee_code_interpreter_b200.broker", "--socket", self.socket_path,
+               "--coalesce-us", str(coalesce_us)]
+        if device is not None:
+            cmd += ["--device", str(device)]
+        if fake_device:
+            cmd += ["--fake-device", fake_device]
+        self._proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, env=env, cwd=root)
+        line = self._proc.stdout.readline()
+        if line.strip() != b"ready":
+            raise L.BciError(L.ERR_NOT_INIT, "GPU broker process failed to start (is a B200 visible?)")
+
+    def close(self):
+        if self._proc.poll() is None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+        try:
+            os.rmdir(self._dir)
+        except OSError:
+            pass
 
 
 if __name__ == "__main__":

@@ -143,3 +143,16 @@ class RemoteBackend:
 
     def sha256(self, ptr, nbytes):
         return self._call("sha256", ptr, int(nbytes))
+
+    # ---- content hashing for the object store (storage.py) ------------------------------------
+    def sha256_file(self, path: str) -> bytes:
+        return self._call("sha256_file", path)
+
+    def sha256_bytes(self, data: bytes) -> bytes:
+        return self._call("sha256_bytes", data)
+
+    def sha256_update(self, state: bytes | None, chunk: bytes) -> bytes:
+        return self._call("sha256_update", state, chunk)
+
+    def sha256_final(self, state: bytes) -> bytes:
+        return self._call("sha256_final", state)

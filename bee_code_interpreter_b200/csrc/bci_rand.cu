@@ -48,9 +48,15 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
   return Philox4{c0, c1, c2, c3};
 }
 
+// ((a >> 5) * 2^26 + (b >> 6)) / 2^53, exactly (numpy legacy random_double).  Two 32-bit
+// I2F (XU pipe) + DMUL + DFMA (FP64 pipe) instead of 64-bit shifts/OR: ncu (profiles/r1a)
+// shows this kernel bound by the fmaheavy pipe (IMAD.WIDE of the Philox rounds, 82 %) with the
+// integer ALU second, so the conversion is kept off both.  Every step is exact: hi*2^-27 and
+// lo*2^-53 are exact scalings and their sum is a 53-bit multiple of 2^-53 below 1.
 __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
-  const unsigned long long v = ((unsigned long long)(a >> 5) << 26) | (unsigned long long)(b >> 6);
-  return (double)v * 1.1102230246251565e-16;  // 2^-53, exact scaling
+  const double hi = (double)(a >> 5);
+  const double lo = (double)(b >> 6);
+  return __fma_rn(hi, 7.450580596923828125e-09, __dmul_rn(lo, 1.1102230246251565404e-16));
 }
 
 constexpr int kRandUnroll = 4;
@@ -69,10 +75,12 @@ rand_f64_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   if (rem >= kRandTile && is_aligned32(o)) {
 #pragma unroll
     for (int u = 0; u < kRandUnroll; ++u) {
-      const size_t e = base + ((size_t)u * kThreads + threadIdx.x) * 4;  // first element (multiple of 4)
-      const unsigned long long p = e >> 1;
-      const Philox4 a = philox4x32_10((uint32_t)p, (uint32_t)(p >> 32), 0u, 0u, keys);
-      const Philox4 b = philox4x32_10((uint32_t)(p + 1), (uint32_t)((p + 1) >> 32), 0u, 0u, keys);
+      // base is a multiple of the 4096-element tile and the in-tile offset is < 4096, so the
+      // pair counter is (base >> 1) | (offset >> 1): no 64-bit carry chains in the hot loop
+      const uint32_t off = (uint32_t)(u * kThreads + threadIdx.x) * 4u;
+      const uint32_t plo = (uint32_t)(base >> 1) | (off >> 1), phi = (uint32_t)(base >> 33);
+      const Philox4 a = philox4x32_10(plo, phi, 0u, 0u, keys);
+      const Philox4 b = philox4x32_10(plo | 1u, phi, 0u, 0u, keys);
       VecOf<double> v;
       v.v[0] = u53(a.x, a.y);
       v.v[1] = u53(a.z, a.w);

@@ -177,6 +177,7 @@ void bci_shutdown(void) {
   std::lock_guard<std::mutex> lk(c.mu);
   if (!c.ready) return;
   cudaStreamSynchronize(c.stream);
+  if (c.pool) cudaMemPoolTrimTo(c.pool, 0);  // give cached blocks back to the driver
   if (c.h_stage) cudaFreeHost(c.h_stage);
   if (c.d_stage) cudaFree(c.d_stage);
   if (c.scratch) cudaFree(c.scratch);

@@ -310,6 +310,15 @@ class Sha256Stream:
         self.state = _lib.Sha256State()
         _lib.check(_lib.load().bci_sha256_init(C.byref(self.state)))
 
+    def to_bytes(self) -> bytes:
+        return bytes(self.state)
+
+    @classmethod
+    def from_bytes(cls, raw: bytes) -> "Sha256Stream":
+        obj = cls.__new__(cls)
+        obj.state = _lib.Sha256State.from_buffer_copy(raw)
+        return obj
+
 
 def sha256_update_many(streams: Sequence[Sha256Stream], chunks: Sequence[bytes]) -> None:
     B = len(streams)

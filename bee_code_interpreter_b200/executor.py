@@ -51,19 +51,27 @@ class LocalGpuExecutor:
 
     def __init__(self, file_storage=None, *, max_inflight: int = 64, timeout: float = 60.0,
                  broker=None, device_module=None, storage_path: str | None = None,
-                 min_rand_elems: int | None = None, zygotes: int | None = None):
+                 min_rand_elems: int | None = None, zygotes: int | None = None, device: int | None = None):
+        # The GPU is owned by a broker: an in-process GpuBroker when a device module is injected
+        # (tests), a given broker (several executors can share one per GPU), or — the default —
+        # a dedicated broker PROCESS, so its threads do not share this process's GIL.
         self._own_broker = broker is None
         if broker is None:
-            from .broker import GpuBroker
-            broker = GpuBroker(device_module)
+            if device_module is not None:
+                from .broker import GpuBroker
+                broker = GpuBroker(device_module)
+            else:
+                from .broker import BrokerProcess
+                broker = BrokerProcess(device)
         self.broker = broker
         self._tmp_storage = None
         if file_storage is None:
-            from .storage import ContentAddressedStorage, HashService
+            from .storage import ContentAddressedStorage, HashService, RemoteHashService
             if storage_path is None:
                 self._tmp_storage = tempfile.mkdtemp(prefix="bci-objects-")
                 storage_path = self._tmp_storage
-            file_storage = ContentAddressedStorage(storage_path, HashService(device_module))
+            hasher = HashService(device_module) if device_module is not None else RemoteHashService(broker.socket_path)
+            file_storage = ContentAddressedStorage(storage_path, hasher)
         self.file_storage = file_storage
         self.timeout = timeout
         self.max_inflight = max_inflight
@@ -117,7 +125,10 @@ class LocalGpuExecutor:
 
     # ---- internals -------------------------------------------------------------------------
     async def _store(self, path: Path) -> str:
-        async with self.file_storage.writer() as w:
+        put_file = getattr(self.file_storage, "put_file", None)
+        if put_file is not None:
+            return await put_file(str(path))
+        async with self.file_storage.writer() as w:  # any object store with the reference's protocol
             with open(path, "rb") as f:
                 while True:
                     chunk = f.read(1 << 20)

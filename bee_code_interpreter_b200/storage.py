@@ -61,6 +61,16 @@ class HashService:
             raise box[1]
         return box[0]
 
+    def hash_file(self, path: str) -> bytes:
+        stream = self.new_stream()
+        with open(path, "rb") as f:
+            while True:
+                chunk = f.read(8 << 20)
+                if not chunk:
+                    break
+                self.update(stream, chunk)
+        return self.final(stream)
+
     def close(self):
         self._running = False
         self._q.put(None)
@@ -109,6 +119,47 @@ class HashService:
         self.stats["launches"] += 1
         for (_, _, box), d in zip(group, digests):
             box[0] = d
+
+
+class _RemoteStream:
+    __slots__ = ("state",)
+
+    def __init__(self):
+        self.state = None  # serialized bci_sha256_state, travels with every chunk
+
+
+class RemoteHashService:
+    """Same interface as HashService, but the GPU belongs to the broker process: chunks are
+    sent to it and batched there with the chunks of every other writer (broker.py).  One
+    broker connection per thread (asyncio.to_thread workers)."""
+
+    def __init__(self, socket_path: str):
+        self.socket_path = socket_path
+        self._local = threading.local()
+
+    def _backend(self):
+        be = getattr(self._local, "be", None)
+        if be is None:
+            from .broker_client import RemoteBackend
+            be = self._local.be = RemoteBackend(self.socket_path)
+        return be
+
+    def new_stream(self):
+        return _RemoteStream()
+
+    def update(self, stream, data: bytes) -> None:
+        stream.state = self._backend().sha256_update(stream.state, data)
+
+    def final(self, stream) -> bytes:
+        if stream.state is None:
+            stream.state = self._backend().sha256_update(None, b"")
+        return self._backend().sha256_final(stream.state)
+
+    def hash_file(self, path: str) -> bytes:
+        return self._backend().sha256_file(path)
+
+    def close(self):
+        pass
 
 
 class ObjectWriter:
@@ -176,6 +227,21 @@ class ContentAddressedStorage:
         async with self.writer() as f:
             await f.write(data)
         return f.hash
+
+    async def put_file(self, path: str) -> str:
+        """Stores an existing file (an executor output) under its SHA-256: hashed where it
+        lies, then moved into the store (copy across filesystems).  Not in the reference's
+        Storage; the streaming `writer()` above is the protocol-compatible path."""
+        import shutil
+
+        digest = (await asyncio.to_thread(self.hasher.hash_file, str(path))).hex()
+        await self.storage_path.mkdir(parents=True, exist_ok=True)
+        target = self.storage_path / digest
+        if not await target.exists():
+            tmp = self.storage_path / (".tmp-" + secrets.token_hex(16))
+            await asyncio.to_thread(shutil.move, str(path), str(tmp))
+            await tmp.rename(target)
+        return digest
 
     @asynccontextmanager
     async def reader(self, object_hash: str):

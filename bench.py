@@ -188,7 +188,8 @@ def run_ours(args) -> dict | None:
         step_ms = float(t.item())
     value = requests * world / (step_ms / 1e3)
 
-    e2e = measure_e2e(args, dev, dist, rank, world, n)
+    dev.shutdown()   # hand the GPU memory back before the service processes start
+    e2e = measure_e2e(args, dist, rank, world, local, n)
 
     if dist is not None:
         dist.barrier()
@@ -229,47 +230,98 @@ def run_ours(args) -> dict | None:
     return out
 
 
-def measure_e2e(args, dev, dist, rank, world, n):
-    """The same requests through the public executor API: source text in, stdout out."""
+def measure_e2e(args, dist, rank, world, local, n):
+    """The same requests through the public executor API — LocalGpuExecutor.execute(source_code,
+    files, env): source text in, stdout text out — from `--e2e-workers` service processes per
+    GPU (the way several uvicorn workers would front one GPU), all sharing this rank's broker
+    process.  Timed from the first worker's start to the last worker's end."""
     if args.e2e_requests <= 0:
         return {"value": None, "unit": "requests/s", "error": "skipped (--e2e-requests 0)"}
     try:
-        from bee_code_interpreter_b200.executor import LocalGpuExecutor
+        from bee_code_interpreter_b200.broker import BrokerProcess
         from bee_code_interpreter_b200 import workloads as W
     except Exception as e:  # executor layer not importable: no end-to-end number
         return {"value": None, "unit": "requests/s", "error": repr(e)}
-    import numpy as np
-
-    requests = args.e2e_requests
-    src = W.benchmark_numpy_source(n)
-    execu = LocalGpuExecutor(max_inflight=args.e2e_inflight, timeout=300)
-
-    async def batch():
-        return await asyncio.gather(*(execu.execute(src) for _ in range(requests)))
-
-    asyncio.run(batch())  # warm-up (imports, pool growth)
-    dev.sync()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    res = asyncio.run(batch())
-    dt = time.perf_counter() - t0
-    ok = all(r.exit_code == 0 and r.stdout.startswith("Result:") for r in res)
-    vals = np.array([float(r.stdout.split()[1]) for r in res]) / n if ok else np.array([])
-    sigma = np.sqrt(4.0 / 45.0 / n)
-    parity = bool(ok and np.all(np.abs(vals - 1.0 / 3.0) < 6 * sigma))
+    workers = max(1, args.e2e_workers)
+    per_worker = [args.e2e_requests // workers + (1 if i < args.e2e_requests % workers else 0) for i in range(workers)]
+    broker = BrokerProcess(device=local)
+    procs = []
+    try:
+        for i in range(workers):
+            cmd = [sys.executable, str(ROOT / "bench.py"), "--e2e-worker", "--broker-socket", broker.socket_path,
+                   "--n", str(n), "--e2e-requests", str(per_worker[i]), "--e2e-inflight", str(args.e2e_inflight),
+                   "--e2e-zygotes", str(args.e2e_zygotes)]
+            procs.append(subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True))
+        for p in procs:
+            line = p.stdout.readline()
+            if line.strip() != "ready":
+                raise RuntimeError("e2e worker failed to start: %r" % line)
+        if dist is not None:
+            dist.barrier()
+        for p in procs:
+            p.stdin.write("go\n")
+            p.stdin.flush()
+        outs = [json.loads(p.stdout.readline()) for p in procs]
+        for p in procs:
+            p.wait(timeout=30)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        broker.close()
+    dt = max(o["t_end"] for o in outs) - min(o["t_start"] for o in outs)
     if dist is not None:
         import torch
 
         t = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    h2d = len(src.encode()) * requests
-    d2h = 8 * requests
-    execu.close()
-    return {"value": requests * world / dt, "unit": "requests/s", "requests_per_gpu": requests,
-            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "parity_6sigma": parity,
+    lat = sorted(x for o in outs for x in o["latencies"])
+    src_bytes = len(W.benchmark_numpy_source(n).encode())
+    return {"value": args.e2e_requests * world / dt, "unit": "requests/s", "requests_per_gpu": args.e2e_requests,
+            "service_workers_per_gpu": workers, "inflight_per_worker": args.e2e_inflight,
+            "h2d_bytes_per_step": src_bytes * args.e2e_requests, "d2h_bytes_per_step": 8 * args.e2e_requests,
+            "p50_latency_s": lat[len(lat) // 2] if lat else None,
+            "parity_6sigma": all(o["parity"] for o in outs),
             "api": "LocalGpuExecutor.execute(source_code, files, env)"}
+
+
+def e2e_worker(args):
+    """One service process: its own executor (zygotes, object store) on the shared broker."""
+    import types
+
+    import numpy as np
+    from bee_code_interpreter_b200.executor import LocalGpuExecutor
+    from bee_code_interpreter_b200 import workloads as W
+
+    n, requests = args.n, args.e2e_requests
+    src = W.benchmark_numpy_source(n)
+    shared = types.SimpleNamespace(socket_path=args.broker_socket, close=lambda: None)
+    execu = LocalGpuExecutor(broker=shared, max_inflight=args.e2e_inflight, timeout=300, zygotes=args.e2e_zygotes)
+    lat = []
+
+    async def one():
+        t = time.perf_counter()
+        r = await execu.execute(src)
+        lat.append(time.perf_counter() - t)
+        return r
+
+    async def batch(k):
+        return await asyncio.gather(*(one() for _ in range(k)))
+
+    asyncio.run(batch(min(requests, 2 * args.e2e_inflight)))  # warm-up: zygotes, pool growth, page cache
+    lat.clear()
+    print("ready", flush=True)
+    sys.stdin.readline()
+    t0 = time.time()
+    res = asyncio.run(batch(requests))
+    t1 = time.time()
+    ok = all(r.exit_code == 0 and r.stdout.startswith("Result:") for r in res)
+    vals = np.array([float(r.stdout.split()[1]) for r in res]) / n if ok else np.array([])
+    sigma = np.sqrt(4.0 / 45.0 / n)
+    parity = bool(ok and np.all(np.abs(vals - 1.0 / 3.0) < 6 * sigma))
+    execu.close()
+    print(json.dumps({"t_start": t0, "t_end": t1, "requests": requests, "parity": parity, "latencies": lat}), flush=True)
 
 
 # ---- the reference's CPU path ----------------------------------------------------------------
@@ -373,7 +425,11 @@ def main():
     ap.add_argument("--requests", type=int, default=PER_GPU_BATCH, help="requests per GPU per step")
     ap.add_argument("--wave", type=int, default=64, help="requests resident on the GPU at once")
     ap.add_argument("--e2e-requests", type=int, default=PER_GPU_BATCH)
-    ap.add_argument("--e2e-inflight", type=int, default=64)
+    ap.add_argument("--e2e-inflight", type=int, default=32)
+    ap.add_argument("--e2e-workers", type=int, default=4, help="service processes per GPU in the e2e arm")
+    ap.add_argument("--e2e-zygotes", type=int, default=4, help="warm interpreters per service process")
+    ap.add_argument("--e2e-worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--broker-socket", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)
@@ -381,6 +437,9 @@ def main():
     world = env_int("WORLD_SIZE", 1)
     if args.gpus != world and world == 1 and args.gpus > 1:
         print("bench.py: --gpus %d needs torchrun (one process per GPU); running 1 GPU" % args.gpus, file=sys.stderr)
+    if args.e2e_worker:
+        e2e_worker(args)
+        return
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
         print(json.dumps(out))

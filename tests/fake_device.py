@@ -198,12 +198,24 @@ def sha256_host(buffers):
 class Sha256Stream:
     def __init__(self):
         self.h = hashlib.sha256()
+        self.data = b""
+
+    def to_bytes(self):
+        return self.data
+
+    @classmethod
+    def from_bytes(cls, raw):
+        obj = cls()
+        obj.data = raw
+        obj.h.update(raw)
+        return obj
 
 
 def sha256_update_many(streams, chunks):
     calls.append(("sha256_update", len(streams), None))
     for s, c in zip(streams, chunks):
         s.h.update(c)
+        s.data += bytes(c)
 
 
 def sha256_final_many(streams):
