@@ -97,6 +97,10 @@ SIGNATURES = {
     "bci_sha256_init": (C.c_int, [C.POINTER(Sha256State)]),
     "bci_sha256_update_batch": (C.c_int, [C.c_int, C.POINTER(C.POINTER(Sha256State)), _VPP, _SZP]),
     "bci_sha256_final_batch": (C.c_int, [C.c_int, C.POINTER(C.POINTER(Sha256State)), C.c_void_p]),
+    # include/bci_broker.h
+    "bci_broker_start": (C.c_int, [C.c_char_p, C.c_int]),
+    "bci_broker_stop": (None, []),
+    "bci_broker_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

@@ -1,33 +1,57 @@
 """GPU broker: the one process (per GPU) that owns the CUDA context and packs the device ops
-of many concurrent `/v1/execute` requests into one launch per op class.
+of many concurrent `/v1/execute` requests into one launch per op class (protocol and
+rationale: include/bci_broker.h).
 
-Each reference request is its own OS process (executor/server.rs:152-157 spawns the script;
-kubernetes_code_executor.py:248-264 gives it a fresh pod).  Here the sandboxed script
-processes hold no CUDA context: their numpy proxies (numpy_proxy.DeviceArray) send small op
-descriptors over a Unix socket; array bytes never cross it unless the script really reads
-an array on the host.  The broker
-  * owns every device buffer, scoped to the connection that created it (a script can only
-    name its own buffers; everything it leaves behind is freed when it disconnects — the
-    analogue of deleting the pod, kubernetes_code_executor.py:262-264);
-  * queues compute ops and drains the queue in a dispatcher thread: all pending ops of the
-    same class (op, dtype, pre-transform) become ONE batched C-ABI call = one launch.
-Wire format: multiprocessing.connection (length-prefixed pickles) over AF_UNIX.
+  NativeBroker   the product: C++ threads inside libbci.so (csrc/bci_broker.cu) started with
+                 bci_broker_start(); no Python on the per-op path.
+  BrokerProcess  launches `python -m bee_code_interpreter_b200.broker` as the GPU-owning
+                 process (it calls bci_init + bci_broker_start and then just sleeps).
+  GpuBroker      a Python implementation of the SAME wire protocol over an injected device
+                 module — used by the CPU test-suite with tests/fake_device.py to exercise
+                 ownership, batching and the client without a GPU.
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import queue
+import socket
+import struct
 import tempfile
 import threading
 import time
 from collections import defaultdict
-from multiprocessing.connection import Listener
 
 import numpy as np
 
 from . import _lib as L
+from . import wire as W
 
-INLINE_MAX = 1 << 16  # arrays up to 64 KiB travel inline; larger ones through /dev/shm files
+STATE_SIZE = C.sizeof(L.Sha256State)
+_DTYPE = {L.F32: np.dtype(np.float32), L.F64: np.dtype(np.float64), L.I32: np.dtype(np.int32), L.I64: np.dtype(np.int64)}
+
+
+class NativeBroker:
+    """In-process handle on the C++ broker of libbci.so (the calling process owns the GPU)."""
+
+    def __init__(self, socket_path: str | None = None, coalesce_us: int = 150, device: int | None = None):
+        from . import device as dev
+
+        if not dev.is_initialised():
+            dev.init(device)
+        if socket_path is None:
+            socket_path = os.path.join(tempfile.mkdtemp(prefix="bci-broker-"), "broker.sock")
+        self.socket_path = socket_path
+        L.check(L.load().bci_broker_start(socket_path.encode(), int(coalesce_us)))
+
+    @property
+    def stats(self) -> dict:
+        arr = (C.c_uint64 * 4)()
+        L.load().bci_broker_stats(arr)
+        return {"jobs": arr[0], "batches": arr[1], "max_batch": arr[2], "connections": arr[3]}
+
+    def close(self):
+        L.load().bci_broker_stop()
 
 
 class _Job:
@@ -41,34 +65,33 @@ class _Job:
 
 
 class GpuBroker:
-    def __init__(self, device_module=None, socket_path: str | None = None, coalesce_us: int = 150):
-        if device_module is None:
-            from . import device as device_module  # the real C-ABI binding
-            if not device_module.is_initialised():
-                device_module.init()
+    """Python stand-in for the native broker: same protocol, injected device module."""
+
+    def __init__(self, device_module, socket_path: str | None = None, coalesce_us: int = 150):
         self.dev = device_module
+        if not self.dev.is_initialised():
+            self.dev.init()
         if socket_path is None:
             socket_path = os.path.join(tempfile.mkdtemp(prefix="bci-broker-"), "broker.sock")
         self.socket_path = socket_path
         self.coalesce_s = coalesce_us / 1e6
-        self._listener = Listener(address=socket_path, family="AF_UNIX", backlog=1024)
+        self._srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self._srv.bind(socket_path)
+        self._srv.listen(1024)
         self._jobs: "queue.SimpleQueue[_Job | None]" = queue.SimpleQueue()
         self._running = True
         self.stats = {"batches": 0, "jobs": 0, "max_batch": 0, "connections": 0}
-        self._threads = [threading.Thread(target=self._accept_loop, name="bci-accept", daemon=True),
-                         threading.Thread(target=self._dispatch_loop, name="bci-dispatch", daemon=True)]
-        for t in self._threads:
-            t.start()
+        for target, name in ((self._accept_loop, "bci-accept"), (self._dispatch_loop, "bci-dispatch")):
+            threading.Thread(target=target, name=name, daemon=True).start()
 
-    # ---- lifecycle ---------------------------------------------------------------------
     def close(self):
         if not self._running:
             return
         self._running = False
         self._jobs.put(None)
         try:
-            self._listener.close()
-        except Exception:
+            self._srv.close()
+        except OSError:
             pass
         try:
             os.unlink(self.socket_path)
@@ -109,8 +132,7 @@ class GpuBroker:
                 self.stats["jobs"] += len(group)
                 self.stats["max_batch"] = max(self.stats["max_batch"], len(group))
                 try:
-                    results = self._run_batch(key, [j.args for j in group])
-                    for j, r in zip(group, results):
+                    for j, r in zip(group, self._run_batch(key, [j.args for j in group])):
                         j.result = r
                 except Exception as e:
                     if len(group) == 1:
@@ -125,66 +147,54 @@ class GpuBroker:
                     j.done.set()
 
     def _run_batch(self, key, argl):
-        dev = self.dev
-        kind = key[0]
-        if kind == "rand":
-            dev.rand_f64([a[0] for a in argl], [a[1] for a in argl], [a[2] for a in argl])
+        dev, kind = self.dev, key[0]
+        col = lambda i: [a[i] for a in argl]  # noqa: E731
+        if kind == W.RAND:
+            dev.rand_f64(col(0), col(1), col(2))
             return [None] * len(argl)
-        if kind == "ewise":
+        if kind == W.EWISE:
             _, op, dt, has_in1 = key
-            dev.ewise(op, dt, [a[0] for a in argl], [a[1] for a in argl] if has_in1 else None,
-                      None if has_in1 else [a[2] for a in argl], [a[3] for a in argl], [a[4] for a in argl])
+            dev.ewise(op, dt, col(0), col(1) if has_in1 else None, None if has_in1 else col(2), col(3), col(4))
             return [None] * len(argl)
-        if kind == "reduce":
+        if kind == W.REDUCE:
             _, op, pre, dt = key
-            res = dev.reduce(op, dt, [a[0] for a in argl], [a[1] for a in argl], pre=pre)
-            return list(res)
-        if kind == "reduce_fused":
+            return list(dev.reduce(op, dt, col(0), col(1), pre=pre))
+        if kind == W.REDUCE_FUSED:
             _, op, pre, ew, dt, has_in1, has_add = key
-            res = dev.reduce_fused(op, ew, dt, [a[0] for a in argl], [a[1] for a in argl] if has_in1 else None,
-                                   None if has_in1 else [a[2] for a in argl], [a[4] for a in argl], pre=pre,
-                                   addends=[a[3] for a in argl] if has_add else None)
-            return list(res)
-        if kind == "argext":
-            _, op, dt = key
-            return list(dev.argext(op, dt, [a[0] for a in argl], [a[1] for a in argl]))
-        if kind == "cumsum":
-            dev.cumsum(key[1], [a[0] for a in argl], [a[1] for a in argl], [a[2] for a in argl])
+            return list(dev.reduce_fused(op, ew, dt, col(0), col(1) if has_in1 else None, None if has_in1 else col(2),
+                                         col(4), pre=pre, addends=col(3) if has_add else None))
+        if kind == W.ARGEXT:
+            return list(dev.argext(key[1], key[2], col(0), col(1)))
+        if kind in (W.CUMSUM, W.SORT, W.ARGSORT):
+            fn = {W.CUMSUM: dev.cumsum, W.SORT: dev.sort, W.ARGSORT: dev.argsort}[kind]
+            fn(key[1], col(0), col(1), col(2))
             return [None] * len(argl)
-        if kind == "sort":
-            dev.sort(key[1], [a[0] for a in argl], [a[1] for a in argl], [a[2] for a in argl])
+        if kind == W.MATMUL:
+            dev.matmul_f32(col(0), col(1), col(2), key[1], key[2], key[3])
             return [None] * len(argl)
-        if kind == "argsort":
-            dev.argsort(key[1], [a[0] for a in argl], [a[1] for a in argl], [a[2] for a in argl])
-            return [None] * len(argl)
-        if kind == "matmul":
-            _, M, N, K = key
-            dev.matmul_f32([a[0] for a in argl], [a[1] for a in argl], [a[2] for a in argl], M, N, K)
-            return [None] * len(argl)
-        if kind == "sha256":
-            return dev.sha256_device([a[0] for a in argl], [a[1] for a in argl])
-        if kind == "sha256_host":      # whole payloads (bytes or mmapped files) of many requests
-            return dev.sha256_host([a[0] for a in argl])
-        if kind == "sha256_update":    # one chunk per streaming writer
-            streams = [a[0] for a in argl]
-            dev.sha256_update_many(streams, [a[1] for a in argl])
-            return streams
-        if kind == "sha256_final":
-            return dev.sha256_final_many([a[0] for a in argl])
+        if kind == W.SHA256_DEV:
+            return dev.sha256_device(col(0), col(1))
+        if kind == W.SHA256_BYTES:
+            return dev.sha256_host(col(0))
+        if kind == W.SHA256_UPDATE:
+            dev.sha256_update_many(col(0), col(1))
+            return col(0)
+        if kind == W.SHA256_FINAL:
+            return dev.sha256_final_many(col(0))
         raise ValueError(f"unknown op class {kind!r}")
 
     # ---- connections ------------------------------------------------------------------------
     def _accept_loop(self):
         while self._running:
             try:
-                conn = self._listener.accept()
-            except Exception:
+                conn, _ = self._srv.accept()
+            except OSError:
                 break
             self.stats["connections"] += 1
             threading.Thread(target=self._serve, args=(conn,), name="bci-conn", daemon=True).start()
 
     def _serve(self, conn):
-        owned: dict[int, int] = {}  # device pointer -> bytes, buffers this script may name
+        owned: dict[int, int] = {}  # device pointer -> bytes: the buffers this script may name
         dev = self.dev
 
         def need(ptr, nbytes):
@@ -201,22 +211,26 @@ class GpuBroker:
         try:
             while True:
                 try:
-                    msg = conn.recv()
+                    head = W.recv_exact(conn, W.REQ.size)
+                    (op, code, dtc, pre, aux, flags, p0, p1, n, i0, i1, i2, s0, s1, plen, _r) = W.REQ.unpack(head)
+                    payload = W.recv_exact(conn, plen) if plen else b""
                 except (EOFError, OSError):
                     break
-                op = msg[0]
+                if op == W.FREE:
+                    if owned.pop(p0, None) is not None:
+                        dev.free(p0)
+                    continue
                 try:
-                    if op == "free":  # fire and forget
-                        p = msg[1]
-                        if owned.pop(p, None) is not None:
-                            dev.free(p)
-                        continue
-                    reply = self._handle(op, msg, need, new, owned)
-                    conn.send(("ok", reply))
+                    value, out = self._handle(op, code, dtc, pre, aux, flags, p0, p1, n, (i0, i1, i2), s0, s1, payload, need, new)
+                    conn.sendall(W.REP.pack(L.OK, len(out), value & 0xFFFFFFFFFFFFFFFF) + out)
                 except L.BciError as e:
-                    conn.send(("err", e.code, str(e)))
+                    text = str(e).encode()
+                    conn.sendall(W.REP.pack(e.code, len(text), 0) + text)
                 except Exception as e:  # protocol misuse etc.
-                    conn.send(("err", L.ERR_INVALID, repr(e)))
+                    text = repr(e).encode()
+                    conn.sendall(W.REP.pack(L.ERR_INVALID, len(text), 0) + text)
+        except OSError:
+            pass
         finally:
             for p in list(owned):
                 try:
@@ -224,150 +238,102 @@ class GpuBroker:
                 except Exception:
                     pass
             owned.clear()
-            try:
-                conn.close()
-            except Exception:
-                pass
+            conn.close()
 
-    def _handle(self, op, msg, need, new, owned):
+    def _handle(self, op, code, dtc, pre, aux, flags, p0, p1, n, ints, s0, s1, payload, need, new):
         dev = self.dev
-        if op == "alloc":
-            return new(msg[1])
-        if op == "rand":
-            _, n, seed = msg
+        dt = _DTYPE.get(dtc)
+        isf = dtc in (L.F32, L.F64)
+        if op == W.ALLOC:
+            return new(n), b""
+        if op == W.PING:
+            s = self.stats
+            return 0, struct.pack("<4Q", s["jobs"], s["batches"], s["max_batch"], s["connections"])
+        if op == W.RAND:
             p = new(n * 8)
-            self.submit(("rand",), (p, n, seed))
-            return p
-        if op == "ewise":
-            _, code, dt, in0, in1, scalar, n = msg
-            dt = np.dtype(dt)
+            self.submit((W.RAND,), (p, n, s0))
+            return p, b""
+        if op == W.EWISE:
             nb = n * dt.itemsize
+            has_in1 = bool(flags & W.F_IN1)
             out = new(nb)
-            self.submit(("ewise", code, dt, in1 is not None),
-                        (need(in0, nb), need(in1, nb) if in1 is not None else None, scalar, out, n))
-            return out
-        if op == "reduce":
-            _, code, pre, dt, p, n = msg
-            dt = np.dtype(dt)
-            return self.submit(("reduce", code, pre, dt), (need(p, n * dt.itemsize), n))
-        if op == "reduce_fused":
-            _, code, pre, ew, dt, in0, in1, scalar, addend, n = msg
-            dt = np.dtype(dt)
+            self.submit((W.EWISE, code, dt, has_in1),
+                        (need(p0, nb), need(p1, nb) if has_in1 else None, W.scalar_from_bits(s0, isf), out, n))
+            return out, b""
+        if op == W.REDUCE:
+            r = self.submit((W.REDUCE, code, pre, dt), (need(p0, n * dt.itemsize), n))
+            return _result_bits(r), b""
+        if op == W.REDUCE_FUSED:
             nb = n * dt.itemsize
-            return self.submit(("reduce_fused", code, pre, ew, dt, in1 is not None, addend is not None),
-                               (need(in0, nb), need(in1, nb) if in1 is not None else None, scalar, addend, n))
-        if op == "argext":
-            _, code, dt, p, n = msg
-            dt = np.dtype(dt)
-            return int(self.submit(("argext", code, dt), (need(p, n * dt.itemsize), n)))
-        if op == "cumsum":
-            _, dt, p, n = msg
-            dt = np.dtype(dt)
-            odt = dev.cumsum_out_dtype(dt)
-            out = new(n * odt.itemsize)
-            self.submit(("cumsum", dt), (need(p, n * dt.itemsize), out, n))
-            return out
-        if op in ("sort", "argsort"):
-            _, dt, p, n, inplace = msg
-            dt = np.dtype(dt)
-            need(p, n * dt.itemsize)
-            out = p if (inplace and op == "sort") else new(n * (8 if op == "argsort" else dt.itemsize))
-            self.submit((op, dt), (p, out, n))
-            return out
-        if op == "matmul":
-            _, a, b, M, N, K = msg
+            has_in1, has_add = bool(flags & W.F_IN1), bool(flags & W.F_ADDEND)
+            r = self.submit((W.REDUCE_FUSED, code, pre, aux, dt, has_in1, has_add),
+                            (need(p0, nb), need(p1, nb) if has_in1 else None, W.scalar_from_bits(s0, isf),
+                             W.scalar_from_bits(s1, isf), n))
+            return _result_bits(r), b""
+        if op == W.ARGEXT:
+            return int(self.submit((W.ARGEXT, code, dt), (need(p0, n * dt.itemsize), n))), b""
+        if op == W.CUMSUM:
+            out = new(n * dev.cumsum_out_dtype(dt).itemsize)
+            self.submit((W.CUMSUM, dt), (need(p0, n * dt.itemsize), out, n))
+            return out, b""
+        if op in (W.SORT, W.ARGSORT):
+            need(p0, n * dt.itemsize)
+            inplace = op == W.SORT and bool(flags & W.F_INPLACE)
+            out = p0 if inplace else new(n * (8 if op == W.ARGSORT else dt.itemsize))
+            self.submit((op, dt), (p0, out, n))
+            return out, b""
+        if op == W.MATMUL:
+            M, N, K = ints
             out = new(M * N * 4)
-            self.submit(("matmul", M, N, K), (need(a, M * K * 4), need(b, K * N * 4), out))
-            return out
-        if op == "d2d":
-            _, src, nbytes = msg
-            out = new(nbytes)
-            dev.d2d(out, need(src, nbytes), nbytes)
-            return out
-        if op == "upload":
-            _, dt, n, payload = msg
-            dt = np.dtype(dt)
-            arr = _payload_array(payload, dt, n)
-            p = new(arr.nbytes)
-            if arr.nbytes:
-                dev.h2d(p, arr)
+            self.submit((W.MATMUL, M, N, K), (need(p0, M * K * 4), need(p1, K * N * 4), out))
+            return out, b""
+        if op == W.COPY:
+            out = new(n)
+            dev.d2d(out, need(p0, n), n)
+            return out, b""
+        if op == W.UPLOAD:
+            data = np.fromfile(payload.decode(), dtype=np.uint8, count=n) if flags & W.F_SHM else np.frombuffer(payload, dtype=np.uint8, count=n)
+            p = new(n)
+            if n:
+                dev.h2d(p, data)
                 dev.sync()
-            return p
-        if op == "download":
-            _, p, dt, n, shm_path = msg
-            dt = np.dtype(dt)
-            need(p, n * dt.itemsize)
-            if shm_path is None:
-                return dev.download(p, n, dt).tobytes()
-            mm = np.memmap(shm_path, dtype=dt, mode="r+", shape=(n,))
-            host = dev.download(p, n, dt)
-            mm[:] = host
-            mm.flush()
-            del mm
-            return None
-        if op == "sha256":
-            _, p, nbytes = msg
-            return self.submit(("sha256",), (need(p, nbytes), nbytes))
-        if op == "sha256_file":        # executor output files: hashed where they lie (page cache -> GPU)
-            _, path = msg
-            size = os.path.getsize(path)
-            data = np.memmap(path, dtype=np.uint8, mode="r") if size else b""
-            return self.submit(("sha256_host",), (data,))
-        if op == "sha256_bytes":
-            return self.submit(("sha256_host",), (msg[1],))
-        if op == "sha256_update":      # streaming ObjectWriter: state travels with the message
-            _, state, chunk = msg
-            st = dev.Sha256Stream.from_bytes(state) if state is not None else dev.Sha256Stream()
-            return self.submit(("sha256_update",), (st, chunk)).to_bytes()
-        if op == "sha256_final":
-            return self.submit(("sha256_final",), (dev.Sha256Stream.from_bytes(msg[1]),))
-        if op == "ping":
-            return {"device": dev.device_info() if hasattr(dev, "device_info") else None, "stats": dict(self.stats)}
+            return p, b""
+        if op == W.DOWNLOAD:
+            host = dev.download(need(p0, n), n, np.uint8)
+            if flags & W.F_SHM:
+                mm = np.memmap(payload.decode(), dtype=np.uint8, mode="r+", shape=(n,))
+                mm[:] = host
+                mm.flush()
+                return 0, b""
+            return 0, host.tobytes()
+        if op == W.SHA256_DEV:
+            return 0, self.submit((W.SHA256_DEV,), (need(p0, n), n))
+        if op == W.SHA256_FILE:
+            path = os.fsdecode(payload)
+            data = np.memmap(path, dtype=np.uint8, mode="r") if os.path.getsize(path) else b""
+            return 0, self.submit((W.SHA256_BYTES,), (data,))
+        if op == W.SHA256_BYTES:
+            return 0, self.submit((W.SHA256_BYTES,), (payload,))
+        if op == W.SHA256_UPDATE:
+            if flags & W.F_STATE:
+                st, chunk = dev.Sha256Stream.from_bytes(payload[:STATE_SIZE]), payload[STATE_SIZE:]
+            else:
+                st, chunk = dev.Sha256Stream(), payload
+            return 0, self.submit((W.SHA256_UPDATE,), (st, chunk)).to_bytes()
+        if op == W.SHA256_FINAL:
+            return 0, self.submit((W.SHA256_FINAL,), (dev.Sha256Stream.from_bytes(payload[:STATE_SIZE]),))
         raise ValueError(f"unknown message {op!r}")
 
 
-def _payload_array(payload, dt, n):
-    kind, data = payload
-    if kind == "inline":
-        return np.frombuffer(data, dtype=dt, count=n)
-    return np.array(np.memmap(data, dtype=dt, mode="r", shape=(n,)))
-
-
-def main():  # standalone: python -m bee_code_interpreter_b200.broker --socket PATH [--device N]
-    import argparse
-    import signal
-    import sys
-
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--socket", required=True)
-    ap.add_argument("--device", type=int, default=None)
-    ap.add_argument("--coalesce-us", type=int, default=150)
-    ap.add_argument("--fake-device", default=None, help="(tests only) python module path of a device double")
-    args = ap.parse_args()
-    if args.fake_device:
-        import importlib
-
-        device = importlib.import_module(args.fake_device)
-        device.init(args.device)
-    else:
-        from . import device
-
-        device.init(args.device)
-    broker = GpuBroker(device, socket_path=args.socket, coalesce_us=args.coalesce_us)
-    sys.stdout.write("ready\n")
-    sys.stdout.flush()
-    parent = os.getppid()
-    signal.signal(signal.SIGTERM, lambda *_: sys.exit(0))
-    try:
-        while os.getppid() == parent:   # do not outlive the service that started us
-            time.sleep(1.0)
-    finally:
-        broker.close()
+def _result_bits(value) -> int:
+    """The 8-byte result slot bci_reduce would have written for this value."""
+    raw = np.asarray(value).tobytes()
+    return int.from_bytes(raw.ljust(8, b"\0"), "little")
 
 
 class BrokerProcess:
-    """The GPU owner as its own OS process (its Python threads do not share a GIL with the
-    service's request handling).  One per GPU."""
+    """The GPU owner as its own OS process.  One per GPU; any number of service processes and
+    script processes connect to its socket."""
 
     def __init__(self, device: int | None = None, coalesce_us: int = 150, fake_device: str | None = None,
                  extra_pythonpath: str | None = None):
@@ -402,6 +368,34 @@ class BrokerProcess:
             os.rmdir(self._dir)
         except OSError:
             pass
+
+
+def main():  # python -m bee_code_interpreter_b200.broker --socket PATH [--device N]
+    import argparse
+    import signal
+    import sys
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--socket", required=True)
+    ap.add_argument("--device", type=int, default=None)
+    ap.add_argument("--coalesce-us", type=int, default=150)
+    ap.add_argument("--fake-device", default=None, help="(tests only) module name of a device double")
+    args = ap.parse_args()
+    if args.fake_device:
+        import importlib
+
+        broker = GpuBroker(importlib.import_module(args.fake_device), socket_path=args.socket, coalesce_us=args.coalesce_us)
+    else:
+        broker = NativeBroker(socket_path=args.socket, coalesce_us=args.coalesce_us, device=args.device)
+    sys.stdout.write("ready\n")
+    sys.stdout.flush()
+    parent = os.getppid()
+    signal.signal(signal.SIGTERM, lambda *_: sys.exit(0))
+    try:
+        while os.getppid() == parent:   # do not outlive the service that started us
+            time.sleep(1.0)
+    finally:
+        broker.close()
 
 
 if __name__ == "__main__":

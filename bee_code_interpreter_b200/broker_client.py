@@ -1,21 +1,44 @@
-"""Script-side backend: same call surface `numpy_proxy` uses on `device.py`, but every call is
-a message to the GPU broker (broker.py).  The script process never loads CUDA.
+"""Script-side backend: the call surface `numpy_proxy` uses, implemented as messages to the
+per-GPU broker (include/bci_broker.h).  The script process never loads CUDA.
 
 One request = one connection; the broker frees everything the connection allocated when it
-closes, so a crashed or killed script leaks nothing."""
+closes, so a crashed or killed script leaks nothing.  Reduction results come back as the raw
+8-byte result slot of bci_reduce and are decoded with the same rules as device.py."""
 from __future__ import annotations
 
 import os
+import socket
+import struct
 import tempfile
 import threading
-from multiprocessing.connection import Client
 
 import numpy as np
 
 from . import _lib as L
-from .broker import INLINE_MAX
+from . import wire as W
 
 SOCKET_ENV = "BCI_BROKER_SOCKET"
+_CODE = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64, np.dtype(np.int32): L.I32, np.dtype(np.int64): L.I64}
+_DTYPE = {v: k for k, v in _CODE.items()}
+
+
+def _code(dtype) -> int:
+    try:
+        return _CODE[np.dtype(dtype)]
+    except KeyError:
+        raise L.Unsupported(L.ERR_UNSUPPORTED, f"dtype {dtype} is not handled on the device") from None
+
+
+def _decode_reduce(bits: int, op: int, code: int):
+    if op == L.RED_MEAN:
+        res = L.F32 if code == L.F32 else L.F64
+    elif op == L.RED_SUM:
+        res = L.I64 if code == L.I32 else code
+    else:
+        res = code
+    dt = _DTYPE[res]
+    raw = struct.pack("<Q", bits)
+    return np.frombuffer(raw[: dt.itemsize], dtype=dt)[0]
 
 
 class RemoteBackend:
@@ -23,136 +46,156 @@ class RemoteBackend:
         self.socket_path = socket_path or os.environ.get(SOCKET_ENV)
         if not self.socket_path:
             raise L.BciError(L.ERR_NOT_INIT, f"{SOCKET_ENV} is not set: no GPU broker to talk to")
-        self._conn = None
+        self._sock = None
         self._lock = threading.Lock()
 
     # ---- transport ---------------------------------------------------------------------
     def _connection(self):
-        if self._conn is None:
+        if self._sock is None:
+            s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
             try:
-                self._conn = Client(address=self.socket_path, family="AF_UNIX")
+                s.connect(self.socket_path)
             except OSError as e:
+                s.close()
                 raise L.BciError(L.ERR_NOT_INIT, f"cannot reach the GPU broker at {self.socket_path}: {e}") from None
-        return self._conn
+            self._sock = s
+        return self._sock
 
-    def _call(self, *msg):
+    def _call(self, op, **kw):
+        """Returns (value, payload)."""
+        msg = W.pack_req(op, **kw)
         with self._lock:
-            conn = self._connection()
             try:
-                conn.send(msg)
-                reply = conn.recv()
+                s = self._connection()
+                s.sendall(msg)
+                status, plen, value = W.REP.unpack(W.recv_exact(s, W.REP.size))
+                payload = W.recv_exact(s, plen) if plen else b""
             except (EOFError, OSError) as e:
-                self._conn = None
+                self._drop()
                 raise L.BciError(L.ERR_CUDA, f"GPU broker connection lost: {e}") from None
-        if reply[0] == "ok":
-            return reply[1]
-        _, code, text = reply
-        if code == L.ERR_UNSUPPORTED:
-            raise L.Unsupported(code, text)
-        raise L.BciError(code, text)
+        if status == L.OK:
+            return value, payload
+        text = payload.decode("utf-8", "replace")
+        if status == L.ERR_UNSUPPORTED:
+            raise L.Unsupported(status, text)
+        raise L.BciError(status, text)
 
-    def _post(self, *msg):
+    def _post(self, op, **kw):
         with self._lock:
             try:
-                self._connection().send(msg)
-            except (EOFError, OSError):
-                self._conn = None
+                self._connection().sendall(W.pack_req(op, **kw))
+            except (OSError, L.BciError):
+                self._drop()
+
+    def _drop(self):
+        if self._sock is not None:
+            try:
+                self._sock.close()
+            except OSError:
+                pass
+            self._sock = None
 
     def close(self):
         with self._lock:
-            if self._conn is not None:
-                try:
-                    self._conn.close()
-                finally:
-                    self._conn = None
+            self._drop()
 
-    def ping(self):
-        return self._call("ping")
+    def ping(self) -> dict:
+        _, payload = self._call(W.PING)
+        jobs, batches, max_batch, conns = struct.unpack("<4Q", payload[:32])
+        return {"stats": {"jobs": jobs, "batches": batches, "max_batch": max_batch, "connections": conns}}
 
-    # ---- device API subset used by numpy_proxy --------------------------------------------------
+    # ---- buffers ---------------------------------------------------------------------------
     def alloc(self, nbytes):
-        return self._call("alloc", int(nbytes))
+        return self._call(W.ALLOC, n=int(nbytes))[0]
 
     def free(self, ptr):
         if ptr:
-            self._post("free", ptr)
+            self._post(W.FREE, p0=ptr)
 
     def upload(self, arr: np.ndarray):
         arr = np.ascontiguousarray(arr)
-        if arr.nbytes <= INLINE_MAX:
-            return self._call("upload", arr.dtype.str, arr.size, ("inline", arr.tobytes()))
+        if arr.nbytes <= W.INLINE_MAX:
+            return self._call(W.UPLOAD, n=arr.nbytes, payload=arr.tobytes())[0]
         fd, path = tempfile.mkstemp(prefix="bci-up-", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
             with os.fdopen(fd, "wb") as f:
                 f.write(memoryview(arr).cast("B"))
-            return self._call("upload", arr.dtype.str, arr.size, ("shm", path))
+            return self._call(W.UPLOAD, n=arr.nbytes, flags=W.F_SHM, payload=path.encode())[0]
         finally:
             os.unlink(path)
 
     def download(self, ptr, n, dtype):
         dtype = np.dtype(dtype)
         nbytes = int(n) * dtype.itemsize
-        if nbytes <= INLINE_MAX:
-            return np.frombuffer(self._call("download", ptr, dtype.str, int(n), None), dtype=dtype).copy()
+        if nbytes <= W.INLINE_MAX:
+            return np.frombuffer(self._call(W.DOWNLOAD, p0=ptr, n=nbytes)[1], dtype=dtype).copy()
         fd, path = tempfile.mkstemp(prefix="bci-down-", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         try:
             os.ftruncate(fd, nbytes)
             os.close(fd)
-            self._call("download", ptr, dtype.str, int(n), path)
+            self._call(W.DOWNLOAD, p0=ptr, n=nbytes, flags=W.F_SHM, payload=path.encode())
             return np.fromfile(path, dtype=dtype, count=int(n))
         finally:
             os.unlink(path)
 
-    def d2d(self, dst, src, nbytes):
-        raise NotImplementedError  # proxies use copy_buffer() through the broker
-
     def copy_buffer(self, src, nbytes):
-        return self._call("d2d", src, int(nbytes))
+        return self._call(W.COPY, p0=src, n=int(nbytes))[0]
 
-    def rand_f64(self, out_ptrs, ns, seeds):
-        raise NotImplementedError  # allocation + fill is one message: rand()
-
+    # ---- ops (one request each; the broker packs concurrent requests into one launch) -------
     def rand(self, n, seed):
-        return self._call("rand", int(n), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        return self._call(W.RAND, n=int(n), s0=int(seed) & 0xFFFFFFFFFFFFFFFF)[0]
 
     def ewise_new(self, op, dtype, in0, in1, scalar, n):
-        return self._call("ewise", op, np.dtype(dtype).str, in0, in1, scalar, int(n))
+        code = _code(dtype)
+        isf = code in (L.F32, L.F64)
+        return self._call(W.EWISE, code=op, dtype=code, p0=in0, p1=in1 or 0, n=int(n),
+                          flags=W.F_IN1 if in1 is not None else 0, s0=W.scalar_bits(scalar, isf))[0]
 
     def reduce(self, op, dtype, in_ptrs, ns, pre=L.PRE_NONE):
-        return [self._call("reduce", op, pre, np.dtype(dtype).str, in_ptrs[0], int(ns[0]))]
+        code = _code(dtype)
+        bits = self._call(W.REDUCE, code=op, dtype=code, pre=pre, p0=in_ptrs[0], n=int(ns[0]))[0]
+        return [_decode_reduce(bits, op, code)]
 
     def reduce_fused(self, op, ew_op, dtype, in0, in1, scalars, ns, pre=L.PRE_NONE, addends=None):
-        return [self._call("reduce_fused", op, pre, ew_op, np.dtype(dtype).str, in0[0],
-                           in1[0] if in1 is not None else None, scalars[0] if scalars is not None else None,
-                           addends[0] if addends is not None else None, int(ns[0]))]
+        code = _code(dtype)
+        isf = code in (L.F32, L.F64)
+        flags = (W.F_IN1 if in1 is not None else 0) | (W.F_ADDEND if addends is not None else 0)
+        bits = self._call(W.REDUCE_FUSED, code=op, dtype=code, pre=pre, aux=ew_op, flags=flags, p0=in0[0],
+                          p1=in1[0] if in1 is not None else 0, n=int(ns[0]),
+                          s0=W.scalar_bits(scalars[0] if scalars is not None else None, isf),
+                          s1=W.scalar_bits(addends[0] if addends is not None else None, isf))[0]
+        return [_decode_reduce(bits, op, code)]
 
     def argext(self, op, dtype, in_ptrs, ns):
-        return [self._call("argext", op, np.dtype(dtype).str, in_ptrs[0], int(ns[0]))]
+        v = self._call(W.ARGEXT, code=op, dtype=_code(dtype), p0=in_ptrs[0], n=int(ns[0]))[0]
+        return [np.int64(v)]
 
     def cumsum_new(self, dtype, ptr, n):
-        return self._call("cumsum", np.dtype(dtype).str, ptr, int(n))
+        return self._call(W.CUMSUM, dtype=_code(dtype), p0=ptr, n=int(n))[0]
 
     def sort_new(self, dtype, ptr, n, inplace=False):
-        return self._call("sort", np.dtype(dtype).str, ptr, int(n), bool(inplace))
+        return self._call(W.SORT, dtype=_code(dtype), p0=ptr, n=int(n), flags=W.F_INPLACE if inplace else 0)[0]
 
     def argsort_new(self, dtype, ptr, n):
-        return self._call("argsort", np.dtype(dtype).str, ptr, int(n), False)
+        return self._call(W.ARGSORT, dtype=_code(dtype), p0=ptr, n=int(n))[0]
 
     def matmul_new(self, a, b, M, N, K):
-        return self._call("matmul", a, b, int(M), int(N), int(K))
-
-    def sha256(self, ptr, nbytes):
-        return self._call("sha256", ptr, int(nbytes))
+        return self._call(W.MATMUL, p0=a, p1=b, i0=int(M), i1=int(N), i2=int(K))[0]
 
     # ---- content hashing for the object store (storage.py) ------------------------------------
+    def sha256(self, ptr, nbytes):
+        return self._call(W.SHA256_DEV, p0=ptr, n=int(nbytes))[1]
+
     def sha256_file(self, path: str) -> bytes:
-        return self._call("sha256_file", path)
+        return self._call(W.SHA256_FILE, payload=os.fsencode(path))[1]
 
     def sha256_bytes(self, data: bytes) -> bytes:
-        return self._call("sha256_bytes", data)
+        return self._call(W.SHA256_BYTES, payload=bytes(data))[1]
 
     def sha256_update(self, state: bytes | None, chunk: bytes) -> bytes:
-        return self._call("sha256_update", state, chunk)
+        if state is None:
+            return self._call(W.SHA256_UPDATE, payload=bytes(chunk))[1]
+        return self._call(W.SHA256_UPDATE, flags=W.F_STATE, payload=state + bytes(chunk))[1]
 
     def sha256_final(self, state: bytes) -> bytes:
-        return self._call("sha256_final", state)
+        return self._call(W.SHA256_FINAL, payload=state)[1]

@@ -1,0 +1,480 @@
+// bci_broker.cu — native per-GPU broker (see include/bci_broker.h).
+//
+// Threads: one acceptor, one per connection (blocking reads of 96-byte requests), one
+// dispatcher.  Connection threads validate buffer ownership, allocate result buffers and
+// enqueue a Job; the dispatcher sleeps `coalesce_us` after the first arrival, drains the
+// queue, groups jobs by op class and issues ONE batched call of the C ABI (bci.h) per group —
+// the "one launch per op class for all concurrent requests" of the north star — then wakes
+// the waiting connection threads with their results.  A failing group is retried job by job
+// so one bad request cannot fail its neighbours.
+#include "bci_common.cuh"
+#include "../../include/bci_broker.h"
+
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <errno.h>
+#include <signal.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+namespace bci {
+namespace {
+
+struct Job {
+  bci_wire_req rq;
+  uint64_t out_ptr = 0;             // result buffer (already allocated by the connection thread)
+  const void* host_data = nullptr;  // sha256 of host bytes
+  size_t host_len = 0;
+  bci_sha256_state* state = nullptr;
+  // results
+  int status = BCI_OK;
+  uint64_t value = 0;
+  uint8_t digest[32];
+  std::string error;
+  bool done = false;
+};
+
+using Key = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, int64_t, int64_t, int64_t>;
+
+struct Broker {
+  std::string path;
+  int listen_fd = -1;
+  int coalesce_us = 150;
+  std::atomic<bool> running{false};
+  std::thread acceptor, dispatcher;
+  std::mutex mu;
+  std::condition_variable cv_jobs, cv_done;
+  std::deque<Job*> queue;
+  std::atomic<uint64_t> n_jobs{0}, n_batches{0}, max_batch{0}, n_conn{0};
+};
+
+Broker g;
+
+Key key_of(const bci_wire_req& r) {
+  // everything that must be equal for two requests to share one launch
+  switch (r.op) {
+    case BRK_RAND: return Key{r.op, 0, 0, 0, 0, 0, 0, 0, 0};
+    case BRK_EWISE: return Key{r.op, r.code, r.dtype, 0, 0, r.flags & BRK_F_IN1, 0, 0, 0};
+    case BRK_REDUCE: return Key{r.op, r.code, r.dtype, r.pre, 0, 0, 0, 0, 0};
+    case BRK_REDUCE_FUSED: return Key{r.op, r.code, r.dtype, r.pre, r.aux, r.flags & (BRK_F_IN1 | BRK_F_ADDEND), 0, 0, 0};
+    case BRK_ARGEXT: return Key{r.op, r.code, r.dtype, 0, 0, 0, 0, 0, 0};
+    case BRK_CUMSUM: case BRK_SORT: case BRK_ARGSORT: return Key{r.op, 0, r.dtype, 0, 0, 0, 0, 0, 0};
+    case BRK_MATMUL: return Key{r.op, 0, 0, 0, 0, 0, r.i0, r.i1, r.i2};
+    default: return Key{r.op, 0, 0, 0, 0, 0, 0, 0, 0};
+  }
+}
+
+bci_scalar scalar_of(uint64_t bits) {
+  bci_scalar s;
+  memcpy(&s, &bits, 8);
+  return s;
+}
+
+// One batched C-ABI call for a group of same-class jobs.  Returns the call's status.
+int run_group(std::vector<Job*>& grp) {
+  const int B = (int)grp.size();
+  const bci_wire_req& h = grp[0]->rq;
+  std::vector<const void*> in0(B), in1(B);
+  std::vector<void*> out(B);
+  std::vector<size_t> n(B);
+  for (int i = 0; i < B; ++i) {
+    in0[i] = reinterpret_cast<const void*>(grp[i]->rq.p0);
+    in1[i] = reinterpret_cast<const void*>(grp[i]->rq.p1);
+    out[i] = reinterpret_cast<void*>(grp[i]->out_ptr);
+    n[i] = (size_t)grp[i]->rq.n;
+  }
+  switch (h.op) {
+    case BRK_RAND: {
+      std::vector<uint64_t> seeds(B);
+      for (int i = 0; i < B; ++i) seeds[i] = grp[i]->rq.s0;
+      return bci_rand_f64(B, out.data(), n.data(), seeds.data());
+    }
+    case BRK_EWISE: {
+      std::vector<bci_scalar> sc(B);
+      for (int i = 0; i < B; ++i) sc[i] = scalar_of(grp[i]->rq.s0);
+      const bool arr = h.flags & BRK_F_IN1;
+      return bci_ewise((int)h.code, (int)h.dtype, B, in0.data(), arr ? in1.data() : nullptr, sc.data(), out.data(), n.data());
+    }
+    case BRK_REDUCE: case BRK_REDUCE_FUSED: {
+      std::vector<uint64_t> res(B, 0);
+      int rc;
+      if (h.op == BRK_REDUCE) {
+        rc = bci_reduce((int)h.code, (int)h.pre, (int)h.dtype, B, in0.data(), n.data(), res.data());
+      } else {
+        std::vector<bci_scalar> sc(B), ad(B);
+        for (int i = 0; i < B; ++i) { sc[i] = scalar_of(grp[i]->rq.s0); ad[i] = scalar_of(grp[i]->rq.s1); }
+        rc = bci_reduce_fused((int)h.code, (int)h.pre, (int)h.aux, (int)h.dtype, B, in0.data(),
+                              (h.flags & BRK_F_IN1) ? in1.data() : nullptr, sc.data(),
+                              (h.flags & BRK_F_ADDEND) ? ad.data() : nullptr, n.data(), res.data());
+      }
+      if (rc == BCI_OK) for (int i = 0; i < B; ++i) grp[i]->value = res[i];
+      return rc;
+    }
+    case BRK_ARGEXT: {
+      std::vector<int64_t> res(B, 0);
+      int rc = bci_argext((int)h.code, (int)h.dtype, B, in0.data(), n.data(), res.data());
+      if (rc == BCI_OK) for (int i = 0; i < B; ++i) grp[i]->value = (uint64_t)res[i];
+      return rc;
+    }
+    case BRK_CUMSUM: return bci_cumsum((int)h.dtype, B, in0.data(), out.data(), n.data());
+    case BRK_SORT: return bci_sort((int)h.dtype, B, in0.data(), out.data(), n.data());
+    case BRK_ARGSORT: return bci_argsort((int)h.dtype, B, in0.data(), reinterpret_cast<int64_t* const*>(out.data()), n.data());
+    case BRK_MATMUL: return bci_matmul_f32(B, in0.data(), in1.data(), out.data(), (int)h.i0, (int)h.i1, (int)h.i2);
+    case BRK_SHA256_DEV: case BRK_SHA256_FILE: case BRK_SHA256_BYTES: {
+      std::vector<uint8_t> dig((size_t)B * 32);
+      const bool on_dev = h.op == BRK_SHA256_DEV;
+      if (!on_dev) for (int i = 0; i < B; ++i) { in0[i] = grp[i]->host_data; n[i] = grp[i]->host_len; }
+      int rc = bci_sha256(B, in0.data(), n.data(), on_dev ? 1 : 0, dig.data());
+      if (rc == BCI_OK) for (int i = 0; i < B; ++i) memcpy(grp[i]->digest, &dig[(size_t)i * 32], 32);
+      return rc;
+    }
+    case BRK_SHA256_UPDATE: {
+      std::vector<bci_sha256_state*> st(B);
+      for (int i = 0; i < B; ++i) { st[i] = grp[i]->state; in0[i] = grp[i]->host_data; n[i] = grp[i]->host_len; }
+      return bci_sha256_update_batch(B, st.data(), in0.data(), n.data());
+    }
+    case BRK_SHA256_FINAL: {
+      std::vector<bci_sha256_state*> st(B);
+      std::vector<uint8_t> dig((size_t)B * 32);
+      for (int i = 0; i < B; ++i) st[i] = grp[i]->state;
+      int rc = bci_sha256_final_batch(B, st.data(), dig.data());
+      if (rc == BCI_OK) for (int i = 0; i < B; ++i) memcpy(grp[i]->digest, &dig[(size_t)i * 32], 32);
+      return rc;
+    }
+  }
+  set_error("broker: op %u cannot be batched", h.op);
+  return BCI_ERR_INVALID;
+}
+
+void dispatch_loop() {
+  while (g.running.load()) {
+    std::vector<Job*> jobs;
+    {
+      std::unique_lock<std::mutex> lk(g.mu);
+      g.cv_jobs.wait(lk, [] { return !g.queue.empty() || !g.running.load(); });
+      if (!g.running.load() && g.queue.empty()) break;
+    }
+    if (g.coalesce_us > 0) std::this_thread::sleep_for(std::chrono::microseconds(g.coalesce_us));
+    {
+      std::lock_guard<std::mutex> lk(g.mu);
+      jobs.assign(g.queue.begin(), g.queue.end());
+      g.queue.clear();
+    }
+    std::map<Key, std::vector<Job*>> groups;
+    for (Job* j : jobs) groups[key_of(j->rq)].push_back(j);
+    for (auto& kv : groups) {
+      std::vector<Job*>& grp = kv.second;
+      g.n_batches++;
+      g.n_jobs += grp.size();
+      if (grp.size() > g.max_batch.load()) g.max_batch = grp.size();
+      int rc = run_group(grp);
+      if (rc != BCI_OK && grp.size() > 1) {
+        for (Job* j : grp) {  // isolate the offender
+          std::vector<Job*> one{j};
+          j->status = run_group(one);
+          if (j->status != BCI_OK) j->error = bci_last_error();
+        }
+      } else {
+        const std::string err = rc != BCI_OK ? bci_last_error() : "";
+        for (Job* j : grp) { j->status = rc; j->error = err; }
+      }
+    }
+    {
+      std::lock_guard<std::mutex> lk(g.mu);
+      for (Job* j : jobs) j->done = true;
+    }
+    g.cv_done.notify_all();
+  }
+}
+
+void submit_and_wait(Job& job) {
+  std::unique_lock<std::mutex> lk(g.mu);
+  g.queue.push_back(&job);
+  g.cv_jobs.notify_one();
+  g.cv_done.wait(lk, [&] { return job.done; });
+}
+
+bool read_full(int fd, void* buf, size_t n) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(buf);
+  while (n) {
+    ssize_t r = ::recv(fd, p, n, 0);
+    if (r == 0) return false;
+    if (r < 0) { if (errno == EINTR) continue; return false; }
+    p += r; n -= (size_t)r;
+  }
+  return true;
+}
+bool write_full(int fd, const void* buf, size_t n) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(buf);
+  while (n) {
+    ssize_t r = ::send(fd, p, n, MSG_NOSIGNAL);
+    if (r < 0) { if (errno == EINTR) continue; return false; }
+    p += r; n -= (size_t)r;
+  }
+  return true;
+}
+bool reply(int fd, int status, uint64_t value, const void* payload, size_t len) {
+  bci_wire_rep rp;
+  rp.status = status; rp.payload_len = (uint32_t)len; rp.value = value;
+  if (!write_full(fd, &rp, sizeof rp)) return false;
+  return len == 0 || write_full(fd, payload, len);
+}
+bool reply_err(int fd, int status, const std::string& msg) { return reply(fd, status, 0, msg.data(), msg.size()); }
+
+struct MappedFile {
+  void* ptr = nullptr; size_t len = 0; int fd = -1;
+  bool open_ro(const std::string& path) {
+    fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0) return false;
+    len = (size_t)st.st_size;
+    if (len) { ptr = mmap(nullptr, len, PROT_READ, MAP_SHARED, fd, 0); if (ptr == MAP_FAILED) { ptr = nullptr; return false; } }
+    return true;
+  }
+  bool open_rw(const std::string& path, size_t want) {
+    fd = ::open(path.c_str(), O_RDWR);
+    if (fd < 0) return false;
+    len = want;
+    if (len) { ptr = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0); if (ptr == MAP_FAILED) { ptr = nullptr; return false; } }
+    return true;
+  }
+  ~MappedFile() { if (ptr) munmap(ptr, len); if (fd >= 0) ::close(fd); }
+};
+
+size_t out_elem_size(uint32_t op, uint32_t dtype) {
+  if (op == BRK_ARGSORT) return 8;
+  if (op == BRK_CUMSUM && dtype == BCI_I32) return 8;
+  return elem_size((int)dtype);
+}
+
+void serve(int fd) {
+  std::unordered_map<uint64_t, size_t> owned;
+  auto owns = [&](uint64_t p, size_t bytes) {
+    auto it = owned.find(p);
+    return it != owned.end() && bytes <= it->second;
+  };
+  auto new_buf = [&](size_t bytes, uint64_t* out) {
+    void* d = nullptr;
+    int rc = bci_alloc(bytes, &d);
+    if (rc == BCI_OK) { *out = reinterpret_cast<uint64_t>(d); owned[*out] = bytes ? bytes : 1; }
+    return rc;
+  };
+  auto drop = [&](uint64_t p) {
+    if (owned.erase(p)) bci_free(reinterpret_cast<void*>(p));
+  };
+  std::vector<uint8_t> payload;
+  for (;;) {
+    bci_wire_req rq;
+    if (!read_full(fd, &rq, sizeof rq)) break;
+    payload.resize(rq.payload_len);
+    if (rq.payload_len && !read_full(fd, payload.data(), rq.payload_len)) break;
+    const size_t es = elem_size((int)rq.dtype);
+    bool ok = true;
+    switch (rq.op) {
+      case BRK_FREE: drop(rq.p0); break;
+      case BRK_ALLOC: {
+        uint64_t p = 0;
+        int rc = new_buf((size_t)rq.n, &p);
+        ok = rc == BCI_OK ? reply(fd, BCI_OK, p, nullptr, 0) : reply_err(fd, rc, bci_last_error());
+        break;
+      }
+      case BRK_PING: {
+        uint64_t st[4] = {g.n_jobs.load(), g.n_batches.load(), g.max_batch.load(), g.n_conn.load()};
+        ok = reply(fd, BCI_OK, 0, st, sizeof st);
+        break;
+      }
+      case BRK_COPY: {
+        if (!owns(rq.p0, (size_t)rq.n)) { ok = reply_err(fd, BCI_ERR_INVALID, "buffer does not belong to this request"); break; }
+        uint64_t p = 0;
+        int rc = new_buf((size_t)rq.n, &p);
+        if (rc == BCI_OK) rc = bci_d2d(reinterpret_cast<void*>(p), reinterpret_cast<void*>(rq.p0), (size_t)rq.n);
+        ok = rc == BCI_OK ? reply(fd, BCI_OK, p, nullptr, 0) : reply_err(fd, rc, bci_last_error());
+        break;
+      }
+      case BRK_UPLOAD: {
+        uint64_t p = 0;
+        int rc = new_buf((size_t)rq.n, &p);
+        if (rc == BCI_OK && rq.n) {
+          if (rq.flags & BRK_F_SHM) {
+            MappedFile mf;
+            if (!mf.open_ro(std::string(payload.begin(), payload.end())) || mf.len < rq.n) { rc = BCI_ERR_INVALID; set_error("broker: cannot map upload file"); }
+            else rc = bci_h2d(reinterpret_cast<void*>(p), mf.ptr, (size_t)rq.n);
+            if (rc == BCI_OK) rc = bci_sync();
+          } else if (payload.size() >= rq.n) {
+            rc = bci_h2d(reinterpret_cast<void*>(p), payload.data(), (size_t)rq.n);
+            if (rc == BCI_OK) rc = bci_sync();
+          } else { rc = BCI_ERR_INVALID; set_error("broker: short upload payload"); }
+        }
+        if (rc != BCI_OK && p) drop(p);
+        ok = rc == BCI_OK ? reply(fd, BCI_OK, p, nullptr, 0) : reply_err(fd, rc, bci_last_error());
+        break;
+      }
+      case BRK_DOWNLOAD: {
+        if (!owns(rq.p0, (size_t)rq.n)) { ok = reply_err(fd, BCI_ERR_INVALID, "buffer does not belong to this request"); break; }
+        if (rq.flags & BRK_F_SHM) {
+          MappedFile mf;
+          int rc = BCI_OK;
+          if (!mf.open_rw(std::string(payload.begin(), payload.end()), (size_t)rq.n)) { rc = BCI_ERR_INVALID; set_error("broker: cannot map download file"); }
+          else if (rq.n) rc = bci_d2h(mf.ptr, reinterpret_cast<void*>(rq.p0), (size_t)rq.n);
+          ok = rc == BCI_OK ? reply(fd, BCI_OK, 0, nullptr, 0) : reply_err(fd, rc, bci_last_error());
+        } else {
+          std::vector<uint8_t> host((size_t)rq.n);
+          int rc = rq.n ? bci_d2h(host.data(), reinterpret_cast<void*>(rq.p0), (size_t)rq.n) : BCI_OK;
+          ok = rc == BCI_OK ? reply(fd, BCI_OK, 0, host.data(), host.size()) : reply_err(fd, rc, bci_last_error());
+        }
+        break;
+      }
+      case BRK_RAND: case BRK_EWISE: case BRK_CUMSUM: case BRK_SORT: case BRK_ARGSORT: case BRK_MATMUL:
+      case BRK_REDUCE: case BRK_REDUCE_FUSED: case BRK_ARGEXT: case BRK_SHA256_DEV: {
+        Job job;
+        job.rq = rq;
+        // ownership + sizes
+        bool valid = true;
+        size_t in_bytes = (size_t)rq.n * es, out_bytes = 0;
+        if (rq.op == BRK_RAND) { in_bytes = 0; out_bytes = (size_t)rq.n * 8; }
+        else if (rq.op == BRK_SHA256_DEV) { in_bytes = (size_t)rq.n; valid = owns(rq.p0, in_bytes); }
+        else if (rq.op == BRK_MATMUL) {
+          valid = rq.i0 > 0 && rq.i1 > 0 && rq.i2 > 0 && owns(rq.p0, (size_t)rq.i0 * rq.i2 * 4) && owns(rq.p1, (size_t)rq.i2 * rq.i1 * 4);
+          out_bytes = (size_t)rq.i0 * rq.i1 * 4;
+        } else {
+          valid = es != 0 && owns(rq.p0, in_bytes);
+          if (valid && (rq.flags & BRK_F_IN1) && (rq.op == BRK_EWISE || rq.op == BRK_REDUCE_FUSED)) valid = owns(rq.p1, in_bytes);
+          if (rq.op == BRK_EWISE || rq.op == BRK_CUMSUM || rq.op == BRK_SORT || rq.op == BRK_ARGSORT)
+            out_bytes = (size_t)rq.n * out_elem_size(rq.op, rq.dtype);
+        }
+        if (!valid) { ok = reply_err(fd, BCI_ERR_INVALID, "buffer does not belong to this request"); break; }
+        const bool inplace = rq.op == BRK_SORT && (rq.flags & BRK_F_INPLACE);
+        const bool needs_out = !inplace && (rq.op == BRK_RAND || rq.op == BRK_EWISE || rq.op == BRK_CUMSUM ||
+                                            rq.op == BRK_SORT || rq.op == BRK_ARGSORT || rq.op == BRK_MATMUL);
+        if (inplace) job.out_ptr = rq.p0;
+        if (needs_out) {
+          int rc = new_buf(out_bytes, &job.out_ptr);
+          if (rc != BCI_OK) { ok = reply_err(fd, rc, bci_last_error()); break; }
+        }
+        submit_and_wait(job);
+        if (job.status != BCI_OK) {
+          if (job.out_ptr && job.out_ptr != rq.p0) drop(job.out_ptr);
+          ok = reply_err(fd, job.status, job.error);
+        } else if (rq.op == BRK_SHA256_DEV) {
+          ok = reply(fd, BCI_OK, 0, job.digest, 32);
+        } else {
+          const bool scalar_result = rq.op == BRK_REDUCE || rq.op == BRK_REDUCE_FUSED || rq.op == BRK_ARGEXT;
+          ok = reply(fd, BCI_OK, scalar_result ? job.value : job.out_ptr, nullptr, 0);
+        }
+        break;
+      }
+      case BRK_SHA256_FILE: case BRK_SHA256_BYTES: {
+        Job job;
+        job.rq = rq;
+        MappedFile mf;
+        if (rq.op == BRK_SHA256_FILE) {
+          if (!mf.open_ro(std::string(payload.begin(), payload.end()))) { ok = reply_err(fd, BCI_ERR_INVALID, "broker: cannot open file to hash"); break; }
+          job.host_data = mf.ptr; job.host_len = mf.len;
+        } else { job.host_data = payload.data(); job.host_len = payload.size(); }
+        submit_and_wait(job);
+        ok = job.status == BCI_OK ? reply(fd, BCI_OK, 0, job.digest, 32) : reply_err(fd, job.status, job.error);
+        break;
+      }
+      case BRK_SHA256_UPDATE: case BRK_SHA256_FINAL: {
+        Job job;
+        job.rq = rq;
+        bci_sha256_state st;
+        size_t off = 0;
+        if (rq.op == BRK_SHA256_FINAL || (rq.flags & BRK_F_STATE)) {
+          if (payload.size() < sizeof st) { ok = reply_err(fd, BCI_ERR_INVALID, "broker: short hash state"); break; }
+          memcpy(&st, payload.data(), sizeof st);
+          if (st.buf_len >= 64) { ok = reply_err(fd, BCI_ERR_INVALID, "broker: corrupt hash state"); break; }
+          off = sizeof st;
+        } else {
+          bci_sha256_init(&st);
+        }
+        job.state = &st;
+        job.host_data = payload.data() + off;
+        job.host_len = payload.size() - off;
+        submit_and_wait(job);
+        if (job.status != BCI_OK) ok = reply_err(fd, job.status, job.error);
+        else if (rq.op == BRK_SHA256_FINAL) ok = reply(fd, BCI_OK, 0, job.digest, 32);
+        else ok = reply(fd, BCI_OK, 0, &st, sizeof st);
+        break;
+      }
+      default:
+        ok = reply_err(fd, BCI_ERR_INVALID, "broker: unknown op");
+    }
+    if (!ok) break;
+  }
+  for (auto& kv : owned) bci_free(reinterpret_cast<void*>(kv.first));
+  ::close(fd);
+}
+
+void accept_loop() {
+  while (g.running.load()) {
+    int fd = ::accept(g.listen_fd, nullptr, nullptr);
+    if (fd < 0) {
+      if (errno == EINTR) continue;
+      break;
+    }
+    g.n_conn++;
+    std::thread(serve, fd).detach();
+  }
+}
+
+}  // namespace
+}  // namespace bci
+
+using namespace bci;
+
+extern "C" int bci_broker_start(const char* socket_path, int coalesce_us) {
+  BCI_REQUIRE_INIT();
+  if (!socket_path) { set_error("bci_broker_start: NULL path"); return BCI_ERR_INVALID; }
+  if (g.running.load()) { set_error("bci_broker_start: already running"); return BCI_ERR_INVALID; }
+  sockaddr_un addr;
+  memset(&addr, 0, sizeof addr);
+  addr.sun_family = AF_UNIX;
+  if (strlen(socket_path) >= sizeof addr.sun_path) { set_error("bci_broker_start: socket path too long"); return BCI_ERR_INVALID; }
+  strcpy(addr.sun_path, socket_path);
+  ::unlink(socket_path);
+  int fd = ::socket(AF_UNIX, SOCK_STREAM, 0);
+  if (fd < 0 || ::bind(fd, reinterpret_cast<sockaddr*>(&addr), sizeof addr) != 0 || ::listen(fd, 4096) != 0) {
+    set_error("bci_broker_start: cannot listen on %s: %s", socket_path, strerror(errno));
+    if (fd >= 0) ::close(fd);
+    return BCI_ERR_INVALID;
+  }
+  g.path = socket_path;
+  g.listen_fd = fd;
+  g.coalesce_us = coalesce_us;
+  g.running = true;
+  g.dispatcher = std::thread(dispatch_loop);
+  g.acceptor = std::thread(accept_loop);
+  return BCI_OK;
+}
+
+extern "C" void bci_broker_stop(void) {
+  if (!g.running.exchange(false)) return;
+  ::shutdown(g.listen_fd, SHUT_RDWR);
+  ::close(g.listen_fd);
+  g.cv_jobs.notify_all();
+  if (g.acceptor.joinable()) g.acceptor.join();
+  if (g.dispatcher.joinable()) g.dispatcher.join();
+  ::unlink(g.path.c_str());
+}
+
+extern "C" int bci_broker_stats(uint64_t stats[4]) {
+  if (!stats) return BCI_ERR_INVALID;
+  stats[0] = g.n_jobs.load(); stats[1] = g.n_batches.load(); stats[2] = g.max_batch.load(); stats[3] = g.n_conn.load();
+  return BCI_OK;
+}

@@ -28,10 +28,14 @@ RED = {L.RED_SUM: np.sum, L.RED_MEAN: np.mean, L.RED_MAX: np.max, L.RED_MIN: np.
 PRE = {L.PRE_NONE: lambda a: a, L.PRE_SQUARE: np.square, L.PRE_ABS: np.absolute}
 
 
+_reset_floor = [0]
+
+
 def reset():
     with _lock:
         _mem.clear()
         calls.clear()
+        _reset_floor[0] = _next[0]
 
 
 def live_buffers() -> int:
@@ -73,7 +77,7 @@ def alloc(nbytes):
 
 def free(ptr):
     with _lock:
-        if ptr:
+        if ptr and ptr >= _reset_floor[0]:  # buffers from before the last reset() are already gone
             _mem.pop(ptr)  # KeyError = double free / foreign pointer: a real bug
 
 
@@ -195,19 +199,27 @@ def sha256_host(buffers):
     return [hashlib.sha256(bytes(b)).digest() for b in buffers]
 
 
+_streams: dict[int, "hashlib._Hash"] = {}
+_stream_ids = [0]
+
+
 class Sha256Stream:
+    """Serialises to a fixed-size blob like bci_sha256_state (an id into a registry here)."""
+
     def __init__(self):
         self.h = hashlib.sha256()
-        self.data = b""
 
     def to_bytes(self):
-        return self.data
+        with _lock:
+            _stream_ids[0] += 1
+            sid = _stream_ids[0]
+            _streams[sid] = self.h.copy()
+        return sid.to_bytes(8, "little").ljust(112, b"\0")
 
     @classmethod
     def from_bytes(cls, raw):
         obj = cls()
-        obj.data = raw
-        obj.h.update(raw)
+        obj.h = _streams[int.from_bytes(raw[:8], "little")].copy()
         return obj
 
 
@@ -215,7 +227,6 @@ def sha256_update_many(streams, chunks):
     calls.append(("sha256_update", len(streams), None))
     for s, c in zip(streams, chunks):
         s.h.update(c)
-        s.data += bytes(c)
 
 
 def sha256_final_many(streams):

@@ -11,7 +11,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 def header_symbols():
-    text = (ROOT / "include" / "bci.h").read_text()
+    text = (ROOT / "include" / "bci.h").read_text() + (ROOT / "include" / "bci_broker.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return set(re.findall(r"\b(bci_[a-z0-9_]+)\s*\(", text))
 

@@ -24,15 +24,16 @@ def executor(dev):
 
 def test_metric_script_through_executor(executor, dev):
     n = 10_000_000
-    launches0 = dev.launch_count()
     res = asyncio.run(_many(executor, W.benchmark_numpy_source(n), 24))
     for r in res:
         assert r.exit_code == 0, r.stderr
         v = float(r.stdout.splitlines()[0].split()[1])
         assert abs(v / n - 1 / 3) < 6 * np.sqrt(4 / 45 / n)
-    # 24 requests x (rand + fused reduce) packed into fewer launches than requests x 2
-    assert 2 <= dev.launch_count() - launches0 <= 48
-    assert executor.broker.stats["max_batch"] >= 1
+    # the GPU work happened in the broker process (this process launched nothing for it)
+    from bee_code_interpreter_b200.broker_client import RemoteBackend
+
+    stats = RemoteBackend(executor.broker.socket_path).ping()["stats"]
+    assert stats["jobs"] >= 48 and stats["batches"] <= stats["jobs"]      # 24 x (rand + fused reduce)
 
 
 async def _many(ex, src, k):
