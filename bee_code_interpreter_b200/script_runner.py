@@ -15,7 +15,10 @@ import traceback
 
 import numpy  # noqa: F401  (preloaded in the zygote: forked children share these pages)
 
-from . import numpy_hook, numpy_proxy  # noqa: F401
+from . import broker_client, numpy_hook, numpy_proxy  # noqa: F401  (everything a request touches is imported HERE,
+#                                                                   in the zygote: a child must not pay imports)
+
+numpy_hook.numpy_view()  # build the agent-facing numpy view once; children inherit it
 
 
 def run_in_child(req: dict) -> int:
