@@ -98,9 +98,14 @@ sort_hist_kernel(const Req* __restrict__ reqs, const unsigned long long* __restr
   __syncthreads();
   const int lane = threadIdx.x & 31;
   if (m == kSortTile) {
-#pragma unroll 4
+    // all 16 loads are issued before the first shared atomic (ncu r1b: this kernel sat on
+    // long-scoreboard stalls at 22 % of HBM with the loads interleaved with the atomics)
+    K keys[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) keys[k] = src[k * kThreads + threadIdx.x];
+#pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
-      K key = src[k * kThreads + threadIdx.x];
+      K key = keys[k];
       if (first) key = to_key<K>(key, dtype);
       const uint32_t d = (uint32_t)(key >> shift) & 255u;
       // a constant digit (exponent byte of uniform floats) would serialise 32 same-address
@@ -170,7 +175,7 @@ sort_scan_kernel(const Req* __restrict__ reqs, uint32_t* __restrict__ hist, cons
 }
 
 template <typename K, bool PAIRS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 4 : 2)
 sort_scatter_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
                     int shift, int dtype, int first, int last, const uint32_t* __restrict__ hist) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
