@@ -60,6 +60,9 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
       ::bci::set_error("bci_init() has not been called (or failed)");      \
       return BCI_ERR_NOT_INIT;                                             \
     }                                                                      \
+    /* the CUDA current device is per THREAD: broker/service threads other \
+       than the one that called bci_init() start on device 0 */            \
+    (void)cudaSetDevice(::bci::ctx().device);                              \
   } while (0)
 
 #define BCI_CHECK_LAUNCH()                                                 \

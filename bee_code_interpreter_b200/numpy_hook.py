@@ -101,7 +101,9 @@ def _build_view():
                 return fallback()
             seed = int.from_bytes(os.urandom(8), "little")
             return P.device_rand(_backend(), tuple(int(s) for s in shape), seed)
-        except Exception:
+        except Exception as e:
+            if os.environ.get("BCI_DEBUG_FALLBACK"):
+                print(f"[bci] device rand fell back to numpy: {e!r}", file=sys.stderr)
             return fallback()
 
     def rand(*shape):

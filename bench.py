@@ -264,6 +264,9 @@ def measure_e2e(args, dist, rank, world, local, n):
         outs = [json.loads(p.stdout.readline()) for p in procs]
         for p in procs:
             p.wait(timeout=30)
+        from bee_code_interpreter_b200.broker_client import RemoteBackend
+
+        broker_stats = RemoteBackend(broker.socket_path).ping()["stats"]
     finally:
         for p in procs:
             if p.poll() is None:
@@ -283,6 +286,10 @@ def measure_e2e(args, dist, rank, world, local, n):
             "h2d_bytes_per_step": src_bytes * args.e2e_requests, "d2h_bytes_per_step": 8 * args.e2e_requests,
             "p50_latency_s": lat[len(lat) // 2] if lat else None,
             "parity_6sigma": all(o["parity"] for o in outs),
+            # every request must have reached the GPU (rand + fused reduce = 2 broker jobs): a
+            # script that silently fell back to host numpy would make this number meaningless
+            "broker_jobs": broker_stats["jobs"], "broker_launch_groups": broker_stats["batches"],
+            "all_requests_on_gpu": broker_stats["jobs"] >= 2 * sum(o["requests"] for o in outs),
             "api": "LocalGpuExecutor.execute(source_code, files, env)"}
 
 

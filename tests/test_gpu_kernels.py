@@ -400,3 +400,33 @@ def test_matmul_tcgen05_3xtf32_path(dev, bufs, shape, monkeypatch):
         assert np.abs(got - want).max() <= 2e-6 * scale, np.abs(got - want).max() / scale
         assert np.abs(simt - want).max() <= 1e-5 * scale
         assert np.abs(got - simt).max() <= 1e-5 * scale
+
+
+def test_api_from_worker_threads_on_a_nonzero_device(dev):
+    """The CUDA current device is per thread: broker/service threads must land on the device
+    bci_init() bound, not on device 0 (regression: rank 1 of a 2-GPU run failed every op)."""
+    import subprocess
+    import sys
+    import textwrap
+
+    if dev.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    code = textwrap.dedent('''
+        import sys, threading
+        import numpy as np
+        sys.path.insert(0, %r)
+        from bee_code_interpreter_b200 import _lib as L, device as dev
+        dev.init(1)
+        out = {}
+        def work():
+            p = dev.alloc(8 * 100000)
+            dev.rand_f64([p], [100000], [5])
+            out["s"] = float(dev.reduce(L.RED_SUM, np.float64, [p], [100000], pre=L.PRE_SQUARE)[0])
+            dev.free(p)
+        t = threading.Thread(target=work); t.start(); t.join()
+        assert dev.device_info()["device"] == 1
+        assert abs(out["s"] / 100000 - 1 / 3) < 0.01, out
+        print("ok")
+    ''') % str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
