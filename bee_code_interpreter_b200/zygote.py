@@ -103,6 +103,10 @@ class ZygoteClient:
         env = dict(os.environ)
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         env["PYTHONPATH"] = root + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
+        # no BLAS/OpenMP worker threads in the zygote: fork() must copy a single-threaded
+        # process, and a sandboxed request gets one host thread (heavy array work goes to the GPU)
+        for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+            env.setdefault(var, "1")
         self._proc = subprocess.Popen([sys.executable, "-m", "bee_code_interpreter_b200.zygote", self.socket_path],
                                       stdout=subprocess.PIPE, env=env, cwd=root)
         line = self._proc.stdout.readline()

@@ -242,7 +242,9 @@ def measure_e2e(args, dist, rank, world, local, n):
         from bee_code_interpreter_b200 import workloads as W
     except Exception as e:  # executor layer not importable: no end-to-end number
         return {"value": None, "unit": "requests/s", "error": repr(e)}
-    workers = max(1, args.e2e_workers)
+    # the host's fork/exit capacity (~4k processes/s on this 128-core box, tools/spawn_scale.py) is
+    # shared by all ranks: fewer service processes per GPU when several GPUs are driven at once
+    workers = max(1, args.e2e_workers if args.e2e_workers > 0 else (4 if world == 1 else 2))
     per_worker = [args.e2e_requests // workers + (1 if i < args.e2e_requests % workers else 0) for i in range(workers)]
     broker = BrokerProcess(device=local)
     procs = []
@@ -433,7 +435,7 @@ def main():
     ap.add_argument("--wave", type=int, default=64, help="requests resident on the GPU at once")
     ap.add_argument("--e2e-requests", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--e2e-inflight", type=int, default=32)
-    ap.add_argument("--e2e-workers", type=int, default=4, help="service processes per GPU in the e2e arm")
+    ap.add_argument("--e2e-workers", type=int, default=0, help="service processes per GPU in the e2e arm (0 = auto)")
     ap.add_argument("--e2e-zygotes", type=int, default=4, help="warm interpreters per service process")
     ap.add_argument("--e2e-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--broker-socket", default=None, help=argparse.SUPPRESS)
