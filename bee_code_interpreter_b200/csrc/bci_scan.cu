@@ -13,6 +13,7 @@
 #include "bci_ops.cuh"
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace bci {
 
@@ -189,8 +190,198 @@ scan_tile_apply(const Req* __restrict__ reqs, const unsigned long long* __restri
   }
 }
 
+// ---- single-pass form: chained scan with decoupled look-back (Merrill & Garland 2016) --------
+// One read + one write of the data (the 2 algorithmic passes).  A tile (32 KiB of input held in
+// registers) publishes its aggregate, warp 0 sums the aggregates of the preceding tiles of the
+// SAME request 32 at a time until it meets one whose inclusive prefix is known, then the tile
+// publishes its own inclusive prefix and writes its scanned values.  Flags and 64-bit values
+// live in separate arrays (value first, release-store of the flag after).  Tile indices come
+// from an atomic counter, so a tile only waits for tiles that already started.
+constexpr int kLbSub = 4;  // sub-tiles (256 x 256-bit) per tile
+template <typename T> constexpr size_t lb_tile_elems() { return (size_t)kThreads * kLbSub * (32 / sizeof(T)); }
+
+__device__ __forceinline__ uint32_t lb_ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void lb_st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
+                     uint32_t* __restrict__ flags, typename ScanTypes<T>::Acc* __restrict__ part,
+                     typename ScanTypes<T>::Acc* __restrict__ incl, uint32_t* __restrict__ counter) {
+  using A = typename ScanTypes<T>::Acc;
+  using O = typename ScanTypes<T>::Out;
+  constexpr int VN = 32 / sizeof(T);
+  constexpr int VO = 32 / sizeof(O);
+  constexpr int NST = VN / VO;
+  constexpr size_t TILE = (size_t)kThreads * kLbSub * VN;
+  __shared__ A warp_tot[kLbSub][kThreads / 32];
+  __shared__ A tile_excl;
+  __shared__ unsigned int tile_id;
+  if (threadIdx.x == 0) tile_id = atomicAdd(counter, 1u);
+  __syncthreads();
+  const unsigned long long tile = tile_id;
+  const int r = find_req(tile_start, B, tile);
+  const Req q = reqs[r];
+  const unsigned long long first_tile = q.tile_start;
+  const size_t base = (size_t)(tile - first_tile) * TILE;
+  const size_t rem = (size_t)q.n - base;
+  const T* __restrict__ a = reinterpret_cast<const T*>(q.in0) + base;
+  O* __restrict__ o = reinterpret_cast<O*>(q.out) + base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool fast = rem >= TILE && is_aligned32(a) && is_aligned32(o);
+
+  // ---- load the tile, thread-local inclusive scans, warp scans of the thread totals
+  A x[kLbSub][VN];
+  A lane_excl[kLbSub];
+#pragma unroll
+  for (int s = 0; s < kLbSub; ++s) {
+    const size_t e0 = ((size_t)s * kThreads + threadIdx.x) * VN;
+    if (fast) {
+      VecOf<T> v;
+      v.u = ldg256(a + e0);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) x[s][j] = (A)v.v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) x[s][j] = (e0 + j < rem) ? (A)a[e0 + j] : A(0);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kLbSub; ++s) {
+#pragma unroll
+    for (int j = 1; j < VN; ++j) x[s][j] = fadd_(x[s][j - 1], x[s][j]);
+    A inc = x[s][VN - 1];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const A y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc = fadd_(inc, y);
+    }
+    if (lane == 31) warp_tot[s][warp] = inc;
+    A ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = A(0);
+    lane_excl[s] = ex;
+  }
+  __syncthreads();
+  // ---- warp 0: tile aggregate, publish, look back
+  if (warp == 0) {
+    // 32 (sub-tile, warp) totals, one per lane, in element order
+    const A mine = warp_tot[lane / (kThreads / 32)][lane % (kThreads / 32)];
+    A agg = mine;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) agg = fadd_(agg, __shfl_xor_sync(0xffffffffu, agg, d));
+    const bool is_first = tile == first_tile;
+    if (lane == 0) {
+      if (is_first) {
+        incl[tile] = agg;
+        __threadfence();
+        lb_st_release(flags + tile, 2u);
+      } else {
+        part[tile] = agg;
+        __threadfence();
+        lb_st_release(flags + tile, 1u);
+      }
+    }
+    A excl = A(0);
+    if (!is_first) {
+      long long p = (long long)tile - 1;
+      for (;;) {
+        const long long idx = p - lane;
+        uint32_t f = 2u;
+        A v = A(0);
+        if (idx >= (long long)first_tile) {
+          f = lb_ld_acquire(flags + idx);
+          for (unsigned spins = 0; f == 0u; ++spins) {
+            if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
+            f = lb_ld_acquire(flags + idx);
+          }
+          v = f == 2u ? *reinterpret_cast<volatile A*>(incl + idx) : *reinterpret_cast<volatile A*>(part + idx);
+        }
+        const unsigned has_incl = __ballot_sync(0xffffffffu, f == 2u);
+        const int stop = has_incl ? (__ffs(has_incl) - 1) : 31;  // nearest tile whose prefix is complete
+        A contrib = lane <= stop ? v : A(0);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib = fadd_(contrib, __shfl_xor_sync(0xffffffffu, contrib, d));
+        excl = fadd_(excl, contrib);
+        if (has_incl) break;
+        p -= 32;
+      }
+      if (lane == 0) {
+        incl[tile] = fadd_(excl, agg);
+        __threadfence();
+        lb_st_release(flags + tile, 2u);
+      }
+    }
+    if (lane == 0) tile_excl = excl;
+  }
+  __syncthreads();
+  // ---- write: tile prefix + earlier (sub-tile, warp) totals + lane prefix + local scan
+  A carry = tile_excl;
+#pragma unroll
+  for (int s = 0; s < kLbSub; ++s) {
+    A wprefix = A(0), all = A(0);
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+      const A wt = warp_tot[s][w];
+      if (w < warp) wprefix = fadd_(wprefix, wt);
+      all = fadd_(all, wt);
+    }
+    const A off = fadd_(fadd_(carry, wprefix), lane_excl[s]);
+    const size_t e0 = ((size_t)s * kThreads + threadIdx.x) * VN;
+    if (fast) {
+#pragma unroll
+      for (int k = 0; k < NST; ++k) {
+        VecOf<O> vo;
+#pragma unroll
+        for (int j = 0; j < VO; ++j) vo.v[j] = (O)fadd_(off, x[s][k * VO + j]);
+        stg256(o + e0 + (size_t)k * VO, vo.u);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VN; ++j)
+        if (e0 + j < rem) o[e0 + j] = (O)fadd_(off, x[s][j]);
+    }
+    carry = fadd_(carry, all);
+  }
+}
+
+template <typename T>
+static int launch_cumsum_lookback(Req* reqs, int B) {
+  using A = typename ScanTypes<T>::Acc;
+  Ctx& c = ctx();
+  Batch bt;
+  int rc = upload_batch(reqs, B, lb_tile_elems<T>(), &bt);
+  if (rc != BCI_OK) return rc;
+  if (bt.total_tiles == 0) return BCI_OK;
+  if (bt.total_tiles > 0x7fffffffull) { set_error("bci_cumsum: batch too large for one launch"); return BCI_ERR_INVALID; }
+  // scratch: [counter (256 B)][flags T x u32][part T x A][incl T x A]
+  const size_t flag_bytes = (256 + bt.total_tiles * sizeof(uint32_t) + 255) & ~size_t(255);
+  void* sc = nullptr;
+  rc = scratch_get(flag_bytes + 2 * bt.total_tiles * sizeof(A), &sc);
+  if (rc != BCI_OK) return rc;
+  uint8_t* sb = reinterpret_cast<uint8_t*>(sc);
+  uint32_t* counter = reinterpret_cast<uint32_t*>(sb);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(sb + 256);
+  A* part = reinterpret_cast<A*>(sb + flag_bytes);
+  A* incl = part + bt.total_tiles;
+  BCI_CUDA(cudaMemsetAsync(sb, 0, flag_bytes, c.stream));
+  scan_lookback_kernel<T><<<(unsigned)bt.total_tiles, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, flags, part,
+                                                                              incl, counter);
+  BCI_CHECK_LAUNCH();
+  return BCI_OK;
+}
+
 template <typename T>
 static int launch_cumsum(Req* reqs, int B) {
+  {
+    const char* force = getenv("BCI_SCAN");
+    if (!(force && strcmp(force, "legacy") == 0)) return launch_cumsum_lookback<T>(reqs, B);
+  }
   using A = typename ScanTypes<T>::Acc;
   Ctx& c = ctx();
   Batch bt;

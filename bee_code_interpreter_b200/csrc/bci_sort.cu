@@ -19,61 +19,12 @@
 // HBM traffic: 3 key passes per digit pass (hist read + scatter read/write) where the
 // one-sweep/look-back form needs 2: algorithmic bytes are 9*n*4 for
 // float32, this implementation moves 12*n*4.  Bit-exact with numpy for all dtypes.
-#include "bci_common.cuh"
+#include "bci_sort_common.cuh"
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 
 namespace bci {
-
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kThreads * kSortItems;  // 4096 keys
-constexpr int kSortWarps = kThreads / 32;
-
-template <typename K> __device__ __forceinline__ K to_key(K bits, int dtype);
-template <> __device__ __forceinline__ uint32_t to_key<uint32_t>(uint32_t b, int dtype) {
-  if (dtype == BCI_F32) {
-    if ((b & 0x7fffffffu) > 0x7f800000u) return 0xffffffffu;  // NaN last
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-  }
-  return b ^ 0x80000000u;
-}
-template <> __device__ __forceinline__ unsigned long long to_key<unsigned long long>(unsigned long long b, int dtype) {
-  if (dtype == BCI_F64) {
-    if ((b & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) return ~0ull;
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-  }
-  return b ^ 0x8000000000000000ull;
-}
-template <typename K> __device__ __forceinline__ K from_key(K u, int dtype);
-template <> __device__ __forceinline__ uint32_t from_key<uint32_t>(uint32_t u, int dtype) {
-  if (dtype == BCI_F32) return (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
-  return u ^ 0x80000000u;
-}
-template <> __device__ __forceinline__ unsigned long long from_key<unsigned long long>(unsigned long long u, int dtype) {
-  if (dtype == BCI_F64) return (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
-  return u ^ 0x8000000000000000ull;
-}
-
-// Lanes of the warp holding the same digit as this lane (and the same validity).  Eight
-// ballots, one per digit bit, each folded in with a single LOP3 — the MATCH.ANY instruction
-// does the same job but measured ~400 cycles per warp (ncu, profiles/r1b), 10x this loop.
-// A row whose 32 digits are all equal (exponent byte of uniform floats) short-circuits.
-__device__ __forceinline__ unsigned match_digit(uint32_t d, bool valid, bool ragged_tile) {
-  unsigned peers = 0xffffffffu;
-  if (!__all_sync(0xffffffffu, d == __shfl_sync(0xffffffffu, d, 0))) {
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const unsigned m = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? m : ~m;
-    }
-  }
-  if (ragged_tile) {  // only the last tile of a request has lanes past the end
-    const unsigned v = __ballot_sync(0xffffffffu, valid);
-    peers &= valid ? v : ~v;
-  }
-  return peers;
-}
 
 // Req fields for the sort kernels:
 //   in0 = source keys, in1 = source indices (u32; nullptr on the first pass: generated),
@@ -380,6 +331,12 @@ static int sort_common(bool pairs, int dtype, int B, const void* const* in, void
     if (n[i] && (!in[i] || !out[i])) { set_error("bci_sort: NULL buffer in request %d", i); return BCI_ERR_INVALID; }
   Ctx& c = ctx();
   std::lock_guard<std::mutex> lk(c.mu);
+  // default: one-sweep passes with decoupled look-back (bci_sort_onesweep.cu); the
+  // reduce-then-scan passes below stay as the fallback for n >= 2^30 and for A/B runs
+  const char* force = getenv("BCI_SORT");
+  bool legacy = force && strcmp(force, "legacy") == 0;
+  for (int i = 0; i < B && !legacy; ++i) legacy = n[i] >= (1ull << 30);
+  if (!legacy) return sort_onesweep(pairs, dtype, B, in, out, n);
   const bool wide = elem_size(dtype) == 8;
   if (!pairs) return wide ? sort_run<unsigned long long, false>(dtype, B, in, out, n)
                           : sort_run<uint32_t, false>(dtype, B, in, out, n);

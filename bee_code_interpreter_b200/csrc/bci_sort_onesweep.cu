@@ -1,0 +1,357 @@
+// bci_sort_onesweep.cu — K5 radix sort, one-sweep form (Adinets & Merrill, "Onesweep: A Faster
+// Least Significant Digit Radix Sort for GPUs", 2022), segmented by request.
+//
+//   digit_hist_kernel : ONE read of the keys counts every 8-bit digit of every pass
+//                       (4 histograms for 32-bit keys, 8 for 64-bit) per request;
+//   digit_scan_kernel : exclusive scan over the 256 digits -> where each digit's run starts;
+//   onesweep_kernel   : per pass, a tile ranks its keys stably (8 ballots per 32-key row,
+//                       per-warp digit counters), publishes its 256 digit counts, and obtains
+//                       the counts of all earlier tiles of the SAME request by decoupled
+//                       look-back (status word = 2 flag bits + 30-bit count, one thread per
+//                       digit), then stages the tile in digit order in shared memory and writes
+//                       every digit run with coalesced stores.
+// HBM traffic = 1 + 2 per pass key sweeps: 9*n*4 bytes for float32 = the algorithmic figure of
+// SURVEY.md §8a K5 (the reduce-then-scan form in bci_sort.cu moves 12).  Tiles take their
+// index from an atomic counter, so a tile only ever waits for tiles that already started:
+// no deadlock; spins are bounded and trap instead of hanging the GPU.  Bit-exact with numpy.
+#include "bci_sort_common.cuh"
+#include <vector>
+#include <cstring>
+
+namespace bci {
+namespace {
+
+constexpr uint32_t kPartial = 1u << 30, kInclusive = 2u << 30, kFlagMask = 3u << 30, kValMask = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- all digit histograms in one read ---------------------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(kThreads)
+digit_hist_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
+                  unsigned long long total_tiles, int dtype, uint32_t* __restrict__ ghist) {
+  constexpr int P = (int)sizeof(K);
+  __shared__ uint32_t sh[P][256];
+  const unsigned long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+  const unsigned long long t0 = (unsigned long long)blockIdx.x * per;
+  const unsigned long long t1 = t0 + per < total_tiles ? t0 + per : total_tiles;
+  if (t0 >= t1) return;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int p = 0; p < P; ++p) sh[p][threadIdx.x] = 0;
+  __syncthreads();
+  int r = find_req(tile_start, B, t0);
+  auto flush = [&](int req) {
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const uint32_t v = sh[p][threadIdx.x];
+      if (v) atomicAdd(&ghist[((size_t)req * P + p) * 256 + threadIdx.x], v);
+      sh[p][threadIdx.x] = 0;
+    }
+    __syncthreads();
+  };
+  for (unsigned long long t = t0; t < t1; ++t) {
+    if (t >= __ldg(tile_start + r + 1)) {
+      flush(r);
+      while (t >= __ldg(tile_start + r + 1)) ++r;
+    }
+    const Req q = reqs[r];
+    const size_t base = (size_t)(t - q.tile_start) * kSortTile;
+    const size_t rem = (size_t)q.n - base;
+    const int m = rem < (size_t)kSortTile ? (int)rem : kSortTile;
+    const K* __restrict__ src = reinterpret_cast<const K*>(q.in0) + base;
+    if (m == kSortTile) {
+      K keys[kSortItems];
+#pragma unroll
+      for (int k = 0; k < kSortItems; ++k) keys[k] = src[k * kThreads + threadIdx.x];
+#pragma unroll
+      for (int k = 0; k < kSortItems; ++k) {
+        const K key = to_key<K>(keys[k], dtype);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const uint32_t d = (uint32_t)(key >> (8 * p)) & 255u;
+          // constant digits (exponent byte, high bytes of small integers) would serialise 32
+          // same-address shared atomics: one add per uniform row instead
+          if (__all_sync(0xffffffffu, d == __shfl_sync(0xffffffffu, d, 0))) {
+            if (lane == 0) atomicAdd(&sh[p][d], 32u);
+          } else {
+            atomicAdd(&sh[p][d], 1u);
+          }
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < m; i += kThreads) {
+        const K key = to_key<K>(src[i], dtype);
+#pragma unroll
+        for (int p = 0; p < P; ++p) atomicAdd(&sh[p][(uint32_t)(key >> (8 * p)) & 255u], 1u);
+      }
+    }
+  }
+  flush(r);
+}
+
+// one CTA per (request, pass): ghist[..][256] counts -> exclusive offsets, in place
+__global__ void __launch_bounds__(kThreads)
+digit_scan_kernel(uint32_t* __restrict__ ghist) {
+  __shared__ uint32_t wsum[kSortWarps];
+  uint32_t* h = ghist + (size_t)blockIdx.x * 256;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t c = h[threadIdx.x];
+  uint32_t inc = c;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, s);
+    if (lane >= s) inc += y;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  uint32_t wprefix = 0;
+  for (int w = 0; w < warp; ++w) wprefix += wsum[w];
+  h[threadIdx.x] = wprefix + inc - c;
+}
+
+// ---- one pass -----------------------------------------------------------------------------------
+// Req fields: in0 = source keys, in1 = source indices (u32; nullptr on the first pass: generated),
+// out = destination keys (nullptr when only indices leave the last pass), s0.i = destination
+// indices (u32*, or int64* on the last pass).
+template <typename K, bool PAIRS>
+__global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 4 : 2)
+onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
+                int pass, int dtype, int first, int last, const uint32_t* __restrict__ gbase,
+                uint32_t* __restrict__ status, uint32_t* __restrict__ counter) {
+  constexpr int P = (int)sizeof(K);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  K* skeys = reinterpret_cast<K*>(smem_raw);
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kSortTile);
+  uint32_t* warp_hist = sidx + (PAIRS ? kSortTile : 0);  // [kSortWarps][256]
+  uint32_t* digit_base = warp_hist + kSortWarps * 256;    // [256] tile-local exclusive digit offsets
+  uint32_t* goff = digit_base + 256;                      // [256] global offset - digit_base
+  uint32_t* wsum = goff + 256;                            // [kSortWarps] (+1: dynamic tile id)
+
+  // tiles are taken in the order CTAs start: whoever a tile waits for is already running
+  if (threadIdx.x == 0) wsum[kSortWarps] = atomicAdd(counter, 1u);
+  for (int i = threadIdx.x; i < kSortWarps * 256; i += kThreads) warp_hist[i] = 0;
+  __syncthreads();
+  const unsigned long long tile = wsum[kSortWarps];
+  const int r = find_req(tile_start, B, tile);
+  const Req q = reqs[r];
+  const unsigned long long tl = tile - q.tile_start;
+  const size_t base = (size_t)tl * kSortTile;
+  const size_t rem = (size_t)q.n - base;
+  const int m = rem < (size_t)kSortTile ? (int)rem : kSortTile;
+  const int shift = pass * 8;
+  const K* __restrict__ src = reinterpret_cast<const K*>(q.in0) + base;
+  const uint32_t* __restrict__ srci = q.in1 ? reinterpret_cast<const uint32_t*>(q.in1) + base : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  // this request's run start for digit d of this pass (independent load, issued early)
+  const uint32_t run_start = __ldg(gbase + ((size_t)r * P + pass) * 256 + threadIdx.x);
+
+  // striped arrangement: row k of warp w covers tile positions w*512 + k*32 + [0,32)
+  K key[kSortItems];
+  uint32_t idx[kSortItems];
+  uint32_t rank[kSortItems];
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const int p = warp * (32 * kSortItems) + k * 32 + lane;
+    K x = ~K(0);
+    if (p < m) {
+      x = src[p];
+      if (first) x = to_key<K>(x, dtype);
+    }
+    key[k] = x;
+    if (PAIRS) idx[k] = (p < m) ? (srci ? srci[p] : (uint32_t)(base + p)) : 0u;
+  }
+  uint32_t* wh = warp_hist + warp * 256;
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const int p = warp * (32 * kSortItems) + k * 32 + lane;
+    const bool valid = p < m;
+    const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
+    const unsigned peers = match_digit(d, valid, m != kSortTile);
+    const int leader = __ffs(peers) - 1;
+    uint32_t cnt = 0;
+    if (lane == leader && valid) {
+      cnt = wh[d];
+      wh[d] = cnt + (uint32_t)__popc(peers);
+    }
+    cnt = __shfl_sync(0xffffffffu, cnt, leader);
+    rank[k] = cnt + (uint32_t)__popc(peers & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+  // thread d owns digit d: counts over warps, publish, look back, tile-local digit offsets
+  {
+    const int d = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const uint32_t c = warp_hist[w * 256 + d];
+      warp_hist[w * 256 + d] = run;
+      run += c;
+    }
+    uint32_t* my_status = status + (size_t)tile * 256 + d;
+    st_release(my_status, (tl == 0 ? kInclusive : kPartial) | run);
+    uint32_t excl = 0;
+    if (tl > 0) {
+      const uint32_t* look = my_status - 256;
+      for (;;) {
+        uint32_t v = ld_acquire(look);
+        for (unsigned spins = 0; (v & kFlagMask) == 0; ++spins) {
+          if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
+          v = ld_acquire(look);
+        }
+        excl += v & kValMask;
+        if (v & kInclusive) break;
+        look -= 256;
+      }
+      st_release(my_status, kInclusive | (excl + run));
+    }
+    uint32_t inc = run;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, s);
+      if (lane >= s) inc += y;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wprefix = 0;
+    for (int w = 0; w < warp; ++w) wprefix += wsum[w];
+    const uint32_t local = wprefix + inc - run;
+    digit_base[d] = local;
+    goff[d] = run_start + excl - local;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const int p = warp * (32 * kSortItems) + k * 32 + lane;
+    if (p < m) {
+      const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
+      const uint32_t lp = digit_base[d] + wh[d] + rank[k];
+      skeys[lp] = key[k];
+      if (PAIRS) sidx[lp] = idx[k];
+    }
+  }
+  __syncthreads();
+  K* __restrict__ dst = reinterpret_cast<K*>(q.out);
+  for (int i = threadIdx.x; i < m; i += kThreads) {
+    const K x = skeys[i];
+    const uint32_t d = (uint32_t)(x >> shift) & 255u;
+    const size_t gp = (size_t)(uint32_t)(goff[d] + (uint32_t)i);
+    if (dst) dst[gp] = last ? from_key<K>(x, dtype) : x;
+    if (PAIRS) {
+      if (last) reinterpret_cast<long long*>(q.s0.i)[gp] = (long long)sidx[i];
+      else reinterpret_cast<uint32_t*>(q.s0.i)[gp] = sidx[i];
+    }
+  }
+}
+
+template <typename K, bool PAIRS>
+size_t onesweep_smem() {
+  return sizeof(K) * kSortTile + (PAIRS ? sizeof(uint32_t) * kSortTile : 0) +
+         sizeof(uint32_t) * (kSortWarps * 256 + 256 + 256 + kSortWarps + 1);
+}
+
+template <typename K, bool PAIRS>
+int onesweep_run(int dtype, int B, const void* const* in, void* const* out, const size_t* n) {
+  Ctx& c = ctx();
+  constexpr int P = (int)sizeof(K);
+  static bool attr_set = false;
+  if (!attr_set) {
+    BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)onesweep_smem<K, PAIRS>()));
+    attr_set = true;
+  }
+  size_t total_tiles = 0;
+  for (int i = 0; i < B; ++i) total_tiles += (n[i] + kSortTile - 1) / kSortTile;
+  if (total_tiles == 0) return BCI_OK;
+  if (total_tiles > 0x7fffffffull) { set_error("bci_sort: batch too large for one launch"); return BCI_ERR_INVALID; }
+  // scratch: [counters P][ghist B*P*256][status total_tiles*256] [per request: keysA (+keysB, idxA, idxB)]
+  const size_t hdr_words = 64 + (size_t)B * P * 256;
+  size_t bytes = (hdr_words + total_tiles * 256) * sizeof(uint32_t);
+  bytes = (bytes + 255) & ~size_t(255);
+  std::vector<size_t> koff((size_t)B);
+  for (int i = 0; i < B; ++i) {
+    koff[i] = bytes;
+    const size_t kb = (n[i] * sizeof(K) + 255) & ~size_t(255);
+    const size_t ib = (n[i] * sizeof(uint32_t) + 255) & ~size_t(255);
+    bytes += PAIRS ? 2 * kb + 2 * ib : kb;
+  }
+  void* sc = nullptr;
+  int rc = scratch_get(bytes, &sc);
+  if (rc != BCI_OK) return rc;
+  uint8_t* sbase = reinterpret_cast<uint8_t*>(sc);
+  uint32_t* counters = reinterpret_cast<uint32_t*>(sbase);
+  uint32_t* ghist = counters + 64;
+  uint32_t* status = reinterpret_cast<uint32_t*>(sbase) + hdr_words;
+  BCI_CUDA(cudaMemsetAsync(sbase, 0, hdr_words * sizeof(uint32_t), c.stream));
+
+  std::vector<Req> reqs((size_t)B);
+  // upfront histogram over the ORIGINAL keys
+  for (int i = 0; i < B; ++i) {
+    memset(&reqs[i], 0, sizeof(Req));
+    reqs[i].in0 = in[i];
+    reqs[i].n = n[i];
+  }
+  Batch bt;
+  rc = upload_batch(reqs.data(), B, kSortTile, &bt);
+  if (rc != BCI_OK) return rc;
+  {
+    const unsigned grid = (unsigned)(total_tiles < (size_t)c.sm_count * 8 ? total_tiles : (size_t)c.sm_count * 8);
+    digit_hist_kernel<K><<<grid, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, total_tiles, dtype, ghist);
+    BCI_CHECK_LAUNCH();
+    digit_scan_kernel<<<(unsigned)(B * P), kThreads, 0, c.stream>>>(ghist);
+    BCI_CHECK_LAUNCH();
+  }
+  for (int p = 0; p < P; ++p) {
+    const bool first = p == 0, last = p == P - 1;
+    for (int i = 0; i < B; ++i) {
+      Req& q = reqs[i];
+      memset(&q, 0, sizeof q);
+      const size_t kb = (n[i] * sizeof(K) + 255) & ~size_t(255);
+      const size_t ib = (n[i] * sizeof(uint32_t) + 255) & ~size_t(255);
+      uint8_t* keysA = sbase + koff[i];
+      q.n = n[i];
+      if (!PAIRS) {
+        // in -> A -> out -> A -> out ... (an even number of passes ends in out)
+        q.in0 = first ? in[i] : ((p & 1) ? (const void*)keysA : (const void*)out[i]);
+        q.out = (p & 1) ? out[i] : (void*)keysA;
+      } else {
+        uint8_t* keysB = keysA + kb;
+        uint8_t* idxA = keysB + kb;
+        uint8_t* idxB = idxA + ib;
+        q.in0 = first ? in[i] : ((p & 1) ? (const void*)keysA : (const void*)keysB);
+        q.in1 = first ? nullptr : ((p & 1) ? (const void*)idxA : (const void*)idxB);
+        q.out = last ? nullptr : ((p & 1) ? (void*)keysB : (void*)keysA);
+        q.s0.i = last ? (int64_t)(intptr_t)out[i] : (int64_t)(intptr_t)((p & 1) ? idxB : idxA);
+      }
+    }
+    rc = upload_batch(reqs.data(), B, kSortTile, &bt);
+    if (rc != BCI_OK) return rc;
+    BCI_CUDA(cudaMemsetAsync(status, 0, total_tiles * 256 * sizeof(uint32_t), c.stream));
+    onesweep_kernel<K, PAIRS><<<(unsigned)total_tiles, kThreads, onesweep_smem<K, PAIRS>(), c.stream>>>(
+        bt.d_reqs, bt.d_tile_start, B, p, dtype, first ? 1 : 0, last ? 1 : 0, ghist, status, counters + p);
+    BCI_CHECK_LAUNCH();
+  }
+  return BCI_OK;
+}
+
+}  // namespace
+
+int sort_onesweep(bool pairs, int dtype, int B, const void* const* in, void* const* out, const size_t* n) {
+  const bool wide = elem_size(dtype) == 8;
+  if (!pairs) return wide ? onesweep_run<unsigned long long, false>(dtype, B, in, out, n)
+                          : onesweep_run<uint32_t, false>(dtype, B, in, out, n);
+  return wide ? onesweep_run<unsigned long long, true>(dtype, B, in, out, n)
+              : onesweep_run<uint32_t, true>(dtype, B, in, out, n);
+}
+
+}  // namespace bci

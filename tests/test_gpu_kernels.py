@@ -430,3 +430,49 @@ def test_api_from_worker_threads_on_a_nonzero_device(dev):
     ''') % str(__import__("pathlib").Path(__file__).resolve().parents[1])
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_sort_and_cumsum_many_small_and_empty_requests(dev, bufs):
+    """Look-back chains must stop at request boundaries: thousands of short requests (some
+    empty, some exactly one tile, some a tile + 1) in one launch."""
+    rng = np.random.default_rng(71)
+    sizes = [0, 1, 2, 31, 32, 33, 4095, 4096, 4097, 8192, 12289] + [int(s) for s in rng.integers(0, 3000, 1500)]
+    xs = [rng.integers(-10**6, 10**6, n, dtype=np.int64) for n in sizes]
+    fs = [rng.standard_normal(n).astype(np.float32) for n in sizes]
+    px = [bufs.up(x) for x in xs]
+    pf = [bufs.up(f) for f in fs]
+    po = [bufs.new(max(x.nbytes, 8)) for x in xs]
+    pfo = [bufs.new(max(f.nbytes, 8)) for f in fs]
+    dev.cumsum(np.int64, px, po, sizes)
+    dev.sort(np.float32, pf, pfo, sizes)
+    for x, p, f, q in zip(xs, po, fs, pfo):
+        assert np.array_equal(dev.download(p, x.size, np.int64), np.cumsum(x))
+        assert np.array_equal(dev.download(q, f.size, np.float32), np.sort(f))
+    pi = [bufs.new(max(x.size * 8, 8)) for x in xs]
+    dev.argsort(np.int64, px, pi, sizes)
+    dev.sort(np.int64, px, po, sizes)
+    for x, p, q in zip(xs, pi, po):
+        assert np.array_equal(dev.download(p, x.size, np.int64), np.argsort(x, kind="stable"))
+        assert np.array_equal(dev.download(q, x.size, np.int64), np.sort(x))
+
+
+@pytest.mark.parametrize("which", ["sort", "scan"])
+def test_single_pass_forms_agree_with_the_multi_pass_fallbacks(dev, bufs, which, monkeypatch):
+    """BCI_SORT=legacy / BCI_SCAN=legacy select the reduce-then-scan kernels: same bits."""
+    rng = np.random.default_rng(72)
+    n = 3_000_017
+    if which == "sort":
+        x = rng.standard_normal(n).astype(np.float32)
+        p, a, b = bufs.up(x), bufs.new(x.nbytes), bufs.new(x.nbytes)
+        dev.sort(np.float32, [p], [a], [n])
+        monkeypatch.setenv("BCI_SORT", "legacy")
+        dev.sort(np.float32, [p], [b], [n])
+        assert np.array_equal(dev.download(a, n, np.float32), dev.download(b, n, np.float32))
+    else:
+        x = rng.standard_normal(n)
+        p, a, b = bufs.up(x), bufs.new(x.nbytes), bufs.new(x.nbytes)
+        dev.cumsum(np.float64, [p], [a], [n])
+        monkeypatch.setenv("BCI_SCAN", "legacy")
+        dev.cumsum(np.float64, [p], [b], [n])
+        ga, gb = dev.download(a, n, np.float64), dev.download(b, n, np.float64)
+        assert np.allclose(ga, gb, rtol=1e-12, atol=1e-9) and np.allclose(ga, np.cumsum(x), rtol=1e-12, atol=1e-9)
