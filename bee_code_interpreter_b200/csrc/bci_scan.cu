@@ -200,20 +200,32 @@ scan_tile_apply(const Req* __restrict__ reqs, const unsigned long long* __restri
 constexpr int kLbSub = 4;  // sub-tiles (256 x 256-bit) per tile
 template <typename T> constexpr size_t lb_tile_elems() { return (size_t)kThreads * kLbSub * (32 / sizeof(T)); }
 
-__device__ __forceinline__ uint32_t lb_ld_acquire(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// One 16-byte status entry per tile = {flag (0 none, 1 aggregate, 2 inclusive prefix), value
+// bits}, read and written as ONE 128-bit cache-global transaction, so flag and value can never
+// be seen torn and no fence / L1 invalidation (ld.acquire = CCTL.IVALL + LD) is needed.
+__device__ __forceinline__ ulonglong2 lb_load(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void lb_st_release(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void lb_store(ulonglong2* p, unsigned long long flag, unsigned long long bits) {
+  asm volatile("st.global.cg.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(flag), "l"(bits) : "memory");
+}
+template <typename A> __device__ __forceinline__ unsigned long long lb_bits(A v) {
+  unsigned long long b;
+  memcpy(&b, &v, 8);
+  return b;
+}
+template <typename A> __device__ __forceinline__ A lb_value(unsigned long long b) {
+  A v;
+  memcpy(&v, &b, 8);
+  return v;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
-                     uint32_t* __restrict__ flags, typename ScanTypes<T>::Acc* __restrict__ part,
-                     typename ScanTypes<T>::Acc* __restrict__ incl, uint32_t* __restrict__ counter) {
+                     ulonglong2* __restrict__ st, uint32_t* __restrict__ counter) {
   using A = typename ScanTypes<T>::Acc;
   using O = typename ScanTypes<T>::Out;
   constexpr int VN = 32 / sizeof(T);
@@ -276,33 +288,24 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) agg = fadd_(agg, __shfl_xor_sync(0xffffffffu, agg, d));
     const bool is_first = tile == first_tile;
-    if (lane == 0) {
-      if (is_first) {
-        incl[tile] = agg;
-        __threadfence();
-        lb_st_release(flags + tile, 2u);
-      } else {
-        part[tile] = agg;
-        __threadfence();
-        lb_st_release(flags + tile, 1u);
-      }
-    }
+    if (lane == 0) lb_store(st + tile, is_first ? 2ull : 1ull, lb_bits<A>(agg));
     A excl = A(0);
     if (!is_first) {
       long long p = (long long)tile - 1;
       for (;;) {
         const long long idx = p - lane;
-        uint32_t f = 2u;
+        unsigned long long f = 2ull;
         A v = A(0);
         if (idx >= (long long)first_tile) {
-          f = lb_ld_acquire(flags + idx);
-          for (unsigned spins = 0; f == 0u; ++spins) {
+          ulonglong2 e = lb_load(st + idx);
+          for (unsigned spins = 0; e.x == 0ull; ++spins) {
             if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
-            f = lb_ld_acquire(flags + idx);
+            e = lb_load(st + idx);
           }
-          v = f == 2u ? *reinterpret_cast<volatile A*>(incl + idx) : *reinterpret_cast<volatile A*>(part + idx);
+          f = e.x;
+          v = lb_value<A>(e.y);
         }
-        const unsigned has_incl = __ballot_sync(0xffffffffu, f == 2u);
+        const unsigned has_incl = __ballot_sync(0xffffffffu, f == 2ull);
         const int stop = has_incl ? (__ffs(has_incl) - 1) : 31;  // nearest tile whose prefix is complete
         A contrib = lane <= stop ? v : A(0);
 #pragma unroll
@@ -311,11 +314,7 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
         if (has_incl) break;
         p -= 32;
       }
-      if (lane == 0) {
-        incl[tile] = fadd_(excl, agg);
-        __threadfence();
-        lb_st_release(flags + tile, 2u);
-      }
+      if (lane == 0) lb_store(st + tile, 2ull, lb_bits<A>(fadd_(excl, agg)));
     }
     if (lane == 0) tile_excl = excl;
   }
@@ -352,26 +351,22 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
 
 template <typename T>
 static int launch_cumsum_lookback(Req* reqs, int B) {
-  using A = typename ScanTypes<T>::Acc;
   Ctx& c = ctx();
   Batch bt;
   int rc = upload_batch(reqs, B, lb_tile_elems<T>(), &bt);
   if (rc != BCI_OK) return rc;
   if (bt.total_tiles == 0) return BCI_OK;
   if (bt.total_tiles > 0x7fffffffull) { set_error("bci_cumsum: batch too large for one launch"); return BCI_ERR_INVALID; }
-  // scratch: [counter (256 B)][flags T x u32][part T x A][incl T x A]
-  const size_t flag_bytes = (256 + bt.total_tiles * sizeof(uint32_t) + 255) & ~size_t(255);
+  // scratch: [counter (256 B)][status T x 16 B]
+  const size_t bytes = 256 + bt.total_tiles * sizeof(ulonglong2);
   void* sc = nullptr;
-  rc = scratch_get(flag_bytes + 2 * bt.total_tiles * sizeof(A), &sc);
+  rc = scratch_get(bytes, &sc);
   if (rc != BCI_OK) return rc;
   uint8_t* sb = reinterpret_cast<uint8_t*>(sc);
   uint32_t* counter = reinterpret_cast<uint32_t*>(sb);
-  uint32_t* flags = reinterpret_cast<uint32_t*>(sb + 256);
-  A* part = reinterpret_cast<A*>(sb + flag_bytes);
-  A* incl = part + bt.total_tiles;
-  BCI_CUDA(cudaMemsetAsync(sb, 0, flag_bytes, c.stream));
-  scan_lookback_kernel<T><<<(unsigned)bt.total_tiles, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, flags, part,
-                                                                              incl, counter);
+  ulonglong2* st = reinterpret_cast<ulonglong2*>(sb + 256);
+  BCI_CUDA(cudaMemsetAsync(sb, 0, bytes, c.stream));
+  scan_lookback_kernel<T><<<(unsigned)bt.total_tiles, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, st, counter);
   BCI_CHECK_LAUNCH();
   return BCI_OK;
 }

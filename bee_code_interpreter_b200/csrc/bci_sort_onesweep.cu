@@ -23,13 +23,16 @@ namespace {
 
 constexpr uint32_t kPartial = 1u << 30, kInclusive = 2u << 30, kFlagMask = 3u << 30, kValMask = (1u << 30) - 1u;
 
-__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+// A status word carries its own payload (flag bits + count), so no ordering against other
+// memory is needed: cache-global relaxed accesses.  (ld.acquire.gpu compiles to CCTL.IVALL + LD
+// and cost 20 % of the kernel's stall samples in the first version, ncu r1c.)
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---- all digit histograms in one read ---------------------------------------------------------
@@ -159,24 +162,60 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   K key[kSortItems];
   uint32_t idx[kSortItems];
   uint32_t rank[kSortItems];
+  // every load of the tile is issued before anything consumes one (ncu r1c: with the key
+  // transform inside the load loop each of the 16 loads exposed its full latency)
+  const int p0 = warp * (32 * kSortItems) + lane;
+  if (m == kSortTile) {
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) key[k] = src[p0 + k * 32];
+    if (PAIRS && srci) {
+#pragma unroll
+      for (int k = 0; k < kSortItems; ++k) idx[k] = srci[p0 + k * 32];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) key[k] = (p0 + k * 32 < m) ? src[p0 + k * 32] : K(0);
+    if (PAIRS && srci) {
+#pragma unroll
+      for (int k = 0; k < kSortItems; ++k) idx[k] = (p0 + k * 32 < m) ? srci[p0 + k * 32] : 0u;
+    }
+  }
+  if (PAIRS && !srci) {
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) idx[k] = (uint32_t)(base + p0 + k * 32);
+  }
 #pragma unroll
   for (int k = 0; k < kSortItems; ++k) {
-    const int p = warp * (32 * kSortItems) + k * 32 + lane;
-    K x = ~K(0);
-    if (p < m) {
-      x = src[p];
-      if (first) x = to_key<K>(x, dtype);
-    }
-    key[k] = x;
-    if (PAIRS) idx[k] = (p < m) ? (srci ? srci[p] : (uint32_t)(base + p)) : 0u;
+    K x = key[k];
+    if (first) x = to_key<K>(x, dtype);
+    key[k] = (p0 + k * 32 < m) ? x : ~K(0);
   }
   uint32_t* wh = warp_hist + warp * 256;
+  // (1) peer masks of all 16 rows first: 16 independent chains of 9 ballots that the scheduler
+  //     can interleave (a per-row loop with the counter update inside serialises them);
+  //     rank[] holds the mask until step (2) replaces it with the rank
 #pragma unroll
   for (int k = 0; k < kSortItems; ++k) {
     const int p = warp * (32 * kSortItems) + k * 32 + lane;
     const bool valid = p < m;
     const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-    const unsigned peers = match_digit(d, valid, m != kSortTile);
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+    peers = valid ? peers : ~peers;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned mb = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? mb : ~mb;
+    }
+    rank[k] = peers;
+  }
+  // (2) rows in order: the lowest peer lane adds the row's count to the warp's digit counter
+#pragma unroll
+  for (int k = 0; k < kSortItems; ++k) {
+    const int p = warp * (32 * kSortItems) + k * 32 + lane;
+    const bool valid = p < m;
+    const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
+    const unsigned peers = rank[k];
     const int leader = __ffs(peers) - 1;
     uint32_t cnt = 0;
     if (lane == leader && valid) {
@@ -199,21 +238,33 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
       run += c;
     }
     uint32_t* my_status = status + (size_t)tile * 256 + d;
-    st_release(my_status, (tl == 0 ? kInclusive : kPartial) | run);
+    st_status(my_status, (tl == 0 ? kInclusive : kPartial) | run);
     uint32_t excl = 0;
     if (tl > 0) {
-      const uint32_t* look = my_status - 256;
-      for (;;) {
-        uint32_t v = ld_acquire(look);
-        for (unsigned spins = 0; (v & kFlagMask) == 0; ++spins) {
-          if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
-          v = ld_acquire(look);
+      // walk back over the earlier tiles of this request, 4 status words per round trip
+      // (speculative: words beyond the first INCLUSIVE one are simply ignored)
+      long long back = 1;                       // distance of the next tile to read
+      const long long max_back = (long long)tl;  // tile tl-... down to the request's first tile
+      bool done = false;
+      while (!done) {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          v[j] = (back + j <= max_back) ? ld_status(my_status - (back + j) * 256) : kInclusive;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (done) break;
+          uint32_t x = v[j];
+          for (unsigned spins = 0; (x & kFlagMask) == 0; ++spins) {
+            if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
+            x = ld_status(my_status - (back + j) * 256);
+          }
+          excl += x & kValMask;
+          if (x & kInclusive) done = true;
         }
-        excl += v & kValMask;
-        if (v & kInclusive) break;
-        look -= 256;
+        back += 4;
       }
-      st_release(my_status, kInclusive | (excl + run));
+      st_status(my_status, kInclusive | (excl + run));
     }
     uint32_t inc = run;
 #pragma unroll
