@@ -141,6 +141,23 @@ __device__ __forceinline__ int find_req(const unsigned long long* __restrict__ t
   return lo;
 }
 
+// Same result, found by the whole CTA in ONE memory round trip per 256 requests (each thread
+// tests one boundary, the block counts the hits) instead of ~log2(B) dependent loads — for
+// kernels whose tiles are short enough that the start-up chain shows (look-back kernels).
+// Must be called by every thread of the CTA.
+__device__ __forceinline__ int find_req_block(const unsigned long long* __restrict__ tile_start,
+                                              int B, unsigned long long tile) {
+  if (B == 1) return 0;
+  int cnt = 0;  // boundaries tile_start[1..B-1] that are <= tile
+  for (int i0 = 1; i0 < B; i0 += (int)blockDim.x) {
+    const int i = i0 + (int)threadIdx.x;
+    const bool le = i < B && __ldg(tile_start + i) <= tile;
+    cnt += __syncthreads_count(le);
+    if (cnt < i0 + (int)blockDim.x - 1) break;  // sorted boundaries: the rest are larger
+  }
+  return cnt;
+}
+
 __device__ __forceinline__ bool is_aligned32(const void* p) {
   return (reinterpret_cast<uintptr_t>(p) & 31) == 0;
 }

@@ -197,8 +197,10 @@ scan_tile_apply(const Req* __restrict__ reqs, const unsigned long long* __restri
 // publishes its own inclusive prefix and writes its scanned values.  Flags and 64-bit values
 // live in separate arrays (value first, release-store of the flag after).  Tile indices come
 // from an atomic counter, so a tile only waits for tiles that already started.
-constexpr int kLbSub = 4;  // sub-tiles (256 x 256-bit) per tile
-template <typename T> constexpr size_t lb_tile_elems() { return (size_t)kThreads * kLbSub * (32 / sizeof(T)); }
+// sub-tiles (256 threads x one 256-bit vector) per tile: every thread holds 32 elements, i.e.
+// 32 KiB tiles for 4-byte inputs and 64 KiB tiles for 8-byte inputs
+template <typename T> constexpr int lb_sub() { return 32 / (32 / (int)sizeof(T)); }
+template <typename T> constexpr size_t lb_tile_elems() { return (size_t)kThreads * lb_sub<T>() * (32 / sizeof(T)); }
 
 // One 16-byte status entry per tile = {flag (0 none, 1 aggregate, 2 inclusive prefix), value
 // bits}, read and written as ONE 128-bit cache-global transaction, so flag and value can never
@@ -231,6 +233,7 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
   constexpr int VN = 32 / sizeof(T);
   constexpr int VO = 32 / sizeof(O);
   constexpr int NST = VN / VO;
+  constexpr int kLbSub = 32 / (32 / (int)sizeof(T));
   constexpr size_t TILE = (size_t)kThreads * kLbSub * VN;
   __shared__ A warp_tot[kLbSub][kThreads / 32];
   __shared__ A tile_excl;
@@ -238,7 +241,7 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
   if (threadIdx.x == 0) tile_id = atomicAdd(counter, 1u);
   __syncthreads();
   const unsigned long long tile = tile_id;
-  const int r = find_req(tile_start, B, tile);
+  const int r = find_req_block(tile_start, B, tile);
   const Req q = reqs[r];
   const unsigned long long first_tile = q.tile_start;
   const size_t base = (size_t)(tile - first_tile) * TILE;
@@ -282,9 +285,11 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
   __syncthreads();
   // ---- warp 0: tile aggregate, publish, look back
   if (warp == 0) {
-    // 32 (sub-tile, warp) totals, one per lane, in element order
-    const A mine = warp_tot[lane / (kThreads / 32)][lane % (kThreads / 32)];
-    A agg = mine;
+    // the (sub-tile, warp) totals, one or two per lane
+    A agg = A(0);
+#pragma unroll
+    for (int e = 0; e < kLbSub * (kThreads / 32); e += 32)
+      agg = fadd_(agg, warp_tot[(e + lane) / (kThreads / 32)][(e + lane) % (kThreads / 32)]);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) agg = fadd_(agg, __shfl_xor_sync(0xffffffffu, agg, d));
     const bool is_first = tile == first_tile;

@@ -144,7 +144,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   for (int i = threadIdx.x; i < kSortWarps * 256; i += kThreads) warp_hist[i] = 0;
   __syncthreads();
   const unsigned long long tile = wsum[kSortWarps];
-  const int r = find_req(tile_start, B, tile);
+  const int r = find_req_block(tile_start, B, tile);
   const Req q = reqs[r];
   const unsigned long long tl = tile - q.tile_start;
   const size_t base = (size_t)tl * kSortTile;
