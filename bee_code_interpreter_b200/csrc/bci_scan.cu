@@ -199,7 +199,7 @@ scan_tile_apply(const Req* __restrict__ reqs, const unsigned long long* __restri
 // from an atomic counter, so a tile only waits for tiles that already started.
 // sub-tiles (256 threads x one 256-bit vector) per tile: every thread holds 32 elements, i.e.
 // 32 KiB tiles for 4-byte inputs and 64 KiB tiles for 8-byte inputs
-template <typename T> constexpr int lb_sub() { return 32 / (32 / (int)sizeof(T)); }
+template <typename T> constexpr int lb_sub() { return 4; }
 template <typename T> constexpr size_t lb_tile_elems() { return (size_t)kThreads * lb_sub<T>() * (32 / sizeof(T)); }
 
 // One 16-byte status entry per tile = {flag (0 none, 1 aggregate, 2 inclusive prefix), value
@@ -233,7 +233,7 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
   constexpr int VN = 32 / sizeof(T);
   constexpr int VO = 32 / sizeof(O);
   constexpr int NST = VN / VO;
-  constexpr int kLbSub = 32 / (32 / (int)sizeof(T));
+  constexpr int kLbSub = 4;
   constexpr size_t TILE = (size_t)kThreads * kLbSub * VN;
   __shared__ A warp_tot[kLbSub][kThreads / 32];
   __shared__ A tile_excl;
@@ -254,15 +254,21 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
   // ---- load the tile, thread-local inclusive scans, warp scans of the thread totals
   A x[kLbSub][VN];
   A lane_excl[kLbSub];
+  if (fast) {
+    // all loads first, conversions after: a branch or a convert between the loads makes every
+    // one of them expose its full latency (ncu r1d: 13 k long-scoreboard samples on this loop)
+    VecOf<T> v[kLbSub];
 #pragma unroll
-  for (int s = 0; s < kLbSub; ++s) {
-    const size_t e0 = ((size_t)s * kThreads + threadIdx.x) * VN;
-    if (fast) {
-      VecOf<T> v;
-      v.u = ldg256(a + e0);
+    for (int s = 0; s < kLbSub; ++s) v[s].u = ldg256(a + ((size_t)s * kThreads + threadIdx.x) * VN);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) x[s][j] = (A)v.v[j];
-    } else {
+    for (int s = 0; s < kLbSub; ++s) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) x[s][j] = (A)v[s].v[j];
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < kLbSub; ++s) {
+      const size_t e0 = ((size_t)s * kThreads + threadIdx.x) * VN;
 #pragma unroll
       for (int j = 0; j < VN; ++j) x[s][j] = (e0 + j < rem) ? (A)a[e0 + j] : A(0);
     }
