@@ -385,8 +385,12 @@ static int launch_cumsum_lookback(Req* reqs, int B) {
 template <typename T>
 static int launch_cumsum(Req* reqs, int B) {
   {
+    // Measured on B200 (profiles/r1_kernel_table.md): the 3-pass form below runs at 6.6 TB/s of
+    // traffic (0.67 of the algorithmic roofline), the single-pass look-back form at 3.9 TB/s
+    // (0.59): one-tile-per-CTA look-back is latency-bound at 2-4 CTAs/SM.  The faster one is the
+    // default; BCI_SCAN=lookback selects the single-pass kernel (kept for the pipelined rewrite).
     const char* force = getenv("BCI_SCAN");
-    if (!(force && strcmp(force, "legacy") == 0)) return launch_cumsum_lookback<T>(reqs, B);
+    if (force && strcmp(force, "lookback") == 0) return launch_cumsum_lookback<T>(reqs, B);
   }
   using A = typename ScanTypes<T>::Acc;
   Ctx& c = ctx();

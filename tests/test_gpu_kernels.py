@@ -432,7 +432,7 @@ def test_api_from_worker_threads_on_a_nonzero_device(dev):
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
 
-def test_sort_and_cumsum_many_small_and_empty_requests(dev, bufs):
+def test_sort_and_cumsum_many_small_and_empty_requests(dev, bufs, monkeypatch):
     """Look-back chains must stop at request boundaries: thousands of short requests (some
     empty, some exactly one tile, some a tile + 1) in one launch."""
     rng = np.random.default_rng(71)
@@ -448,6 +448,11 @@ def test_sort_and_cumsum_many_small_and_empty_requests(dev, bufs):
     for x, p, f, q in zip(xs, po, fs, pfo):
         assert np.array_equal(dev.download(p, x.size, np.int64), np.cumsum(x))
         assert np.array_equal(dev.download(q, f.size, np.float32), np.sort(f))
+    monkeypatch.setenv("BCI_SCAN", "lookback")          # single-pass kernel: chains stop at request starts
+    dev.cumsum(np.int64, px, po, sizes)
+    monkeypatch.delenv("BCI_SCAN")
+    for x, p in zip(xs, po):
+        assert np.array_equal(dev.download(p, x.size, np.int64), np.cumsum(x))
     pi = [bufs.new(max(x.size * 8, 8)) for x in xs]
     dev.argsort(np.int64, px, pi, sizes)
     dev.sort(np.int64, px, po, sizes)
@@ -472,7 +477,11 @@ def test_single_pass_forms_agree_with_the_multi_pass_fallbacks(dev, bufs, which,
         x = rng.standard_normal(n)
         p, a, b = bufs.up(x), bufs.new(x.nbytes), bufs.new(x.nbytes)
         dev.cumsum(np.float64, [p], [a], [n])
-        monkeypatch.setenv("BCI_SCAN", "legacy")
+        monkeypatch.setenv("BCI_SCAN", "lookback")
         dev.cumsum(np.float64, [p], [b], [n])
+        ki = rng.integers(-2**40, 2**40, n, dtype=np.int64)        # integers: the two forms are bit-identical
+        pi, ci = bufs.up(ki), bufs.new(ki.nbytes)
+        dev.cumsum(np.int64, [pi], [ci], [n])
+        assert np.array_equal(dev.download(ci, n, np.int64), np.cumsum(ki))
         ga, gb = dev.download(a, n, np.float64), dev.download(b, n, np.float64)
         assert np.allclose(ga, gb, rtol=1e-12, atol=1e-9) and np.allclose(ga, np.cumsum(x), rtol=1e-12, atol=1e-9)
