@@ -15,9 +15,12 @@
 //        warp 0  (1 thread) TMA producer: 4 x cp.async.bulk.tensor (A_hi, A_lo, Bt_hi, Bt_lo
 //                 tiles of 128 rows x 128 B, SWIZZLE_128B) per stage, mbarrier complete_tx;
 //        warp 1  (1 thread) MMA issuer: 12 x tcgen05.mma.cta_group::1.kind::tf32 per stage
-//                 (3 products x 4 K-steps of 8), accumulator = 128 lanes x 128 columns of TMEM,
-//                 tcgen05.commit releases the stage / signals the epilogue;
-//        warps 2-5 epilogue: tcgen05.ld 32x32b.x32 -> registers -> 128-bit global stores.
+//                 (3 products x 4 K-steps of 8) into one of TWO 128-column TMEM accumulators;
+//                 tcgen05.commit releases the stage and, every 4 k-blocks, hands the
+//                 accumulator to the epilogue;
+//        warps 2-5 epilogue: per chunk tcgen05.ld 32x32b.x32 -> fp32 REGISTER accumulators
+//                 (round-to-nearest adds: the tensor core truncates when it accumulates, and
+//                 1536 dependent adds at K=4096 cost 3e-5 of max|C|), 128-bit stores at the end.
 //      Tensor maps are 3-D (k, row, request) over the split planes, which this file lays
 //      out itself, so ONE launch covers every request of the slice (grid.z = request).
 // Tensor-pipe bound in principle (137.4 GFLOP algorithmic per 4096^3 request, x3 issued);

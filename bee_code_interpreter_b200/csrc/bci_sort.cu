@@ -7,13 +7,14 @@
 //           becomes the all-ones key, so NaNs sort last like numpy (their payload is
 //           canonicalised to +qNaN; -0.0 sorts before +0.0, value-equal to numpy);
 //   int   : flip the sign bit.
+// This file: the dispatcher and the multi-pass fallback (BCI_SORT=legacy, or n >= 2^30); the
+// default is the one-sweep form in bci_sort_onesweep.cu.
 // Per pass (reduce-then-scan, no inter-CTA waiting):
-//   hist    : one CTA per 4096-key tile counts its 256 digits (warp-aggregated with
-//             MATCH.ANY so a constant digit — the exponent byte of uniform floats — does
-//             not serialise the shared-memory atomics) -> hist[req][digit][tile], totals
+//   hist    : one CTA per 4096-key tile counts its 256 digits (uniform rows — the exponent
+//             byte of uniform floats — collapse to one shared atomic) -> hist[req][digit][tile]
 //   scan    : one CTA per (request, digit): exclusive scan over that digit's tiles, based
 //             at the sum of the lower digits' totals -> global offsets, in place
-//   scatter : ranks keys stably inside the tile (MATCH.ANY per 32-key row, per-warp digit
+//   scatter : ranks keys stably inside the tile (8 ballots per 32-key row, per-warp digit
 //             counters), stages the tile in digit order in shared memory and writes each
 //             digit run to its global offset with coalesced stores.
 // HBM traffic: 3 key passes per digit pass (hist read + scatter read/write) where the

@@ -17,6 +17,7 @@
 #include "bci_sort_common.cuh"
 #include <vector>
 #include <cstring>
+#include <type_traits>
 
 namespace bci {
 namespace {
@@ -125,18 +126,20 @@ digit_scan_kernel(uint32_t* __restrict__ ghist) {
 // Req fields: in0 = source keys, in1 = source indices (u32; nullptr on the first pass: generated),
 // out = destination keys (nullptr when only indices leave the last pass), s0.i = destination
 // indices (u32*, or int64* on the last pass).
-template <typename K, bool PAIRS>
-__global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 4 : 2)
+// FIRST / LAST pass and full / ragged tile are compile-time: the first version carried them as
+// runtime flags and spent 40 of its 145 instructions per key on predicates and branches (ncu r1c).
+template <typename K, bool PAIRS, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 3 : 2)
 onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
-                int pass, int dtype, int first, int last, const uint32_t* __restrict__ gbase,
+                int pass, int dtype, const uint32_t* __restrict__ gbase,
                 uint32_t* __restrict__ status, uint32_t* __restrict__ counter) {
   constexpr int P = (int)sizeof(K);
+  constexpr bool WRITE_KEYS = !(PAIRS && LAST);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K* skeys = reinterpret_cast<K*>(smem_raw);
   uint32_t* sidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kSortTile);
   uint32_t* warp_hist = sidx + (PAIRS ? kSortTile : 0);  // [kSortWarps][256]
-  uint32_t* digit_base = warp_hist + kSortWarps * 256;    // [256] tile-local exclusive digit offsets
-  uint32_t* goff = digit_base + 256;                      // [256] global offset - digit_base
+  uint32_t* goff = warp_hist + kSortWarps * 256;          // [256] global offset - tile-local offset
   uint32_t* wsum = goff + 256;                            // [kSortWarps] (+1: dynamic tile id)
 
   // tiles are taken in the order CTAs start: whoever a tile waits for is already running
@@ -152,163 +155,160 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   const int m = rem < (size_t)kSortTile ? (int)rem : kSortTile;
   const int shift = pass * 8;
   const K* __restrict__ src = reinterpret_cast<const K*>(q.in0) + base;
-  const uint32_t* __restrict__ srci = q.in1 ? reinterpret_cast<const uint32_t*>(q.in1) + base : nullptr;
+  const uint32_t* __restrict__ srci = reinterpret_cast<const uint32_t*>(q.in1) + base;  // !FIRST only
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   // this request's run start for digit d of this pass (independent load, issued early)
   const uint32_t run_start = __ldg(gbase + ((size_t)r * P + pass) * 256 + threadIdx.x);
-
-  // striped arrangement: row k of warp w covers tile positions w*512 + k*32 + [0,32)
-  K key[kSortItems];
-  uint32_t idx[kSortItems];
-  uint32_t rank[kSortItems];
-  // every load of the tile is issued before anything consumes one (ncu r1c: with the key
-  // transform inside the load loop each of the 16 loads exposed its full latency)
-  const int p0 = warp * (32 * kSortItems) + lane;
-  if (m == kSortTile) {
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) key[k] = src[p0 + k * 32];
-    if (PAIRS && srci) {
-#pragma unroll
-      for (int k = 0; k < kSortItems; ++k) idx[k] = srci[p0 + k * 32];
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) key[k] = (p0 + k * 32 < m) ? src[p0 + k * 32] : K(0);
-    if (PAIRS && srci) {
-#pragma unroll
-      for (int k = 0; k < kSortItems; ++k) idx[k] = (p0 + k * 32 < m) ? srci[p0 + k * 32] : 0u;
-    }
-  }
-  if (PAIRS && !srci) {
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) idx[k] = (uint32_t)(base + p0 + k * 32);
-  }
-#pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
-    K x = key[k];
-    if (first) x = to_key<K>(x, dtype);
-    key[k] = (p0 + k * 32 < m) ? x : ~K(0);
-  }
   uint32_t* wh = warp_hist + warp * 256;
-  // (1) peer masks of all 16 rows first: 16 independent chains of 9 ballots that the scheduler
-  //     can interleave (a per-row loop with the counter update inside serialises them);
-  //     rank[] holds the mask until step (2) replaces it with the rank
+  const int p0 = warp * (32 * kSortItems) + lane;  // striped: row k of warp w = positions w*512 + k*32 + [0,32)
+
+  auto body = [&](auto full_c) {
+    constexpr bool FULL = decltype(full_c)::value;
+    K key[kSortItems];
+    uint32_t idx[kSortItems];
+    uint32_t rank[kSortItems];
+    // every load of the tile is issued before anything consumes one
 #pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
-    const int p = warp * (32 * kSortItems) + k * 32 + lane;
-    const bool valid = p < m;
-    const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-    unsigned peers = __ballot_sync(0xffffffffu, valid);
-    peers = valid ? peers : ~peers;
+    for (int k = 0; k < kSortItems; ++k) key[k] = (FULL || p0 + k * 32 < m) ? src[p0 + k * 32] : K(0);
+    if constexpr (PAIRS) {
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const unsigned mb = __ballot_sync(0xffffffffu, bit);
-      peers &= bit ? mb : ~mb;
-    }
-    rank[k] = peers;
-  }
-  // (2) rows in order: the lowest peer lane adds the row's count to the warp's digit counter
-#pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
-    const int p = warp * (32 * kSortItems) + k * 32 + lane;
-    const bool valid = p < m;
-    const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-    const unsigned peers = rank[k];
-    const int leader = __ffs(peers) - 1;
-    uint32_t cnt = 0;
-    if (lane == leader && valid) {
-      cnt = wh[d];
-      wh[d] = cnt + (uint32_t)__popc(peers);
-    }
-    cnt = __shfl_sync(0xffffffffu, cnt, leader);
-    rank[k] = cnt + (uint32_t)__popc(peers & lt_mask);
-    __syncwarp();
-  }
-  __syncthreads();
-  // thread d owns digit d: counts over warps, publish, look back, tile-local digit offsets
-  {
-    const int d = threadIdx.x;
-    uint32_t run = 0;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) {
-      const uint32_t c = warp_hist[w * 256 + d];
-      warp_hist[w * 256 + d] = run;
-      run += c;
-    }
-    uint32_t* my_status = status + (size_t)tile * 256 + d;
-    st_status(my_status, (tl == 0 ? kInclusive : kPartial) | run);
-    uint32_t excl = 0;
-    if (tl > 0) {
-      // walk back over the earlier tiles of this request, 4 status words per round trip
-      // (speculative: words beyond the first INCLUSIVE one are simply ignored)
-      long long back = 1;                       // distance of the next tile to read
-      const long long max_back = (long long)tl;  // tile tl-... down to the request's first tile
-      bool done = false;
-      while (!done) {
-        uint32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          v[j] = (back + j <= max_back) ? ld_status(my_status - (back + j) * 256) : kInclusive;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (done) break;
-          uint32_t x = v[j];
-          for (unsigned spins = 0; (x & kFlagMask) == 0; ++spins) {
-            if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
-            x = ld_status(my_status - (back + j) * 256);
-          }
-          excl += x & kValMask;
-          if (x & kInclusive) done = true;
-        }
-        back += 4;
+      for (int k = 0; k < kSortItems; ++k) {
+        if constexpr (FIRST) idx[k] = (uint32_t)(base + p0 + k * 32);
+        else idx[k] = (FULL || p0 + k * 32 < m) ? srci[p0 + k * 32] : 0u;
       }
-      st_status(my_status, kInclusive | (excl + run));
     }
-    uint32_t inc = run;
 #pragma unroll
-    for (int s = 1; s < 32; s <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, inc, s);
-      if (lane >= s) inc += y;
+    for (int k = 0; k < kSortItems; ++k) {
+      if constexpr (FIRST) key[k] = to_key<K>(key[k], dtype);
+      if constexpr (!FULL) key[k] = (p0 + k * 32 < m) ? key[k] : ~K(0);
     }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t wprefix = 0;
-    for (int w = 0; w < warp; ++w) wprefix += wsum[w];
-    const uint32_t local = wprefix + inc - run;
-    digit_base[d] = local;
-    goff[d] = run_start + excl - local;
-  }
-  __syncthreads();
+    // (1) peer masks of all 16 rows first: independent chains of ballots the scheduler can
+    //     interleave; rank[] holds the mask until step (2) replaces it with the rank
 #pragma unroll
-  for (int k = 0; k < kSortItems; ++k) {
-    const int p = warp * (32 * kSortItems) + k * 32 + lane;
-    if (p < m) {
+    for (int k = 0; k < kSortItems; ++k) {
       const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-      const uint32_t lp = digit_base[d] + wh[d] + rank[k];
-      skeys[lp] = key[k];
-      if (PAIRS) sidx[lp] = idx[k];
+      unsigned peers = 0xffffffffu;
+      if constexpr (!FULL) {
+        const bool valid = p0 + k * 32 < m;
+        peers = __ballot_sync(0xffffffffu, valid);
+        peers = valid ? peers : ~peers;
+      }
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned mb = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? mb : ~mb;
+      }
+      rank[k] = peers;
     }
-  }
-  __syncthreads();
-  K* __restrict__ dst = reinterpret_cast<K*>(q.out);
-  for (int i = threadIdx.x; i < m; i += kThreads) {
-    const K x = skeys[i];
-    const uint32_t d = (uint32_t)(x >> shift) & 255u;
-    const size_t gp = (size_t)(uint32_t)(goff[d] + (uint32_t)i);
-    if (dst) dst[gp] = last ? from_key<K>(x, dtype) : x;
-    if (PAIRS) {
-      if (last) reinterpret_cast<long long*>(q.s0.i)[gp] = (long long)sidx[i];
-      else reinterpret_cast<uint32_t*>(q.s0.i)[gp] = sidx[i];
+    // (2) rows in order: the lowest peer lane adds the row's count to the warp's digit counter
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+      const bool valid = FULL || p0 + k * 32 < m;
+      const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
+      const unsigned peers = rank[k];
+      const int leader = __ffs(peers) - 1;
+      uint32_t cnt = 0;
+      if (lane == leader && valid) {
+        cnt = wh[d];
+        wh[d] = cnt + (uint32_t)__popc(peers);
+      }
+      cnt = __shfl_sync(0xffffffffu, cnt, leader);
+      rank[k] = cnt + (uint32_t)__popc(peers & lt_mask);
+      __syncwarp();
     }
-  }
+    __syncthreads();
+    // thread d owns digit d: counts over warps, publish, look back, tile-local digit offsets
+    {
+      const int d = threadIdx.x;
+      uint32_t run = 0;
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = warp_hist[w * 256 + d];
+        warp_hist[w * 256 + d] = run;
+        run += c;
+      }
+      uint32_t* my_status = status + (size_t)tile * 256 + d;
+      st_status(my_status, (tl == 0 ? kInclusive : kPartial) | run);
+      uint32_t excl = 0;
+      if (tl > 0) {
+        // walk back over the earlier tiles of this request, 4 status words per round trip
+        // (speculative: words beyond the first INCLUSIVE one are simply ignored)
+        long long back = 1;                        // distance of the next tile to read
+        const long long max_back = (long long)tl;  // down to the request's first tile
+        bool done = false;
+        while (!done) {
+          uint32_t v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = (back + j <= max_back) ? ld_status(my_status - (back + j) * 256) : kInclusive;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (done) break;
+            uint32_t x = v[j];
+            for (unsigned spins = 0; (x & kFlagMask) == 0; ++spins) {
+              if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
+              x = ld_status(my_status - (back + j) * 256);
+            }
+            excl += x & kValMask;
+            if (x & kInclusive) done = true;
+          }
+          back += 4;
+        }
+        st_status(my_status, kInclusive | (excl + run));
+      }
+      uint32_t inc = run;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, s);
+        if (lane >= s) inc += y;
+      }
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      uint32_t wprefix = 0;
+      for (int w = 0; w < warp; ++w) wprefix += wsum[w];
+      const uint32_t local = wprefix + inc - run;  // tile-local start of digit d
+      // fold it into the per-warp prefixes: one shared load per key in the placement below
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) warp_hist[w * 256 + d] += local;
+      goff[d] = run_start + excl - local;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+      if (FULL || p0 + k * 32 < m) {
+        const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
+        const uint32_t lp = wh[d] + rank[k];
+        skeys[lp] = key[k];
+        if constexpr (PAIRS) sidx[lp] = idx[k];
+      }
+    }
+    __syncthreads();
+    K* __restrict__ dst = reinterpret_cast<K*>(q.out);
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+      const int i = k * kThreads + (int)threadIdx.x;
+      if (FULL || i < m) {
+        const K x = skeys[i];
+        const uint32_t d = (uint32_t)(x >> shift) & 255u;
+        const size_t gp = (size_t)(uint32_t)(goff[d] + (uint32_t)i);
+        if constexpr (WRITE_KEYS) dst[gp] = LAST ? from_key<K>(x, dtype) : x;
+        if constexpr (PAIRS) {
+          if constexpr (LAST) reinterpret_cast<long long*>(q.s0.i)[gp] = (long long)sidx[i];
+          else reinterpret_cast<uint32_t*>(q.s0.i)[gp] = sidx[i];
+        }
+      }
+    }
+  };
+  if (m == kSortTile) body(std::true_type{});
+  else body(std::false_type{});
 }
 
 template <typename K, bool PAIRS>
 size_t onesweep_smem() {
   return sizeof(K) * kSortTile + (PAIRS ? sizeof(uint32_t) * kSortTile : 0) +
-         sizeof(uint32_t) * (kSortWarps * 256 + 256 + 256 + kSortWarps + 1);
+         sizeof(uint32_t) * (kSortWarps * 256 + 256 + kSortWarps + 1);
 }
 
 template <typename K, bool PAIRS>
@@ -317,8 +317,10 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
   constexpr int P = (int)sizeof(K);
   static bool attr_set = false;
   if (!attr_set) {
-    BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)onesweep_smem<K, PAIRS>()));
+    const int smem = (int)onesweep_smem<K, PAIRS>();
+    BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   size_t total_tiles = 0;
@@ -388,8 +390,14 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     rc = upload_batch(reqs.data(), B, kSortTile, &bt);
     if (rc != BCI_OK) return rc;
     BCI_CUDA(cudaMemsetAsync(status, 0, total_tiles * 256 * sizeof(uint32_t), c.stream));
-    onesweep_kernel<K, PAIRS><<<(unsigned)total_tiles, kThreads, onesweep_smem<K, PAIRS>(), c.stream>>>(
-        bt.d_reqs, bt.d_tile_start, B, p, dtype, first ? 1 : 0, last ? 1 : 0, ghist, status, counters + p);
+    const unsigned grid = (unsigned)total_tiles;
+    const size_t smem = onesweep_smem<K, PAIRS>();
+    if (first)
+      onesweep_kernel<K, PAIRS, true, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, status, counters + p);
+    else if (last)
+      onesweep_kernel<K, PAIRS, false, true><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, status, counters + p);
+    else
+      onesweep_kernel<K, PAIRS, false, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, status, counters + p);
     BCI_CHECK_LAUNCH();
   }
   return BCI_OK;
