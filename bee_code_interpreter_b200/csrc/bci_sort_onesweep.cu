@@ -129,7 +129,7 @@ digit_scan_kernel(uint32_t* __restrict__ ghist) {
 // FIRST / LAST pass and full / ragged tile are compile-time: the first version carried them as
 // runtime flags and spent 40 of its 145 instructions per key on predicates and branches (ncu r1c).
 template <typename K, bool PAIRS, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 4 : 2)
 onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
                 int pass, int dtype, const uint32_t* __restrict__ gbase,
                 uint32_t* __restrict__ status, uint32_t* __restrict__ counter) {
@@ -141,10 +141,12 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   uint32_t* warp_hist = sidx + (PAIRS ? kSortTile : 0);  // [kSortWarps][256]
   uint32_t* goff = warp_hist + kSortWarps * 256;          // [256] global offset - tile-local offset
   uint32_t* wsum = goff + 256;                            // [kSortWarps] (+1: dynamic tile id)
+  uint32_t* match = wsum + kSortWarps + 1;                // [kSortWarps][2][256] peer masks, all-zero between tiles
 
   // tiles are taken in the order CTAs start: whoever a tile waits for is already running
   if (threadIdx.x == 0) wsum[kSortWarps] = atomicAdd(counter, 1u);
   for (int i = threadIdx.x; i < kSortWarps * 256; i += kThreads) warp_hist[i] = 0;
+  for (int i = threadIdx.x; i < kSortWarps * 512; i += kThreads) match[i] = 0;
   __syncthreads();
   const unsigned long long tile = wsum[kSortWarps];
   const int r = find_req_block(tile_start, B, tile);
@@ -183,40 +185,59 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
       if constexpr (FIRST) key[k] = to_key<K>(key[k], dtype);
       if constexpr (!FULL) key[k] = (p0 + k * 32 < m) ? key[k] : ~K(0);
     }
-    // (1) peer masks of all 16 rows first: independent chains of ballots the scheduler can
-    //     interleave; rank[] holds the mask until step (2) replaces it with the rank
+    if constexpr (FULL) {
+      // Peers of a row = lanes with the same digit.  Each lane ORs its bit into a per-warp,
+      // per-digit mask word in shared memory and reads the word back: 2 shared-memory
+      // instructions per key where 8 ballots + their selects cost ~45 (ncu r1c: this kernel
+      // is issue-bound at 130-145 instructions per key).  Two rows per step on two mask
+      // arrays; the row leader (lowest peer lane) bumps the warp's digit counter and clears
+      // the mask word, so the arrays are all-zero again when the tile is done.
+      const unsigned my_bit = 1u << lane;
+      uint32_t* mm = match + warp * 512;
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-      const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-      unsigned peers = 0xffffffffu;
-      if constexpr (!FULL) {
+      for (int k = 0; k < kSortItems; k += 2) {
+        const uint32_t d0 = (uint32_t)(key[k] >> shift) & 255u;
+        const uint32_t d1 = (uint32_t)(key[k + 1] >> shift) & 255u;
+        atomicOr(&mm[d0], my_bit);
+        atomicOr(&mm[256 + d1], my_bit);
+        __syncwarp();
+        const unsigned m0 = mm[d0], m1 = mm[256 + d1];
+        const int l0 = __ffs(m0) - 1, l1 = __ffs(m1) - 1;
+        uint32_t c0 = 0, c1 = 0;
+        __syncwarp();  // every lane has read the masks before a leader clears them
+        if (lane == l0) { c0 = wh[d0]; wh[d0] = c0 + (uint32_t)__popc(m0); mm[d0] = 0; }
+        __syncwarp();  // row k's counter update is visible to row k+1's leader
+        if (lane == l1) { c1 = wh[d1]; wh[d1] = c1 + (uint32_t)__popc(m1); mm[256 + d1] = 0; }
+        c0 = __shfl_sync(0xffffffffu, c0, l0);
+        c1 = __shfl_sync(0xffffffffu, c1, l1);
+        rank[k] = c0 + (uint32_t)__popc(m0 & lt_mask);
+        rank[k + 1] = c1 + (uint32_t)__popc(m1 & lt_mask);
+        __syncwarp();
+      }
+    } else {
+      // ragged tile (the last one of a request): 8 ballots per row + one for validity
+#pragma unroll
+      for (int k = 0; k < kSortItems; ++k) {
+        const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
         const bool valid = p0 + k * 32 < m;
-        peers = __ballot_sync(0xffffffffu, valid);
+        unsigned peers = __ballot_sync(0xffffffffu, valid);
         peers = valid ? peers : ~peers;
-      }
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        const bool bit = (d >> b) & 1u;
-        const unsigned mb = __ballot_sync(0xffffffffu, bit);
-        peers &= bit ? mb : ~mb;
+        for (int b = 0; b < 8; ++b) {
+          const bool bit = (d >> b) & 1u;
+          const unsigned mb = __ballot_sync(0xffffffffu, bit);
+          peers &= bit ? mb : ~mb;
+        }
+        const int leader = __ffs(peers) - 1;
+        uint32_t cnt = 0;
+        if (lane == leader && valid) {
+          cnt = wh[d];
+          wh[d] = cnt + (uint32_t)__popc(peers);
+        }
+        cnt = __shfl_sync(0xffffffffu, cnt, leader);
+        rank[k] = cnt + (uint32_t)__popc(peers & lt_mask);
+        __syncwarp();
       }
-      rank[k] = peers;
-    }
-    // (2) rows in order: the lowest peer lane adds the row's count to the warp's digit counter
-#pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
-      const bool valid = FULL || p0 + k * 32 < m;
-      const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-      const unsigned peers = rank[k];
-      const int leader = __ffs(peers) - 1;
-      uint32_t cnt = 0;
-      if (lane == leader && valid) {
-        cnt = wh[d];
-        wh[d] = cnt + (uint32_t)__popc(peers);
-      }
-      cnt = __shfl_sync(0xffffffffu, cnt, leader);
-      rank[k] = cnt + (uint32_t)__popc(peers & lt_mask);
-      __syncwarp();
     }
     __syncthreads();
     // thread d owns digit d: counts over warps, publish, look back, tile-local digit offsets
@@ -308,7 +329,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
 template <typename K, bool PAIRS>
 size_t onesweep_smem() {
   return sizeof(K) * kSortTile + (PAIRS ? sizeof(uint32_t) * kSortTile : 0) +
-         sizeof(uint32_t) * (kSortWarps * 256 + 256 + kSortWarps + 1);
+         sizeof(uint32_t) * (kSortWarps * 256 + 256 + kSortWarps + 1 + kSortWarps * 512);
 }
 
 template <typename K, bool PAIRS>

@@ -211,7 +211,14 @@ def run_ours(args) -> dict | None:
     dom = k_rand if rand_s >= sumsq_s else k_sumsq
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
                 "unit": "GB/s", "frac": (dom["achieved"] / peak) if dom["achieved"] else None,
-                "traffic": None, "peak_kind": peak_kind, "kernels": [k_rand, k_sumsq],
+                # dram__bytes_read+write of one `ncu --set full` capture (profiles/r1a_ncu_full_c1.csv:
+                # 12.74 GB for a 12.8 GB launch of rand_f64_kernel, 12.81 GB for the reduce), scaled
+                # to this launch size: traffic == algorithmic bytes, nothing is re-read
+                "traffic": dom["algorithmic_bytes_per_launch"] * (0.9953 if dom is k_rand else 1.0004),
+                "traffic_source": "ncu capture of a 16-request launch, scaled to the %d-request launch" % wave,
+                "bound_note": "rand_f64_kernel is limited by the fmaheavy pipe (IMAD.WIDE of Philox4x32-10, "
+                              "82 % busy in ncu) before HBM; the fused reduce runs at 1.1x the measured copy peak",
+                "peak_kind": peak_kind, "kernels": [k_rand, k_sumsq],
                 "share_of_step": {"rand": rand_s / (dev_ms / 1e3), "sumsq": sumsq_s / (dev_ms / 1e3)}}
     out = {
         "metric": METRIC, "value": value, "unit": "requests/s", "n_gpus": world, "steps": args.steps,
