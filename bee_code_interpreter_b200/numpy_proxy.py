@@ -160,6 +160,25 @@ class DeviceArray(NDArrayOperatorsMixin):
         rhs = np.asarray(b) if b is not None else self._dtype.type(scalar)
         return _BINARY_NP[op](np.asarray(a), rhs)
 
+    def _assign(self, value) -> None:
+        """`self[...] = value` for a whole-array result (same shape): take its data over."""
+        self._before_mutation()
+        if isinstance(value, DeviceArray) and value.shape == self._shape and value.dtype == self._dtype:
+            ptr = value._device_ptr()
+            if self._ptr is not None and self._ptr != ptr:
+                self._backend.free(self._ptr)
+            self._ptr, value._ptr = ptr, None      # ownership moves; `value` is a dead temporary
+            self._host, self._deferred = value._host, None
+            return
+        host = np.asarray(value)
+        if host.shape != self._shape:
+            host = np.broadcast_to(host, self._shape)
+        self._host = np.array(host, dtype=self._dtype)   # same-kind cast like numpy's out=
+        if self._ptr is not None:
+            self._backend.free(self._ptr)
+            self._ptr = None
+        self._deferred = None
+
     def _before_mutation(self):
         for ref in list(self._dependents.values()):
             dep = ref()
@@ -189,12 +208,21 @@ class DeviceArray(NDArrayOperatorsMixin):
                     return _reduce(REDUCE_UFUNCS[ufunc], inputs[0])
         except (_Fallback, L.Unsupported, L.BciError):
             pass
-        host_inputs = tuple(np.asarray(x) if isinstance(x, DeviceArray) else x for x in inputs)
         if "out" in kwargs:
+            # in-place forms (`x += y`, `np.add(x, y, out=x)`): evaluate without `out`, then the
+            # proxy takes over the result's buffer — numpy semantics, no aliasing hazards
             outs = kwargs["out"]
-            for o in outs if isinstance(outs, tuple) else (outs,):
-                if isinstance(o, DeviceArray):
+            outs = outs if isinstance(outs, tuple) else (outs,)
+            if len(outs) == 1 and isinstance(outs[0], DeviceArray) and method == "__call__":
+                rest = {k: v for k, v in kwargs.items() if k != "out"}
+                result = self.__array_ufunc__(ufunc, method, *inputs, **rest)
+                if result is NotImplemented:
                     return NotImplemented
+                outs[0]._assign(result)
+                return outs[0]
+            if any(isinstance(o, DeviceArray) for o in outs):
+                return NotImplemented
+        host_inputs = tuple(np.asarray(x) if isinstance(x, DeviceArray) else x for x in inputs)
         return getattr(ufunc, method)(*host_inputs, **kwargs)
 
     def __array_function__(self, func, types, args, kwargs):

@@ -314,3 +314,71 @@ def test_content_addressed_storage_protocol(built, tmp_path):
     asyncio.run(scenario())
     assert max(c[1] for c in fake_device.calls if c[0].startswith("sha256")) >= 2        # writers hashed together
     st.hasher.close()
+
+
+def test_in_place_operators_and_out_argument(be):
+    h = np.arange(10, dtype=np.float64)
+    x = P.DeviceArray.from_host(be, h.copy())
+    y = P.DeviceArray.from_host(be, np.ones(10))
+    sq = np.square(x)                      # deferred on the OLD x
+    x += y
+    x *= 2.0
+    assert isinstance(x, P.DeviceArray)
+    assert np.array_equal(np.asarray(x), (h + 1) * 2)
+    assert np.array_equal(np.asarray(sq), h * h)            # not affected by the in-place update
+    np.subtract(x, y, out=x)
+    assert np.array_equal(np.asarray(x), (h + 1) * 2 - 1)
+    x /= 4                                   # true divide of float array by python int stays float64
+    assert np.allclose(np.asarray(x), ((h + 1) * 2 - 1) / 4)
+    z = np.zeros(10)
+    np.add(x, y, out=z)                      # host `out` with device inputs: numpy's own path
+    assert np.allclose(z, np.asarray(x) + 1)
+
+
+def test_random_expressions_match_numpy(be):
+    """Fuzz: random trees of supported operations on random arrays, evaluated through the proxy
+    (deferred / fused / materialised as the proxy decides) and by plain numpy."""
+    from hypothesis import given, settings, strategies as st
+
+    dtypes = [np.float32, np.float64, np.int32, np.int64]
+    unary = [np.square, np.abs, np.negative]
+    binary = [np.add, np.subtract, np.multiply, np.maximum, np.minimum]
+    reducers = [np.sum, np.max, np.min, np.mean, None, None]
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2**31 - 1), depth=st.integers(1, 4), di=st.integers(0, 3), n=st.integers(1, 3000),
+           ri=st.integers(0, len(reducers) - 1))
+    def run(seed, depth, di, n, ri):
+        rng = np.random.default_rng(seed)
+        dt = dtypes[di]
+        mk = (lambda: rng.integers(-50, 50, n, dtype=dt)) if np.issubdtype(dt, np.integer) else (lambda: ((rng.random(n) - 0.5) * 20).astype(dt))
+        hosts = [mk() for _ in range(3)]
+        devs = [P.DeviceArray.from_host(be, h.copy()) for h in hosts]
+        hv, dv = hosts[0], devs[0]
+        for _ in range(depth):
+            c = int(rng.integers(0, 3))
+            if c == 0:
+                f = unary[int(rng.integers(0, len(unary)))]
+                hv, dv = f(hv), f(dv)
+            elif c == 1:
+                f = binary[int(rng.integers(0, len(binary)))]
+                j = int(rng.integers(0, 3))
+                hv, dv = f(hv, hosts[j]), f(dv, devs[j])
+            else:
+                f = binary[int(rng.integers(0, 3))]
+                sc = int(rng.integers(-3, 4)) if np.issubdtype(dt, np.integer) else float(rng.integers(-3, 4)) + 0.5
+                hv, dv = f(hv, sc), f(dv, sc)
+        red = reducers[ri]
+        with np.errstate(all="ignore"):
+            if red is None:
+                got, want = np.asarray(dv), hv
+                assert got.dtype == want.dtype and np.array_equal(got, want)
+            else:
+                got, want = red(dv), red(hv)
+                assert np.asarray(got).dtype == np.asarray(want).dtype
+                if np.issubdtype(dt, np.integer) and red is not np.mean:
+                    assert got == want
+                else:
+                    assert np.isclose(float(got), float(want), rtol=1e-5 if dt == np.float32 else 1e-11, atol=1e-6)
+
+    run()
