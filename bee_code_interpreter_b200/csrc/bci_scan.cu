@@ -5,10 +5,11 @@
 //   (2) tile_scan : one CTA per request scans its tile sums  (tiny)
 //   (3) tile_apply: one CTA re-reads its tile, scans it with warp shuffles and adds the
 //                   tile prefix                               (reads n, writes n)
-// => 3 passes of traffic for 2 algorithmic; no inter-CTA waiting, deterministic.  A single-pass
-// chained scan with decoupled look-back is implemented below as well (BCI_SCAN=lookback): it
-// moves 2 passes but, one tile per CTA, is latency-bound at 3.9 TB/s on B200 where this form
-// streams at 6.6 TB/s — so this one is the default until the pipelined version lands.
+// => 3 passes of traffic for 2 algorithmic; no inter-CTA waiting, deterministic: the form used
+// for float inputs (0.67 of the algorithmic roofline, 6.6 TB/s of traffic).  Integer inputs take
+// the warp-specialised single-pass kernel further down (`scan_pipe_kernel`, BCI_SCAN=pipe: 2
+// passes, 0.78).  The plain one-tile-per-CTA chained scan (BCI_SCAN=lookback, 0.59) is kept as
+// the reference point of that design.  BCI_SCAN=legacy forces the three-pass form.
 // Accumulation type: int32/int64 -> int64 (bit-exact with numpy, two's complement wrap),
 // float64 -> float64, float32 -> float64 rounded once on store (numpy accumulates float32
 // sequentially in float32; see SURVEY.md hard part 2 — ours is the more accurate result).
@@ -16,6 +17,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdlib>
+#include <type_traits>
 
 namespace bci {
 
@@ -226,6 +228,46 @@ template <typename A> __device__ __forceinline__ A lb_value(unsigned long long b
   return v;
 }
 
+// Warp-wide look-back for tile `tile` of a request starting at `first_tile` (tile > first_tile):
+// returns the sum of everything before the tile.  Each round examines kLbWide*32 predecessors;
+// all status loads of a round are issued before any is inspected (a round costs one L2 round
+// trip whatever its width).  The persistent kernel has ~900 tiles in flight and uses 8 x 32; in
+// the one-tile-per-CTA kernel the extra registers cost a resident CTA, so it stays at 1 x 32.
+template <typename A, int kLbWide>
+__device__ __forceinline__ A lb_exclusive(const ulonglong2* __restrict__ st, unsigned long long tile,
+                                          unsigned long long first_tile) {
+  const int lane = threadIdx.x & 31;
+  A acc = A(0);  // per-lane partial; summed across the warp once at the end
+  long long p = (long long)tile - 1;
+  for (;;) {
+    ulonglong2 e[kLbWide];
+#pragma unroll
+    for (int j = 0; j < kLbWide; ++j) {
+      const long long idx = p - (j * 32 + lane);
+      e[j] = idx >= (long long)first_tile ? lb_load(st + idx) : make_ulonglong2(2ull, 0ull);
+    }
+    bool done = false;
+#pragma unroll
+    for (int j = 0; j < kLbWide; ++j) {
+      if (done) continue;
+      const long long idx = p - (j * 32 + lane);
+      for (unsigned spins = 0; e[j].x == 0ull; ++spins) {   // predecessor not published yet
+        if (spins > (1u << 24)) __trap();                    // a protocol bug must not hang the GPU
+        e[j] = lb_load(st + idx);
+      }
+      const unsigned has_incl = __ballot_sync(0xffffffffu, e[j].x == 2ull);
+      const int stop = has_incl ? (__ffs(has_incl) - 1) : 31;  // nearest tile whose prefix is complete
+      if (lane <= stop) acc = fadd_(acc, lb_value<A>(e[j].y));
+      done = has_incl != 0u;
+    }
+    if (done) break;
+    p -= 32 * kLbWide;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc = fadd_(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+  return acc;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
@@ -304,29 +346,7 @@ scan_lookback_kernel(const Req* __restrict__ reqs, const unsigned long long* __r
     if (lane == 0) lb_store(st + tile, is_first ? 2ull : 1ull, lb_bits<A>(agg));
     A excl = A(0);
     if (!is_first) {
-      long long p = (long long)tile - 1;
-      for (;;) {
-        const long long idx = p - lane;
-        unsigned long long f = 2ull;
-        A v = A(0);
-        if (idx >= (long long)first_tile) {
-          ulonglong2 e = lb_load(st + idx);
-          for (unsigned spins = 0; e.x == 0ull; ++spins) {
-            if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
-            e = lb_load(st + idx);
-          }
-          f = e.x;
-          v = lb_value<A>(e.y);
-        }
-        const unsigned has_incl = __ballot_sync(0xffffffffu, f == 2ull);
-        const int stop = has_incl ? (__ffs(has_incl) - 1) : 31;  // nearest tile whose prefix is complete
-        A contrib = lane <= stop ? v : A(0);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) contrib = fadd_(contrib, __shfl_xor_sync(0xffffffffu, contrib, d));
-        excl = fadd_(excl, contrib);
-        if (has_incl) break;
-        p -= 32;
-      }
+      excl = lb_exclusive<A, 1>(st, tile, first_tile);  // registers are this form's limiter: narrow window
       if (lane == 0) lb_store(st + tile, 2ull, lb_bits<A>(fadd_(excl, agg)));
     }
     if (lane == 0) tile_excl = excl;
@@ -384,15 +404,334 @@ static int launch_cumsum_lookback(Req* reqs, int B) {
   return BCI_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised single-pass scan: persistent CTAs (one per SM), a ring of input tiles kept in
+// flight by bulk copies, and the chained-scan protocol run AHEAD of the data path.
+//
+//   warp 8  producer : next tile id from the atomic counter -> request lookup (32 boundaries per
+//                      round trip, monotone) -> stage descriptor -> ONE cp.async.bulk global->shared
+//                      of the whole tile, completing on full[s].  HBM reads never wait for a
+//                      look-back.  (Ragged / unaligned tiles: the warp copies them itself, zero
+//                      padded.)
+//   warp 9  aggregate: as soon as full[s] fires, sums the tile out of shared memory and publishes
+//                      the tile aggregate — i.e. as early as the data allows, never queued behind
+//                      another tile's look-back (that queueing is what made a first pipelined
+//                      version 3x slower than the plain one: 56 polls per tile, ncu r1e).
+//   warps 10-13 look-back (round robin over tiles): exclusive prefix of the tile from its predecessors' status words
+//                      (256 per round), publishes the inclusive prefix, hands `excl` to the scan
+//                      warps through ready[s].
+//   warps 0-7 scan   : tile from shared memory -> registers, release the stage (empty[s]), local +
+//                      warp scans, add `excl`, STG.256.  They never see the look-back latency as
+//                      long as the ring is deeper than it.
+// Tile ids are handed out in increasing order and every role works through the ring in order, so
+// the oldest unfinished tile never waits on a younger one: no deadlock, no co-residency assumption.
+__device__ __forceinline__ uint32_t sc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sc_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sc_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sc_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = sc_smem_u32(bar);
+  uint32_t done = 0;
+  for (unsigned long long spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (spins > (1ull << 26)) __trap();  // a protocol bug must not hang the GPU
+  }
+}
+__device__ __forceinline__ void sc_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sc_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(sc_smem_u32(bar)) : "memory");
+}
+
+constexpr int kWsScanWarps = kThreads / 32;              // 8
+constexpr int kWsLbWarps = 4;                            // look-backs of consecutive tiles overlap
+constexpr int kWsThreads = kThreads + (2 + kWsLbWarps) * 32;  // + producer, aggregate, look-back warps
+template <typename T> struct Pipe {
+  static constexpr int SUB = sizeof(T) == 8 ? 4 : 2;                        // 32 / 16 KiB of input per tile
+  static constexpr size_t TILE = (size_t)kThreads * SUB * (32 / sizeof(T)); // 4096 elements
+  static constexpr size_t TILE_BYTES = TILE * sizeof(T);
+  static constexpr int STAGES = (192 * 1024) / TILE_BYTES > 8 ? 8 : (int)((192 * 1024) / TILE_BYTES);
+  static_assert(STAGES > kWsLbWarps, "the end markers must not wrap onto each other");
+  static constexpr size_t SMEM = (size_t)STAGES * TILE_BYTES + 128;
+};
+
+struct alignas(16) PipeStage {
+  const void* in;                  // first element of the tile
+  void* out;
+  unsigned long long rem;          // elements from `in` to the end of the request
+  unsigned long long tile;
+  unsigned long long first_tile;   // of the tile's request
+  unsigned int valid, fast;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kWsThreads, 1)
+scan_pipe_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
+                 unsigned long long total_tiles, ulonglong2* __restrict__ st, uint32_t* __restrict__ counter) {
+  using A = typename ScanTypes<T>::Acc;
+  using O = typename ScanTypes<T>::Out;
+  constexpr int VN = 32 / sizeof(T);
+  constexpr int VO = 32 / sizeof(O);
+  constexpr int NST = VN / VO;
+  constexpr int SUB = Pipe<T>::SUB;
+  constexpr int STAGES = Pipe<T>::STAGES;
+  constexpr size_t TILE = Pipe<T>::TILE;
+  constexpr uint32_t TILE_BYTES = (uint32_t)Pipe<T>::TILE_BYTES;
+  constexpr int NW = kWsScanWarps;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full[STAGES], aggd[STAGES], ready[STAGES], empty[STAGES];
+  __shared__ PipeStage meta[STAGES];
+  __shared__ A agg_s[STAGES], excl_s[STAGES];
+  __shared__ A warp_tot2[2][SUB][NW];  // double-buffered by iteration parity: one named barrier per tile
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      sc_mbar_init(&full[s], 1);
+      sc_mbar_init(&aggd[s], 1);
+      sc_mbar_init(&ready[s], 1);
+      sc_mbar_init(&empty[s], NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == NW) {
+    // ------------------------------------------------------------------ producer
+    int r = 0;  // request of the last tile fetched (tile ids only grow)
+    int tail = 0;  // end markers written: one per look-back warp, so each of them meets one
+    for (unsigned it = 0;; ++it) {
+      const int s = (int)(it % STAGES);
+      sc_mbar_wait(&empty[s], ((it / STAGES) & 1u) ^ 1u);  // first lap: passes immediately
+      unsigned int id = 0;
+      if (lane == 0) id = atomicAdd(counter, 1u);
+      id = __shfl_sync(0xffffffffu, id, 0);
+      const unsigned long long tile = id;
+      if (tile >= total_tiles) {
+        if (lane == 0) {
+          meta[s].valid = 0u;
+          sc_mbar_arrive(&full[s]);
+        }
+        if (++tail == kWsLbWarps) break;
+        continue;
+      }
+      for (;;) {  // boundaries tile_start[r+1 ...] that are <= tile
+        const int i = r + 1 + lane;
+        const bool le = i < B && __ldg(tile_start + i) <= tile;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, le));
+        r += cnt;
+        if (cnt < 32) break;
+      }
+      const Req q = reqs[r];
+      const size_t base = (size_t)(tile - q.tile_start) * TILE;
+      const size_t rem = (size_t)q.n - base;
+      const T* a = reinterpret_cast<const T*>(q.in0) + base;
+      O* o = reinterpret_cast<O*>(q.out) + base;
+      const bool fast = rem >= TILE && is_aligned32(a) && is_aligned32(o);
+      if (lane == 0) {
+        PipeStage m;
+        m.in = a; m.out = o; m.rem = rem; m.tile = tile; m.first_tile = q.tile_start; m.valid = 1u; m.fast = fast ? 1u : 0u;
+        meta[s] = m;
+      }
+      if (fast) {
+        if (lane == 0) {
+          sc_mbar_expect_tx(&full[s], TILE_BYTES);
+          sc_bulk_load(ring + (size_t)s * TILE_BYTES, a, TILE_BYTES, &full[s]);
+        }
+      } else {
+        T* dst = reinterpret_cast<T*>(ring + (size_t)s * TILE_BYTES);
+#pragma unroll 8
+        for (unsigned e = lane; e < (unsigned)TILE; e += 32) dst[e] = e < rem ? a[e] : T(0);
+        __syncwarp();
+        if (lane == 0) sc_mbar_arrive(&full[s]);
+      }
+    }
+  } else if (warp == NW + 1) {
+    // ------------------------------------------------------------------ aggregate
+    int tail = 0;
+    for (unsigned it = 0;; ++it) {
+      const int s = (int)(it % STAGES);
+      sc_mbar_wait(&full[s], (it / STAGES) & 1u);
+      const PipeStage m = meta[s];
+      if (!m.valid) {
+        if (lane == 0) sc_mbar_arrive(&aggd[s]);
+        if (++tail == kWsLbWarps) break;
+        continue;
+      }
+      const uint4* src = reinterpret_cast<const uint4*>(ring + (size_t)s * TILE_BYTES);
+      A part[4] = {A(0), A(0), A(0), A(0)};
+#pragma unroll 4
+      for (unsigned i = 0; i < TILE_BYTES / 16 / 32; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          union { uint4 q; T v[16 / sizeof(T)]; } w;
+          w.q = src[(size_t)(i + u) * 32 + lane];
+#pragma unroll
+          for (int j = 0; j < (int)(16 / sizeof(T)); ++j) part[u] = fadd_(part[u], (A)w.v[j]);
+        }
+      }
+      A agg = fadd_(fadd_(part[0], part[1]), fadd_(part[2], part[3]));
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) agg = fadd_(agg, __shfl_xor_sync(0xffffffffu, agg, d));
+      if (lane == 0) {
+        lb_store(st + m.tile, m.tile == m.first_tile ? 2ull : 1ull, lb_bits<A>(agg));
+        agg_s[s] = agg;
+        sc_mbar_arrive(&aggd[s]);
+      }
+    }
+  } else if (warp >= NW + 2) {
+    // ------------------------------------------------------------------ look-back (tile it -> warp it % kWsLbWarps)
+    for (unsigned it = (unsigned)(warp - (NW + 2));; it += kWsLbWarps) {
+      const int s = (int)(it % STAGES);
+      sc_mbar_wait(&aggd[s], (it / STAGES) & 1u);
+      const PipeStage m = meta[s];
+      if (!m.valid) {
+        if (lane == 0) sc_mbar_arrive(&ready[s]);
+        break;
+      }
+      A excl = A(0);
+      if (m.tile != m.first_tile) {
+        excl = lb_exclusive<A, 8>(st, m.tile, m.first_tile);
+        if (lane == 0) lb_store(st + m.tile, 2ull, lb_bits<A>(fadd_(excl, agg_s[s])));
+      }
+      if (lane == 0) {
+        excl_s[s] = excl;
+        sc_mbar_arrive(&ready[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ scan warps
+    for (unsigned it = 0;; ++it) {
+      const int s = (int)(it % STAGES);
+      const uint32_t parity = (it / STAGES) & 1u;
+      sc_mbar_wait(&full[s], parity);
+      const PipeStage m = meta[s];
+      if (!m.valid) break;
+      O* __restrict__ o = reinterpret_cast<O*>(m.out);
+      const size_t rem = (size_t)m.rem;
+      const bool fast = m.fast != 0u;
+      A (*warp_tot)[NW] = warp_tot2[it & 1u];
+      A x[SUB][VN];
+      A lane_excl[SUB];
+      {
+        const uint8_t* src = ring + (size_t)s * TILE_BYTES;
+        VecOf<T> v[SUB];
+#pragma unroll
+        for (int k = 0; k < SUB; ++k) {
+          const uint4* p = reinterpret_cast<const uint4*>(src + ((size_t)k * kThreads + threadIdx.x) * 32);
+          const uint4 lo = p[0], hi = p[1];
+          v[k].u.r[0] = lo.x; v[k].u.r[1] = lo.y; v[k].u.r[2] = lo.z; v[k].u.r[3] = lo.w;
+          v[k].u.r[4] = hi.x; v[k].u.r[5] = hi.y; v[k].u.r[6] = hi.z; v[k].u.r[7] = hi.w;
+        }
+#pragma unroll
+        for (int k = 0; k < SUB; ++k) {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) x[k][j] = (A)v[k].v[j];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < SUB; ++k) {
+#pragma unroll
+        for (int j = 1; j < VN; ++j) x[k][j] = fadd_(x[k][j - 1], x[k][j]);
+        A inc = x[k][VN - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const A y = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc = fadd_(inc, y);
+        }
+        if (lane == 31) warp_tot[k][warp] = inc;
+        A ex = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) ex = A(0);
+        lane_excl[k] = ex;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");  // the 8 scan warps only
+      sc_mbar_wait(&ready[s], parity);  // the look-back ran ahead (or finishes while we scanned)
+      A carry = excl_s[s];
+      __syncwarp();
+      // release the stage only now: ready[s] / excl_s[s] must not be re-armed for a later tile
+      // before every scan warp has consumed this one's
+      if (lane == 0) sc_mbar_arrive(&empty[s]);
+#pragma unroll
+      for (int k = 0; k < SUB; ++k) {
+        A wprefix = A(0), all = A(0);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const A wt = warp_tot[k][w];
+          if (w < warp) wprefix = fadd_(wprefix, wt);
+          all = fadd_(all, wt);
+        }
+        const A off = fadd_(fadd_(carry, wprefix), lane_excl[k]);
+        const size_t e0 = ((size_t)k * kThreads + threadIdx.x) * VN;
+        if (fast) {
+#pragma unroll
+          for (int kk = 0; kk < NST; ++kk) {
+            VecOf<O> vo;
+#pragma unroll
+            for (int j = 0; j < VO; ++j) vo.v[j] = (O)fadd_(off, x[k][kk * VO + j]);
+            stg256(o + e0 + (size_t)kk * VO, vo.u);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < VN; ++j)
+            if (e0 + j < rem) o[e0 + j] = (O)fadd_(off, x[k][j]);
+        }
+        carry = fadd_(carry, all);
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_cumsum_pipe(Req* reqs, int B) {
+  Ctx& c = ctx();
+  Batch bt;
+  int rc = upload_batch(reqs, B, Pipe<T>::TILE, &bt);
+  if (rc != BCI_OK) return rc;
+  if (bt.total_tiles == 0) return BCI_OK;
+  if (bt.total_tiles > 0x7fffffffull) { set_error("bci_cumsum: batch too large for one launch"); return BCI_ERR_INVALID; }
+  const size_t bytes = 256 + bt.total_tiles * sizeof(ulonglong2);
+  void* sc = nullptr;
+  rc = scratch_get(bytes, &sc);
+  if (rc != BCI_OK) return rc;
+  uint8_t* sb = reinterpret_cast<uint8_t*>(sc);
+  uint32_t* counter = reinterpret_cast<uint32_t*>(sb);
+  ulonglong2* st = reinterpret_cast<ulonglong2*>(sb + 256);
+  BCI_CUDA(cudaMemsetAsync(sb, 0, bytes, c.stream));
+  static bool configured = false;
+  if (!configured) {
+    BCI_CUDA(cudaFuncSetAttribute(scan_pipe_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pipe<T>::SMEM));
+    configured = true;
+  }
+  unsigned long long grid = (unsigned long long)c.sm_count;
+  if (grid > bt.total_tiles) grid = bt.total_tiles;
+  scan_pipe_kernel<T><<<(unsigned)grid, kWsThreads, Pipe<T>::SMEM, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, bt.total_tiles, st, counter);
+  BCI_CHECK_LAUNCH();
+  return BCI_OK;
+}
+
 template <typename T>
 static int launch_cumsum(Req* reqs, int B) {
   {
-    // Measured on B200 (profiles/r1_kernel_table.md): the 3-pass form below runs at 6.6 TB/s of
-    // traffic (0.67 of the algorithmic roofline), the single-pass look-back form at 3.9 TB/s
-    // (0.59): one-tile-per-CTA look-back is latency-bound at 2-4 CTAs/SM.  The faster one is the
-    // default; BCI_SCAN=lookback selects the single-pass kernel (kept for the pipelined rewrite).
+    // Measured on B200, int64 1e7 x 32 (tools/prof_scan.py): three-pass 4.42 TB/s algorithmic
+    // (0.67), one-tile-per-CTA look-back 3.88 (0.59), warp-specialised pipeline 5.15 (0.78).
     const char* force = getenv("BCI_SCAN");
     if (force && strcmp(force, "lookback") == 0) return launch_cumsum_lookback<T>(reqs, B);
+    if (force && strcmp(force, "pipe") == 0) return launch_cumsum_pipe<T>(reqs, B);
+    // Integers: the warp-specialised single-pass kernel (two's-complement sums are associative, so
+    // the timing-dependent look-back depth cannot change a bit).  Floats stay on the three-pass
+    // form: its summation order is fixed, a chained scan's is not.
+    if (!(force && strcmp(force, "legacy") == 0) && std::is_integral<T>::value) return launch_cumsum_pipe<T>(reqs, B);
   }
   using A = typename ScanTypes<T>::Acc;
   Ctx& c = ctx();

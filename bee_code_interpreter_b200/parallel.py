@@ -123,3 +123,73 @@ def split_cumsum_offset(local_total, dist, integer: bool = False):
     for r in range(rank):
         acc += int(allv[r].item()) if integer else float(allv[r].item())
     return acc
+
+
+def split_sort(local, dist, sort_local, oversample: int = 64):
+    """numpy.sort of ONE array whose contiguous chunks live on the ranks ("sort →
+    sample-sort with one all-to-all bucket exchange").
+
+    `local` is this rank's chunk as a 1-D torch tensor (CUDA under NCCL, CPU under gloo);
+    `sort_local(tensor) -> tensor` is the single-GPU sort (the radix kernel through the C ABI
+    on the GPU box).  Returns this rank's bucket of the global order: concatenating the
+    results by rank gives numpy.sort(whole array), NaNs last (they all land on the last rank).
+    Steps: local sort -> `oversample` regular samples per rank, all_gather -> W-1 splitters ->
+    cut points by binary search in the sorted chunk -> all_to_all of counts, then of keys ->
+    sort of the received runs.  torch is the plumbing (sample gather, cut search over W-1
+    values, NCCL exchange); both sorts are the kernel's."""
+    import torch
+
+    world = dist.get_world_size()
+    s = sort_local(local)
+    n = int(s.numel())
+    n_valid = n - int(torch.isnan(s).sum().item()) if s.is_floating_point() else n   # NaNs sit at the end
+    k = oversample
+    have = torch.tensor([1 if n_valid else 0], dtype=torch.int64, device=s.device)
+    if n_valid:
+        pick = ((torch.arange(1, k + 1, device=s.device, dtype=torch.int64) * n_valid) // (k + 1)).clamp_(max=n_valid - 1)
+        samples = s[pick].contiguous()
+    else:
+        samples = torch.zeros(k, dtype=s.dtype, device=s.device)
+    all_samples = [torch.empty_like(samples) for _ in range(world)]
+    all_have = [torch.empty_like(have) for _ in range(world)]
+    dist.all_gather(all_samples, samples)
+    dist.all_gather(all_have, have)
+    pool = [t for t, h in zip(all_samples, all_have) if int(h.item())]
+    if pool:
+        pooled = torch.sort(torch.cat(pool)).values                      # <= W*k values: plumbing
+        at = (torch.arange(1, world, device=s.device, dtype=torch.int64) * pooled.numel()) // world
+        splitters = pooled[at]
+        cuts = torch.searchsorted(s[:n_valid].contiguous(), splitters, right=True)
+    else:
+        cuts = torch.zeros(world - 1, dtype=torch.int64, device=s.device)
+    bounds = [0] + [int(c) for c in cuts.tolist()] + [n]                 # NaN tail goes with the last bucket
+    send_counts = [bounds[i + 1] - bounds[i] for i in range(world)]
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=s.device)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc)
+    recv_counts = [int(c) for c in rc.tolist()]
+    recv = torch.empty(sum(recv_counts), dtype=s.dtype, device=s.device)
+    if dist.get_backend() == "gloo":
+        # gloo has no uneven all_to_all_single: W rounds of point-to-point (test path only)
+        ins = list(torch.split(s, send_counts))
+        outs = list(torch.split(recv, recv_counts))
+        rank = dist.get_rank()
+        outs[rank].copy_(ins[rank])
+        reqs = []
+        for peer in range(world):
+            if peer != rank:
+                reqs.append(dist.isend(ins[peer].contiguous(), peer))
+                reqs.append(dist.irecv(outs[peer], peer))
+        for r in reqs:
+            r.wait()
+    else:
+        dist.all_to_all_single(recv, s, output_split_sizes=recv_counts, input_split_sizes=send_counts)
+    return sort_local(recv)
+
+
+def split_matmul_rows(a_rows, b_full, dist, matmul_local, src: int = 0):
+    """`A @ B` with A split by rows over the ranks and B held by `src` ("matmul →
+    row-split A, replicate B (broadcast), no reduction").  `b_full` is a tensor of B's shape
+    on every rank (contents significant on `src` only).  Returns this rank's rows of C."""
+    dist.broadcast(b_full, src=src)
+    return matmul_local(a_rows, b_full)

@@ -62,6 +62,37 @@ def main():
     nanv = par.split_extreme(float("nan") if rank == 1 else 1.0, dist, maximum=True)
     nan_arg = par.split_argext(float("nan") if rank == 1 else 5.0, 7, lo, dist, maximum=True)
     ints = par.split_sum(int(rank + 1) * (2**40), dist, integer=True)
+    # split sort: sample sort over the ranks (local sorts = the device sort), NaNs last
+    import torch
+    fs = np.random.default_rng(5).standard_normal(50_001).astype(np.float32)
+    fs[[7, 30_000, 49_999]] = np.nan
+    flo, fhi = par.chunk_bounds(fs.size, rank, world)
+
+    def sort_local(t):
+        h = t.numpy()
+        pi, po = fake_device.upload(h), fake_device.alloc(h.nbytes)
+        fake_device.sort(h.dtype, [pi], [po], [h.size])
+        out = fake_device.download(po, h.size, h.dtype)
+        fake_device.free(pi), fake_device.free(po)
+        return torch.from_numpy(out)
+
+    mine_sorted = par.split_sort(torch.from_numpy(fs[flo:fhi].copy()), dist, sort_local, oversample=16).numpy()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine_sorted)
+    ks = np.random.default_rng(6).integers(-5, 5, 20_000, dtype=np.int64)       # heavy duplicates
+    klo, khi = par.chunk_bounds(ks.size, rank, world)
+    kparts = [None] * world
+    dist.all_gather_object(kparts, par.split_sort(torch.from_numpy(ks[klo:khi].copy()), dist, sort_local, oversample=8).numpy())
+    eparts = [None] * world                                                       # one rank has nothing
+    dist.all_gather_object(eparts, par.split_sort(torch.from_numpy(ks[:0] if rank == 0 else ks[:100].copy()), dist, sort_local).numpy())
+    # split matmul: rows of A per rank, B broadcast from rank 0
+    mat_a = np.random.default_rng(8).random((10, 6), dtype=np.float32)
+    bm = np.random.default_rng(9).random((6, 4), dtype=np.float32)
+    rlo, rhi = par.chunk_bounds(10, rank, world)
+    bt = torch.from_numpy(bm.copy()) if rank == 0 else torch.zeros(6, 4)
+    crow = par.split_matmul_rows(torch.from_numpy(mat_a[rlo:rhi].copy()), bt, dist, lambda a, b: a @ b)
+    cparts = [None] * world
+    dist.all_gather_object(cparts, crow.numpy())
     flags = [cs_ok]
     allf = [None] * world
     dist.all_gather_object(allf, flags)
@@ -75,6 +106,11 @@ def main():
             "nan_ok": bool(np.isnan(nanv)) and nan_arg == par.chunk_bounds(n, 1, world)[0] + 7,
             "int_ok": ints == sum((r + 1) * 2**40 for r in range(world)),
             "chunks": [par.chunk_bounds(n, r, world) for r in range(world)],
+            "sort_ok": bool(np.array_equal(np.concatenate(parts), np.sort(fs), equal_nan=True)),
+            "sort_balanced": min(len(p) for p in parts) > fs.size // (4 * world),
+            "sort_dups_ok": bool(np.array_equal(np.concatenate(kparts), np.sort(ks))),
+            "sort_empty_rank_ok": bool(np.array_equal(np.concatenate(eparts), np.sort(ks[:100]))) if world == 2 else True,
+            "matmul_ok": bool(np.allclose(np.concatenate(cparts), mat_a @ bm, rtol=1e-6)),
         })
         out = {k: (bool(v) if isinstance(v, (bool, np.bool_)) else v) for k, v in out.items()}
         print("RESULT " + json.dumps(out), flush=True)

@@ -226,8 +226,11 @@ def test_argext(dev, bufs, dtype):
         assert dev.argext(L.ARGMIN, dtype, [p], [x.size])[0] == 123_456
 
 
+@pytest.mark.parametrize("mode", ["default", "legacy", "lookback", "pipe"])
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_cumsum(dev, bufs, dtype):
+def test_cumsum(dev, bufs, dtype, mode, monkeypatch):
+    if mode != "default":
+        monkeypatch.setenv("BCI_SCAN", mode)
     rng = np.random.default_rng(41)
     xs = [gen(rng, n, dtype) for n in SIZES + [2_000_003]]
     ns = [x.size for x in xs]
@@ -448,11 +451,15 @@ def test_sort_and_cumsum_many_small_and_empty_requests(dev, bufs, monkeypatch):
     for x, p, f, q in zip(xs, po, fs, pfo):
         assert np.array_equal(dev.download(p, x.size, np.int64), np.cumsum(x))
         assert np.array_equal(dev.download(q, f.size, np.float32), np.sort(f))
-    monkeypatch.setenv("BCI_SCAN", "lookback")          # single-pass kernel: chains stop at request starts
-    dev.cumsum(np.int64, px, po, sizes)
-    monkeypatch.delenv("BCI_SCAN")
-    for x, p in zip(xs, po):
-        assert np.array_equal(dev.download(p, x.size, np.int64), np.cumsum(x))
+    for mode in ("lookback", "pipe", "legacy"):        # single-pass kernels: chains stop at request starts
+        monkeypatch.setenv("BCI_SCAN", mode)
+        for x, p in zip(xs, po):
+            if x.size:
+                dev.h2d(p, np.full(x.size, -7, dtype=np.int64))     # no stale results from the previous form
+        dev.cumsum(np.int64, px, po, sizes)
+        monkeypatch.delenv("BCI_SCAN")
+        for x, p in zip(xs, po):
+            assert np.array_equal(dev.download(p, x.size, np.int64), np.cumsum(x)), mode
     pi = [bufs.new(max(x.size * 8, 8)) for x in xs]
     dev.argsort(np.int64, px, pi, sizes)
     dev.sort(np.int64, px, po, sizes)

@@ -34,5 +34,5 @@ def test_two_rank_gloo_run(built):
     out = json.loads(line[len("RESULT "):])
     assert out["owners"] == [i % 2 for i in range(11)]
     for key in ("round_robin_ok", "sum_ok", "mean_ok", "max_ok", "min_ok", "argmax_ok", "argmin_ok", "cumsum_ok",
-                "nan_ok", "int_ok"):
+                "nan_ok", "int_ok", "sort_ok", "sort_balanced", "sort_dups_ok", "sort_empty_rank_ok", "matmul_ok"):
         assert out[key] is True, (key, out)

@@ -180,6 +180,10 @@ def main():
     dev.sync()
     add("argmax f32 (K6)", f"C5 n=1e7 x{B5}", 4 * n5 * B5, timed(k_argext(L.ARGMAX, np.float32, v, ns)))
     add("cumsum i64 (K7)", f"C5 n=1e7 x{B5}", 16 * n5 * B5, timed(k_inout("bci_cumsum", np.int64, k, ko, ns)), moved_bytes=24 * n5 * B5)
+    for mode in ("legacy", "lookback", "pipe"):
+        os.environ["BCI_SCAN"] = mode
+        add(f"cumsum i64 [{mode}] (K7)", f"C5 n=1e7 x{B5}", 16 * n5 * B5, timed(k_inout("bci_cumsum", np.int64, k, ko, ns)))
+    os.environ.pop("BCI_SCAN")
     add("sort f32 (K5)", f"C5 n=1e7 x{B5}", 36 * n5 * B5, timed(k_inout("bci_sort", np.float32, v, vo, ns), iters=3), moved_bytes=48 * n5 * B5)
     add("sort i64 (K5)", f"n=1e7 x{B5}", 17 * 8 * n5 * B5, timed(k_inout("bci_sort", np.int64, k, ko, ns), iters=3), moved_bytes=24 * 8 * n5 * B5)
     add("argsort f32 stable (K5)", f"n=1e7 x{B5}", (36 + 8) * n5 * B5, timed(k_inout("bci_argsort", np.float32, v, idx, ns), iters=3))
