@@ -97,10 +97,29 @@ def build_oracle(force: bool = False) -> Path:
     return ORACLE_LIB
 
 
+SERVER_SRC = CSRC / "bci_executor_server.cpp"
+SERVER_BIN = PKG_DIR / "bci-executor-server"
+
+
+def build_server(force: bool = False) -> Path:
+    """Compiles the native executor server (the server.rs stand-in; plain C++17, no CUDA)."""
+    if not force and _newer(SERVER_BIN, [SERVER_SRC]):
+        return SERVER_BIN
+    gxx = shutil.which("g++") or "g++"
+    tmp = SERVER_BIN.with_suffix(".tmp")
+    cmd = [gxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", str(tmp), str(SERVER_SRC), "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for the executor server:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, SERVER_BIN)
+    return SERVER_BIN
+
+
 def main() -> None:
     force = "--force" in sys.argv
     verbose = "-v" in sys.argv
     print(build_lib(force=force, verbose=verbose))
+    print(build_server(force=force))
     print(build_oracle(force=force))
 
 

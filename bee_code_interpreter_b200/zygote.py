@@ -8,7 +8,8 @@ fork() of it (~2 ms) and keeps the reference's isolation unit — one OS process
 
 The zygote is single-threaded and holds no CUDA context, so fork() is safe.  Protocol (Unix
 stream socket, one connection per request):
-    client -> zygote : 4-byte length + pickled request dict
+    client -> zygote : 4-byte length + request dict (pickle from ZygoteClient, JSON from
+                       csrc/bci_executor_server.cpp)
     zygote -> client : 4-byte pid of the forked child          (zygote then closes its copy)
     child  -> client : 4-byte exit code, just before os._exit  (absent if the child was killed
                        or crashed: the client maps EOF to -1, like server.rs:165)
@@ -16,6 +17,7 @@ Children are auto-reaped (SIGCHLD ignored).
 """
 from __future__ import annotations
 
+import json
 import os
 import pickle
 import signal
@@ -67,7 +69,9 @@ def serve(socket_path: str) -> None:
                 conn.close()
                 continue
             (length,) = struct.unpack("<I", head)
-            req = pickle.loads(_recv_exact(conn, length))
+            payload = _recv_exact(conn, length)
+            # pickled dict from ZygoteClient, JSON object from the native executor server
+            req = json.loads(payload) if payload[:1] == b"{" else pickle.loads(payload)
             if req.get("op") == "shutdown":
                 conn.close()
                 break

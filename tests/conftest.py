@@ -20,6 +20,7 @@ def built():
 
     build.build_lib()
     build.build_oracle()
+    build.build_server()
     return True
 
 

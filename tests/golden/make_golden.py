@@ -9,6 +9,13 @@
                     (services/storage.py) as the object store.  Pins: response model shape,
                     status codes (200 / 422 / 500), file-map round trip, env propagation,
                     exit-code and stderr behaviour of failing scripts.
+  pod_replay.json   the reference's FULL service stack — FastAPI app + the unmodified
+                    KubernetesCodeExecutor.execute (kubernetes_code_executor.py:80-149: httpx PUT
+                    uploads, POST /execute, streamed GET downloads) + the reference's Storage —
+                    with bci-executor-server standing where the Rust executor pod stands (only
+                    `executor_pod()` is overridden, to hand out 127.0.0.1 instead of asking
+                    kubectl for a pod; one fresh server + workspace per request, like a fresh
+                    pod).  Same request bodies as http_replay.json.
   numeric.npz       seeded inputs and the results stock numpy (the reference's arithmetic)
                     gives for every op class of SURVEY.md §8a; numpy version recorded.
 """
@@ -80,6 +87,72 @@ def http_replay():
     print("http_replay.json:", len(cases), "cases")
 
 
+def pod_replay():
+    import contextlib
+    import os
+    import subprocess
+
+    from fastapi.testclient import TestClient
+
+    from bee_code_interpreter_b200 import build
+    from code_interpreter.services.http_server import create_http_server
+    from code_interpreter.services.kubernetes_code_executor import KubernetesCodeExecutor
+    from code_interpreter.services.storage import Storage
+
+    server_bin = str(build.build_server())
+    storage = Storage(tempfile.mkdtemp(prefix="bci-golden-store-"))
+
+    class PodIsLocalServer(KubernetesCodeExecutor):
+        """Everything of the reference class except pod acquisition."""
+
+        @contextlib.asynccontextmanager
+        async def executor_pod(self):
+            ws = tempfile.mkdtemp(prefix="bci-golden-pod-")
+            # the pod's /workspace cannot exist in the authoring container: files live in `ws` and are
+            # reported under the name they have in the pod
+            env = dict(os.environ, APP_LISTEN_ADDR="127.0.0.1:8000", APP_WORKSPACE=ws, BCI_WORKSPACE_REPORT_AS="/workspace", BCI_PYTHON=sys.executable,
+                       PYTHONPATH=str(ROOT / "bee_code_interpreter_b200" / "site"))
+            proc = subprocess.Popen([server_bin], env=env, stdout=subprocess.PIPE, text=True)
+            try:
+                assert proc.stdout.readline().startswith("listening on")
+                yield {"status": {"podIP": "127.0.0.1"}}
+            finally:
+                proc.terminate()
+                proc.wait()
+
+    executor = PodIsLocalServer(kubectl=None, executor_image="", container_resources={}, file_storage=storage,
+                                executor_pod_spec_extra={}, executor_pod_queue_target_length=0, executor_pod_name_prefix="x")
+
+    class NoTools:
+        def parse(self, **kw):
+            raise NotImplementedError
+
+        async def execute(self, **kw):
+            raise NotImplementedError
+
+    client = TestClient(create_http_server(executor, NoTools(), ContextVar("request_id", default="")), raise_server_exceptions=False)
+    base = json.loads((OUT / "http_replay.json").read_text())["cases"]
+    cases, ids = [], {}
+    for case in base:
+        if case["name"] in ("timeout", "unknown_object"):
+            continue   # 60 s default timeout of the pod contract / retry back-off of the reference class: not replayed
+        body = json.loads(json.dumps(case["request"]))
+        for path, old in list(body.get("files", {}).items()):
+            body["files"][path] = ids.get(old, old)           # object ids are random per Storage instance
+        r = client.post("/v1/execute", json=body)
+        try:
+            payload = r.json()
+        except Exception:
+            payload = r.text
+        if isinstance(payload, dict) and isinstance(case["response"], dict):
+            for path, new in payload.get("files", {}).items():
+                if path in case["response"].get("files", {}):
+                    ids[case["response"]["files"][path]] = new
+        cases.append({"name": case["name"], "request": case["request"], "status": r.status_code, "response": payload})
+    (OUT / "pod_replay.json").write_text(json.dumps({"cases": cases}, indent=1))
+    print("pod_replay.json:", len(cases), "cases")
+
+
 def numeric():
     data = {}
     for name, dt in [("f32", np.float32), ("f64", np.float64), ("i32", np.int32), ("i64", np.int64)]:
@@ -114,5 +187,10 @@ def numeric():
 
 
 if __name__ == "__main__":
-    http_replay()
-    numeric()
+    which = sys.argv[1:] or ["http", "pod", "numeric"]
+    if "http" in which:
+        http_replay()
+    if "pod" in which:
+        pod_replay()
+    if "numeric" in which:
+        numeric()

@@ -100,3 +100,41 @@ def test_proxy_on_device_matches_numpy(dev):
     assert np.array_equal(np.asarray(np.sort(x)), np.sort(xh))
     k = P.DeviceArray.from_host(be, rng.integers(0, 2**31, 1 << 20, dtype=np.int64))
     assert np.array_equal(np.asarray(np.cumsum(k)), np.cumsum(np.asarray(k)))
+
+
+def test_native_executor_server_runs_scripts_on_the_gpu(executor, tmp_path):
+    """bci-executor-server (the server.rs stand-in) in zygote mode, sharing the executor's broker:
+    POST /execute with the metric script -> the array work shows up as broker jobs."""
+    import http.client
+    import json
+    import os
+    import subprocess
+
+    from bee_code_interpreter_b200 import build
+    from bee_code_interpreter_b200.broker_client import RemoteBackend
+    from bee_code_interpreter_b200.zygote import ZygoteClient
+
+    ws = tmp_path / "workspace"
+    ws.mkdir()
+    z = ZygoteClient()
+    env = dict(os.environ, APP_LISTEN_ADDR="127.0.0.1:0", APP_WORKSPACE=str(ws), BCI_ZYGOTE_SOCKET=z.socket_path,
+               BCI_BROKER_SOCKET=executor.broker.socket_path)
+    proc = subprocess.Popen([str(build.build_server())], env=env, stdout=subprocess.PIPE, text=True)
+    try:
+        port = int(proc.stdout.readline().split()[2].rsplit(":", 1)[1])
+        before = RemoteBackend(executor.broker.socket_path).ping()["stats"]["jobs"]
+        n = 10_000_000
+        c = http.client.HTTPConnection("127.0.0.1", port, timeout=120)
+        for _ in range(4):
+            c.request("POST", "/execute", json.dumps({"source_code": W.benchmark_numpy_source(n), "env": {"BCI_DEBUG_FALLBACK": "1"}}),
+                      {"content-type": "application/json"})
+            r = json.loads(c.getresponse().read())
+            assert r["exit_code"] == 0 and r["stderr"] == "", r
+            v = float(r["stdout"].splitlines()[0].split()[1])
+            assert abs(v / n - 1 / 3) < 6 * np.sqrt(4 / 45 / n)
+        after = RemoteBackend(executor.broker.socket_path).ping()["stats"]["jobs"]
+        assert after - before >= 8                                      # 4 x (rand + fused reduce), none on the CPU
+    finally:
+        proc.terminate()
+        proc.wait(timeout=5)
+        z.close()
