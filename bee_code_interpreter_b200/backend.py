@@ -36,6 +36,14 @@ class LocalBackend:
     def rand(self, n, seed):
         return self._new(n * 8, lambda out: self.dev.rand_f64([out], [n], [seed]))
 
+    def rand_mt19937(self, n, state):
+        """-> (buffer, state after); `state` = 625 uint32 (key + pos)."""
+        box = {}
+
+        def run(out):
+            box["st"] = self.dev.rand_mt19937([out], [n], np.asarray(state, dtype=np.uint32).reshape(1, 625))[0]
+        return self._new(n * 8, run), box["st"]
+
     def ewise_new(self, op, dtype, in0, in1, scalar, n):
         dtype = np.dtype(dtype)
         return self._new(n * dtype.itemsize, lambda out: self.dev.ewise(

@@ -152,6 +152,8 @@ class GpuBroker:
         if kind == W.RAND:
             dev.rand_f64(col(0), col(1), col(2))
             return [None] * len(argl)
+        if kind == W.RAND_MT:
+            return list(dev.rand_mt19937(col(0), col(1), np.stack(col(2))))
         if kind == W.EWISE:
             _, op, dt, has_in1 = key
             dev.ewise(op, dt, col(0), col(1) if has_in1 else None, None if has_in1 else col(2), col(3), col(4))
@@ -253,6 +255,12 @@ class GpuBroker:
             p = new(n * 8)
             self.submit((W.RAND,), (p, n, s0))
             return p, b""
+        if op == W.RAND_MT:
+            if len(payload) != 4 * W.MT_STATE_WORDS:
+                raise L.BciError(L.ERR_INVALID, "MT19937 state must be 625 words")
+            p = new(n * 8)
+            after = self.submit((W.RAND_MT,), (p, n, np.frombuffer(payload, dtype="<u4").copy()))
+            return p, np.asarray(after, dtype="<u4").tobytes()
         if op == W.EWISE:
             nb = n * dt.itemsize
             has_in1 = bool(flags & W.F_IN1)

@@ -145,6 +145,13 @@ class RemoteBackend:
     def rand(self, n, seed):
         return self._call(W.RAND, n=int(n), s0=int(seed) & 0xFFFFFFFFFFFFFFFF)[0]
 
+    def rand_mt19937(self, n, state):
+        st = np.ascontiguousarray(state, dtype="<u4")
+        if st.size != W.MT_STATE_WORDS:
+            raise L.BciError(L.ERR_INVALID, "MT19937 state must be 625 words")
+        ptr, payload = self._call(W.RAND_MT, n=int(n), payload=st.tobytes())
+        return ptr, np.frombuffer(payload, dtype="<u4", count=W.MT_STATE_WORDS).copy()
+
     def ewise_new(self, op, dtype, in0, in1, scalar, n):
         code = _code(dtype)
         isf = code in (L.F32, L.F64)

@@ -40,6 +40,7 @@ struct Job {
   const void* host_data = nullptr;  // sha256 of host bytes
   size_t host_len = 0;
   bci_sha256_state* state = nullptr;
+  uint32_t* mt_state = nullptr;     // BRK_RAND_MT: 625 words, updated in place
   // results
   int status = BCI_OK;
   uint64_t value = 0;
@@ -102,6 +103,13 @@ int run_group(std::vector<Job*>& grp) {
       std::vector<uint64_t> seeds(B);
       for (int i = 0; i < B; ++i) seeds[i] = grp[i]->rq.s0;
       return bci_rand_f64(B, out.data(), n.data(), seeds.data());
+    }
+    case BRK_RAND_MT: {
+      std::vector<uint32_t> st((size_t)B * BCI_MT19937_STATE_WORDS);
+      for (int i = 0; i < B; ++i) memcpy(&st[(size_t)i * BCI_MT19937_STATE_WORDS], grp[i]->mt_state, 4 * BCI_MT19937_STATE_WORDS);
+      int rc = bci_rand_mt19937_f64(B, out.data(), n.data(), st.data());
+      if (rc == BCI_OK) for (int i = 0; i < B; ++i) memcpy(grp[i]->mt_state, &st[(size_t)i * BCI_MT19937_STATE_WORDS], 4 * BCI_MT19937_STATE_WORDS);
+      return rc;
     }
     case BRK_EWISE: {
       std::vector<bci_scalar> sc(B);
@@ -376,6 +384,20 @@ void serve(int fd) {
           const bool scalar_result = rq.op == BRK_REDUCE || rq.op == BRK_REDUCE_FUSED || rq.op == BRK_ARGEXT;
           ok = reply(fd, BCI_OK, scalar_result ? job.value : job.out_ptr, nullptr, 0);
         }
+        break;
+      }
+      case BRK_RAND_MT: {
+        if (payload.size() != 4 * BCI_MT19937_STATE_WORDS) { ok = reply_err(fd, BCI_ERR_INVALID, "broker: MT19937 state must be 625 words"); break; }
+        Job job;
+        job.rq = rq;
+        uint32_t st[BCI_MT19937_STATE_WORDS];
+        memcpy(st, payload.data(), sizeof st);
+        job.mt_state = st;
+        int rc = new_buf((size_t)rq.n * 8, &job.out_ptr);
+        if (rc != BCI_OK) { ok = reply_err(fd, rc, bci_last_error()); break; }
+        submit_and_wait(job);
+        if (job.status != BCI_OK) { drop(job.out_ptr); ok = reply_err(fd, job.status, job.error); }
+        else ok = reply(fd, BCI_OK, job.out_ptr, st, sizeof st);
         break;
       }
       case BRK_SHA256_FILE: case BRK_SHA256_BYTES: {

@@ -276,6 +276,15 @@ def rand_f64(out_ptrs: Sequence[int], ns: Sequence[int], seeds: Iterable[int]) -
     _lib.check(_lib.load().bci_rand_f64(len(out_ptrs), _lib.ptr_array(out_ptrs), _lib.size_array(ns), arr))
 
 
+def rand_mt19937(out_ptrs: Sequence[int], ns: Sequence[int], states: np.ndarray) -> np.ndarray:
+    """numpy's legacy generator: `states` is (B, 625) uint32 = key[624] + pos per request
+    (numpy.random.get_state()); returns the states after drawing ns[i] doubles into out_ptrs[i]."""
+    st = np.array(states, dtype=np.uint32, order="C").reshape(len(out_ptrs), 625)
+    _lib.check(_lib.load().bci_rand_mt19937_f64(len(out_ptrs), _lib.ptr_array(out_ptrs), _lib.size_array(ns),
+                                                st.ctypes.data_as(C.POINTER(C.c_uint32))))
+    return st
+
+
 def matmul_f32(a_ptrs: Sequence[int], b_ptrs: Sequence[int], c_ptrs: Sequence[int], M: int, N: int, K: int) -> None:
     _lib.check(_lib.load().bci_matmul_f32(len(a_ptrs), _lib.ptr_array(a_ptrs), _lib.ptr_array(b_ptrs),
                                           _lib.ptr_array(c_ptrs), int(M), int(N), int(K)))

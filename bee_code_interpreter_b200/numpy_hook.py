@@ -97,8 +97,10 @@ def _build_view():
 
     def _device_uniform(shape, fallback):
         try:
-            if _state["seeded"] or _size_of(shape) < _state["min_rand"]:
+            if _size_of(shape) < _state["min_rand"]:
                 return fallback()
+            if _state["seeded"]:   # deterministic stream: the device continues numpy's MT19937 sequence
+                return P.device_rand_legacy(_backend(), tuple(int(s) for s in shape), real_random)
             seed = int.from_bytes(os.urandom(8), "little")
             return P.device_rand(_backend(), tuple(int(s) for s in shape), seed)
         except Exception as e:

@@ -520,6 +520,23 @@ def device_rand(backend, shape, seed: int) -> DeviceArray:
     return DeviceArray(backend, backend.rand(n, seed), shape, np.float64)
 
 
+def device_rand_legacy(backend, shape, random_module) -> DeviceArray:
+    """numpy.random.rand / random_sample on the SEEDED global generator: the MT19937 state goes
+    to the device, the same stream comes back bit for bit, and the advanced state is put back so
+    that host draws before and after this call stay on numpy's sequence."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    name, key, pos, has_gauss, cached = random_module.get_state()
+    if name != "MT19937":
+        raise _Fallback("generator")
+    state = np.empty(625, dtype=np.uint32)
+    state[:624], state[624] = key, pos
+    ptr, after = backend.rand_mt19937(n, state)
+    random_module.set_state((name, np.asarray(after[:624], dtype=np.uint32), int(after[624]), has_gauss, cached))
+    return DeviceArray(backend, ptr, shape, np.float64)
+
+
 def offload(backend, arr):
     """Host ndarray -> DeviceArray when it is big enough to pay for the PCIe hop."""
     if isinstance(arr, DeviceArray):

@@ -167,6 +167,13 @@ int bci_argsort(int dtype, int B, const void* const* in, int64_t* const* out_idx
  * (same 53-bit construction and distribution, not the MT19937 stream). */
 int bci_rand_f64(int B, void* const* out, const size_t* n, const uint64_t* seed);
 
+/* ---- K8b the SEEDED legacy generator, bit-exact: numpy.random.seed(s); numpy.random.rand(n)
+ * (examples/using_imports.py:20-22 seeds the global MT19937).  states = B x 625 uint32 in host
+ * memory, each numpy's get_state(): key[624] followed by pos (0..624); on return it is the
+ * state after drawing n[i] doubles, ready for numpy's set_state().  out[i]: n[i] float64. */
+#define BCI_MT19937_STATE_WORDS 625
+int bci_rand_mt19937_f64(int B, void* const* out, const size_t* n, uint32_t* states);
+
 /* ---- K3 numpy.matmul for 2-D float32, C[i] = A[i] (MxK) @ Bm[i] (KxN), row-major.
  * 3xTF32 split on tcgen05 with fp32 accumulation in TMEM (error ~1e-7 normwise). */
 int bci_matmul_f32(int B, const void* const* A, const void* const* Bm, void* const* C,

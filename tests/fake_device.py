@@ -182,6 +182,19 @@ def rand_f64(out_ptrs, ns, seeds):
         _view(p, n, np.float64)[:] = O.rand_f64(n, s)
 
 
+def rand_mt19937(out_ptrs, ns, states):
+    """numpy's own MT19937 is the oracle here: set_state -> random_sample -> get_state."""
+    calls.append(("rand_mt", len(out_ptrs), None))
+    states = np.array(states, dtype=np.uint32).reshape(len(out_ptrs), 625)
+    for i, (p, n) in enumerate(zip(out_ptrs, ns)):
+        rs = np.random.RandomState()
+        rs.set_state(("MT19937", states[i, :624].copy(), int(states[i, 624]), 0, 0.0))
+        _view(p, n, np.float64)[:] = rs.random_sample(n)
+        st = rs.get_state()
+        states[i, :624], states[i, 624] = st[1], st[2]
+    return states
+
+
 def matmul_f32(a_ptrs, b_ptrs, c_ptrs, M, N, K):
     calls.append(("matmul", len(a_ptrs), (M, N, K)))
     for a, b, c in zip(a_ptrs, b_ptrs, c_ptrs):

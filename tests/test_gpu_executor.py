@@ -138,3 +138,26 @@ def test_native_executor_server_runs_scripts_on_the_gpu(executor, tmp_path):
         proc.terminate()
         proc.wait(timeout=5)
         z.close()
+
+
+def test_seeded_script_gets_numpys_stream_from_the_gpu(executor):
+    """np.random.seed(...) + np.random.rand(big): the device continues MT19937 bit for bit and
+    hands the state back, so the script prints exactly what it prints on a CPU."""
+    src = ("import numpy as np\n"
+           "np.random.seed(20240921)\n"
+           "a = np.random.rand(5)\n"
+           "x = np.random.rand(3_000_001)\n"
+           "b = np.random.rand(2)\n"
+           "print(type(x).__name__)\n"
+           "print(repr(float(x[0])), repr(float(x[1_500_000])), repr(float(x[-1])))\n"
+           "print(repr(a.tolist()), repr(b.tolist()))\n"
+           "print(repr(float(np.max(x))), int(np.argmax(x)))\n")
+    r = asyncio.run(executor.execute(src, env={"BCI_DEBUG_FALLBACK": "1"}))
+    assert r.exit_code == 0 and r.stderr == "", r.stderr
+    np.random.seed(20240921)
+    a = np.random.rand(5); x = np.random.rand(3_000_001); b = np.random.rand(2)
+    lines = r.stdout.splitlines()
+    assert lines[0] == "DeviceArray"
+    assert lines[1] == f"{float(x[0])!r} {float(x[1_500_000])!r} {float(x[-1])!r}"
+    assert lines[2] == f"{a.tolist()!r} {b.tolist()!r}"
+    assert lines[3] == f"{float(np.max(x))!r} {int(np.argmax(x))}"

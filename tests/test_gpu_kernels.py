@@ -492,3 +492,42 @@ def test_single_pass_forms_agree_with_the_multi_pass_fallbacks(dev, bufs, which,
         assert np.array_equal(dev.download(ci, n, np.int64), np.cumsum(ki))
         ga, gb = dev.download(a, n, np.float64), dev.download(b, n, np.float64)
         assert np.allclose(ga, gb, rtol=1e-12, atol=1e-9) and np.allclose(ga, np.cumsum(x), rtol=1e-12, atol=1e-9)
+
+
+def test_rand_mt19937_continues_numpys_legacy_stream_bit_for_bit(dev, bufs):
+    """K8b: seeded numpy.random.rand on the device.  Oracle = numpy's own MT19937
+    (RandomState.set_state / random_sample / get_state), every case bit-exact, including the
+    generator state handed back (examples/using_imports.py:20-22 seeds the global generator)."""
+    cases = []   # (seed, doubles drawn on the host first, n)
+    for seed, pre, n in [(0, 0, 1), (1, 0, 311), (2, 0, 312), (3, 0, 313), (42, 0, 624), (42, 1, 625), (7, 311, 2),
+                         (7, 312, 1), (123456789, 5, 100_003), (2**32 - 1, 623, 1_000_000), (99, 0, 3_000_001), (5, 2, 0)]:
+        cases.append((seed, pre, n))
+    states, want, want_state, outs = [], [], [], []
+    for seed, pre, n in cases:
+        rs = np.random.RandomState(seed)
+        if pre % 2:                     # an odd number of 32-bit words consumed: pairs straddle blocks
+            rs.randint(0, 2**31 - 1)    # legacy randint on a < 2^32 range draws one 32-bit word
+        rs.random_sample(pre // 2)      # `pre` = 32-bit words consumed before the device takes over
+        st = rs.get_state()
+        states.append(np.concatenate([st[1], [st[2]]]).astype(np.uint32))
+        want.append(rs.random_sample(n))
+        st2 = rs.get_state()
+        want_state.append(np.concatenate([st2[1], [st2[2]]]).astype(np.uint32))
+        outs.append(bufs.new(max(8 * n, 8)))
+    assert any(int(s[624]) % 2 == 1 for s in states)                                   # odd positions are covered
+    after = dev.rand_mt19937(outs, [c[2] for c in cases], np.stack(states))
+    for (seed, pre, n), p, w, ws, a in zip(cases, outs, want, want_state, after):
+        got = dev.download(p, n, np.float64)
+        assert np.array_equal(got, w), (seed, pre, n)
+        if n:
+            assert np.array_equal(a, ws), (seed, pre, n)
+    # and the returned state really continues the stream
+    rs = np.random.RandomState()
+    rs.set_state(("MT19937", after[8][:624], int(after[8][624]), 0, 0.0))
+    ref = np.random.RandomState(123456789)
+    ref.randint(0, 2**31 - 1); ref.random_sample(2); ref.random_sample(100_003)
+    assert np.array_equal(rs.random_sample(10), ref.random_sample(10))
+    with pytest.raises(L.BciError):
+        bad = np.stack(states[:1]).copy()
+        bad[0, 624] = 700
+        dev.rand_mt19937(outs[:1], [1], bad)

@@ -152,10 +152,18 @@ def test_hook_gives_agent_code_the_view_and_libraries_the_real_module(be):
     assert isinstance(x, P.DeviceArray) and x.shape == (500,)
     assert isinstance(view.random.rand(10), np.ndarray)                                   # below the offload floor
     assert isinstance(view.random.rand(), float)
-    view.random.seed(42)                                                                  # seeded => numpy's MT19937 stream
-    a = view.random.rand(500)
+    # seeded => numpy's MT19937 stream, continued on the device and handed back: draws before,
+    # on and after the device stay on ONE sequence (odd number of host draws first: pairs straddle)
+    view.random.seed(42)
+    h0 = view.random.rand(7)                                                              # host (small)
+    a = view.random.rand(500)                                                             # device
+    h1 = view.random.rand(3)                                                              # host again
+    b = view.random.random_sample((10, 60))                                               # device, 2-D
     np.random.seed(42)
-    assert isinstance(a, np.ndarray) and np.array_equal(a, np.random.rand(500))
+    want = np.random.rand(7 + 500 + 3 + 600)
+    assert isinstance(h0, np.ndarray) and isinstance(a, P.DeviceArray) and isinstance(b, P.DeviceArray)
+    assert np.array_equal(np.concatenate([h0, np.asarray(a), h1, np.asarray(b).ravel()]), want)
+    assert ("rand_mt", 1, None) in fake_device.calls
     big = np.random.default_rng(0).random(P.OFFLOAD_MIN_ELEMS).astype(np.float32)
     s = view.sort(big)
     assert isinstance(s, P.DeviceArray) and np.array_equal(np.asarray(s), np.sort(big))
@@ -208,6 +216,17 @@ def test_broker_batches_concurrent_clients_and_scopes_buffers(built):
         big = np.random.default_rng(1).random(50_000)
         pb = a.upload(big)
         assert np.array_equal(a.download(pb, big.size, big.dtype), big)
+        # seeded legacy generator over the wire: state in, same stream + advanced state out
+        rs = np.random.RandomState(1234)
+        rs.random_sample(5)                                                           # odd position in the block
+        st = rs.get_state()
+        state = np.concatenate([st[1], [st[2]]]).astype(np.uint32)
+        pm, after = a.rand_mt19937(1001, state)
+        assert np.array_equal(a.download(pm, 1001, np.float64), rs.random_sample(1001))
+        st2 = rs.get_state()
+        assert np.array_equal(after[:624], st2[1]) and int(after[624]) == st2[2]
+        with pytest.raises(L.BciError):
+            a.rand_mt19937(10, state[:100])
         a.close(); b.close()
         import time
 
