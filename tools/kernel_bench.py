@@ -130,6 +130,17 @@ def main():
     outs = [dev.alloc(n1 * 8) for _ in range(B1)]
     ns = [n1] * B1
     add("rand_f64 (K8)", f"C1 n=1e8 f64 x{B1}", 8 * n1 * B1, timed(k_rand(bufs, ns), flush=False))
+    # seeded legacy stream: one CTA per request, so B >= SM count shows the device rate and B = 1 the per-stream rate
+    rs0 = np.random.RandomState(1).get_state()
+    st0 = np.concatenate([rs0[1], [rs0[2]]]).astype(np.uint32)
+    for Bm, nm in ((1, 10**7), (len(bufs), 10**7), (296, 2 * 10**6)):
+        tgt = [bufs[i % len(bufs)] + (i // len(bufs)) * nm * 8 for i in range(Bm)]
+        sts = np.tile(st0, (Bm, 1))
+        o_, n_ = L.ptr_array(tgt), L.size_array([nm] * Bm)
+        stp = sts.ctypes.data_as(C.POINTER(C.c_uint32))
+        ms = timed(lambda: L.check(lib.bci_rand_mt19937_f64(Bm, o_, n_, stp)), iters=3, warm=1, flush=False)
+        add("rand_mt19937 seeded (K8b)", f"n={nm:.0e} x{Bm}", 8 * nm * Bm, ms,
+            extra={"bound": "issue rate of one SM per stream (sequential generator)", "GBps_per_stream": 8 * nm / (ms / 1e3) / 1e9})
     add("ewise square f64 (K1)", f"C1 n=1e8 x{B1}", 16 * n1 * B1, timed(k_ewise(L.EW_SQUARE, np.float64, bufs, None, None, outs, ns), flush=False))
     add("reduce sum f64 (K2)", f"C1 n=1e8 x{B1}", 8 * n1 * B1, timed(k_reduce(L.RED_SUM, np.float64, bufs, ns), flush=False))
     add("reduce sum(square) f64 fused (K1+K2)", f"C1 n=1e8 x{B1}", 24 * n1 * B1,
