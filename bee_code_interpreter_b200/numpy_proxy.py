@@ -242,7 +242,23 @@ class DeviceArray(NDArrayOperatorsMixin):
     def argmax(self, axis=None, out=None, **kw): return argmax(self, axis=axis, out=out, **kw)
     def argmin(self, axis=None, out=None, **kw): return argmin(self, axis=axis, out=out, **kw)
     def cumsum(self, axis=None, dtype=None, out=None): return cumsum(self, axis=axis, dtype=dtype, out=out)
-    def dot(self, other): return matmul(self, other) if self.ndim == 2 else np.dot(np.asarray(self), np.asarray(other))
+    def dot(self, other):
+        try:
+            return _dot(self, other)
+        except (_Fallback, L.Unsupported, L.BciError):
+            return np.dot(np.asarray(self), np.asarray(other))
+
+    def var(self, axis=None, dtype=None, out=None, ddof=0, **kw):
+        try:
+            return _var(self, axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
+        except (_Fallback, L.Unsupported, L.BciError):
+            return np.asarray(self).var(axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
+
+    def std(self, axis=None, dtype=None, out=None, ddof=0, **kw):
+        try:
+            return _std(self, axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
+        except (_Fallback, L.Unsupported, L.BciError):
+            return np.asarray(self).std(axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
 
     def astype(self, dtype, *a, **kw):
         if np.dtype(dtype) == self._dtype and not a and not kw:
@@ -498,13 +514,42 @@ def matmul(a, b, out=None, **kw):
 def _dot(a, b, out=None):
     if isinstance(a, DeviceArray) and isinstance(b, DeviceArray) and a.ndim == 2 and b.ndim == 2:
         return matmul(a, b, out=out)
+    # 1-D . 1-D = sum(a * b): one fused kernel, the product never reaches HBM
+    if (out is None and isinstance(a, DeviceArray) and isinstance(b, DeviceArray) and a.ndim == 1 and b.ndim == 1
+            and a.shape == b.shape and a.dtype == b.dtype and a.dtype in (np.float32, np.float64, np.int64) and a.size
+            and a._backend is b._backend):
+        return _result_scalar(a._backend.reduce_fused(L.RED_SUM, L.EW_MUL, a.dtype, [a._device_ptr()], [b._device_ptr()],
+                                                      None, [a.size])[0])
     raise _Fallback("dot")
+
+
+def _var(a, axis=None, dtype=None, out=None, ddof=0, **kw):
+    """numpy.var for a float array, full reduction: mean(|a - mean(a)|^2) * n / (n - ddof) — numpy's
+    own two-pass formula (numpy/_core/_methods.py:_var), each pass one kernel; `a - mean` and its
+    square are never materialised."""
+    a = _need_dev(a)
+    plain = (axis is None or (a.ndim == 1 and axis in (0, -1))) and dtype is None and out is None and \
+        all(v in (False, np._NoValue, None) or (k == "where" and v is True) for k, v in kw.items()) and \
+        all(k in ("keepdims", "where", "mean", "correction") for k in kw)
+    if not plain or a.dtype.kind != "f" or a.dtype not in SUPPORTED or a.size == 0:
+        raise _Fallback("var kwargs")
+    if isinstance(ddof, bool) or not isinstance(ddof, (int, float)) or a.size - ddof <= 0:
+        raise _Fallback("ddof")
+    be, n = a._backend, a.size
+    ptr = a._device_ptr()                                    # read twice: materialise a deferred producer once
+    mean = be.reduce(L.RED_MEAN, a.dtype, [ptr], [n])[0]
+    msq = be.reduce_fused(L.RED_MEAN, L.EW_SUB, a.dtype, [ptr], None, [float(mean)], [n], pre=L.PRE_SQUARE)[0]
+    return a.dtype.type(a.dtype.type(msq) * a.dtype.type(n) / a.dtype.type(n - ddof)) if ddof else a.dtype.type(msq)
+
+
+def _std(a, axis=None, dtype=None, out=None, ddof=0, **kw):
+    return np.sqrt(_var(a, axis=axis, dtype=dtype, out=out, ddof=ddof, **kw))
 
 
 _FUNCTIONS = {
     np.sum: _np_sum, np.mean: _np_mean, np.max: _np_max, np.min: _np_min, np.amax: _np_max, np.amin: _np_min,
     np.argmax: argmax, np.argmin: argmin, np.cumsum: cumsum, np.sort: sort, np.argsort: argsort,
-    np.matmul: matmul, np.dot: _dot,
+    np.matmul: matmul, np.dot: _dot, np.var: _var, np.std: _std,
 }
 
 

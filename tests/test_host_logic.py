@@ -401,3 +401,31 @@ def test_random_expressions_match_numpy(be):
                     assert np.isclose(float(got), float(want), rtol=1e-5 if dt == np.float32 else 1e-11, atol=1e-6)
 
     run()
+
+
+def test_var_std_and_vector_dot_run_as_fused_reductions(be):
+    rng = np.random.default_rng(11)
+    for dt, rtol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+        h = (rng.standard_normal(20_001) * 3 + 5).astype(dt)
+        g = rng.standard_normal(20_001).astype(dt)
+        x, y = P.DeviceArray.from_host(be, h), P.DeviceArray.from_host(be, g)
+        fake_device.calls.clear()
+        v, s, v1 = np.var(x), np.std(x), x.var(ddof=1)
+        assert names(fake_device.calls) == ["reduce", "reduce_fused"] * 3          # two kernels each, nothing materialised
+        assert fake_device.calls[1][2] == (L.RED_MEAN, L.EW_SUB, L.PRE_SQUARE, False)
+        assert isinstance(v, dt) and isinstance(s, dt) and isinstance(v1, dt)
+        assert np.isclose(v, np.var(h), rtol=rtol) and np.isclose(s, np.std(h), rtol=rtol) and np.isclose(v1, h.var(ddof=1), rtol=rtol)
+        assert np.isclose(x.std(ddof=1), h.std(ddof=1), rtol=rtol)
+        fake_device.calls.clear()
+        d = np.dot(x, y)
+        assert names(fake_device.calls) == ["reduce_fused"] and isinstance(d, dt)
+        assert np.isclose(d, np.dot(h, g), rtol=1e-4 if dt == np.float32 else 1e-10)
+        assert np.isclose(x.dot(y), np.dot(h, g), rtol=1e-4 if dt == np.float32 else 1e-10)
+        assert np.isclose(np.var(x * 2.0), np.var(h * dt(2)), rtol=rtol)             # deferred input: materialised once
+    # what the kernels do not take falls back to numpy with numpy's result
+    m = P.DeviceArray.from_host(be, rng.standard_normal((50, 40)))
+    assert np.allclose(np.var(m, axis=0), np.var(np.asarray(m), axis=0))
+    k = P.DeviceArray.from_host(be, np.arange(100, dtype=np.int64))
+    assert np.var(k) == np.var(np.arange(100)) and np.dot(k, k) == np.dot(np.arange(100), np.arange(100))
+    k32 = P.DeviceArray.from_host(be, np.arange(100, dtype=np.int32))
+    assert np.dot(k32, k32) == np.dot(np.arange(100, dtype=np.int32), np.arange(100, dtype=np.int32))
