@@ -251,7 +251,9 @@ def measure_e2e(args, dist, rank, world, local, n):
         return {"value": None, "unit": "requests/s", "error": repr(e)}
     # the host's fork/exit capacity (~4k processes/s on this 128-core box, tools/spawn_scale.py) is
     # shared by all ranks: fewer service processes per GPU when several GPUs are driven at once
-    workers = max(1, args.e2e_workers if args.e2e_workers > 0 else (4 if world == 1 else 2))
+    # (measured: 4 service processes in total give ~3.0-3.2 k req/s whether they feed 1 GPU or 2,
+    # 8 give ~9 k, 16 give ~8.3 k — so 8 in total up to 4 GPUs, 2 per GPU beyond)
+    workers = max(1, args.e2e_workers if args.e2e_workers > 0 else (4 if world <= 2 else 2))
     per_worker = [args.e2e_requests // workers + (1 if i < args.e2e_requests % workers else 0) for i in range(workers)]
     broker = BrokerProcess(device=local)
     procs = []
