@@ -255,13 +255,16 @@ def measure_e2e(args, dist, rank, world, local, n):
     # 8 give ~9 k, 16 give ~8.3 k — so 8 in total up to 4 GPUs, 2 per GPU beyond)
     workers = max(1, args.e2e_workers if args.e2e_workers > 0 else (4 if world <= 2 else 2))
     per_worker = [args.e2e_requests // workers + (1 if i < args.e2e_requests % workers else 0) for i in range(workers)]
+    # forking processes box-wide: the kernel's fork path peaks at 16-32 of them and degrades beyond
+    # (profiles/r1_fork_scale.md), so the warm interpreters per service process shrink with world size
+    zygotes = args.e2e_zygotes if args.e2e_zygotes > 0 else max(1, min(4, 32 // (world * workers)))
     broker = BrokerProcess(device=local)
     procs = []
     try:
         for i in range(workers):
             cmd = [sys.executable, str(ROOT / "bench.py"), "--e2e-worker", "--broker-socket", broker.socket_path,
                    "--n", str(n), "--e2e-requests", str(per_worker[i]), "--e2e-inflight", str(args.e2e_inflight),
-                   "--e2e-zygotes", str(args.e2e_zygotes)]
+                   "--e2e-zygotes", str(zygotes)]
             procs.append(subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True))
         for p in procs:
             line = p.stdout.readline()
@@ -315,7 +318,7 @@ def e2e_worker(args):
     n, requests = args.n, args.e2e_requests
     src = W.benchmark_numpy_source(n)
     shared = types.SimpleNamespace(socket_path=args.broker_socket, close=lambda: None)
-    execu = LocalGpuExecutor(broker=shared, max_inflight=args.e2e_inflight, timeout=300, zygotes=args.e2e_zygotes)
+    execu = LocalGpuExecutor(broker=shared, max_inflight=args.e2e_inflight, timeout=300, zygotes=args.e2e_zygotes or None)
     lat = []
 
     async def one():
@@ -445,7 +448,7 @@ def main():
     ap.add_argument("--e2e-requests", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--e2e-inflight", type=int, default=32)
     ap.add_argument("--e2e-workers", type=int, default=0, help="service processes per GPU in the e2e arm (0 = auto)")
-    ap.add_argument("--e2e-zygotes", type=int, default=4, help="warm interpreters per service process")
+    ap.add_argument("--e2e-zygotes", type=int, default=0, help="warm interpreters per service process (0 = auto)")
     ap.add_argument("--e2e-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--broker-socket", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
