@@ -1,12 +1,15 @@
 // bci_broker.cu — native per-GPU broker (see include/bci_broker.h).
 //
-// Threads: one acceptor, one per connection (blocking reads of 96-byte requests), one
-// dispatcher.  Connection threads validate buffer ownership, allocate result buffers and
-// enqueue a Job; the dispatcher sleeps `coalesce_us` after the first arrival, drains the
+// Threads: one acceptor, one per connection (blocking reads of 96-byte requests), TWO
+// dispatchers.  Connection threads validate buffer ownership, allocate result buffers and
+// enqueue a Job; a dispatcher sleeps `coalesce_us` after the first arrival, drains the
 // queue, groups jobs by op class and issues ONE batched call of the C ABI (bci.h) per group —
 // the "one launch per op class for all concurrent requests" of the north star — then wakes
 // the waiting connection threads with their results.  A failing group is retried job by job
-// so one bad request cannot fail its neighbours.
+// so one bad request cannot fail its neighbours.  Two dispatchers because a result-returning
+// call (reduce, argmax) waits for the GPU outside the library's lock (bci_runtime.cu result
+// slots): while one dispatcher waits, the other drains what arrived meanwhile and launches it
+// behind the running work, so the op stream does not run dry between dispatch cycles.
 #include "bci_common.cuh"
 #include "../../include/bci_broker.h"
 
@@ -56,7 +59,8 @@ struct Broker {
   int listen_fd = -1;
   int coalesce_us = 150;
   std::atomic<bool> running{false};
-  std::thread acceptor, dispatcher;
+  static constexpr int kDispatchers = 2;
+  std::thread acceptor, dispatcher[kDispatchers];
   std::mutex mu;
   std::condition_variable cv_jobs, cv_done;
   std::deque<Job*> queue;
@@ -480,7 +484,7 @@ extern "C" int bci_broker_start(const char* socket_path, int coalesce_us) {
   g.listen_fd = fd;
   g.coalesce_us = coalesce_us;
   g.running = true;
-  g.dispatcher = std::thread(dispatch_loop);
+  for (auto& d : g.dispatcher) d = std::thread(dispatch_loop);
   g.acceptor = std::thread(accept_loop);
   return BCI_OK;
 }
@@ -491,7 +495,8 @@ extern "C" void bci_broker_stop(void) {
   ::close(g.listen_fd);
   g.cv_jobs.notify_all();
   if (g.acceptor.joinable()) g.acceptor.join();
-  if (g.dispatcher.joinable()) g.dispatcher.join();
+  for (auto& d : g.dispatcher)
+    if (d.joinable()) d.join();
   ::unlink(g.path.c_str());
 }
 

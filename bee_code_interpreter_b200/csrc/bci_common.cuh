@@ -13,6 +13,7 @@
 #include <stddef.h>
 #include <string>
 #include <mutex>
+#include <thread>
 #include <atomic>
 #include "../../include/bci.h"
 
@@ -34,10 +35,17 @@ struct Ctx {
   // grow-only scratch (partials, histograms, tile flags)
   uint8_t* scratch = nullptr;
   size_t scratch_bytes = 0;
-  // results coming back to the host (pinned + device)
-  uint8_t* h_result = nullptr;
-  uint8_t* d_result = nullptr;
-  size_t result_bytes = 0;
+  // results coming back to the host: a few (pinned, device) slots, so that a call can drop the
+  // context lock while it waits for ITS results and the next call can already launch
+  struct ResultSlot {
+    uint8_t* h = nullptr;
+    uint8_t* d = nullptr;
+    size_t bytes = 0;
+    bool busy = false;
+    cudaEvent_t done = nullptr;
+  };
+  static constexpr int kResultSlots = 8;
+  ResultSlot rslot[kResultSlots];
   // L2 flush buffer
   uint8_t* flush = nullptr;
   size_t flush_bytes = 0;
@@ -76,8 +84,24 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int stage_upload(const void* host, size_t bytes, void** dptr);
 // Grow-only device scratch; contents undefined. 256-byte aligned.
 int scratch_get(size_t bytes, void** dptr);
-// Pinned host + device result buffers of at least `bytes`.
-int result_get(size_t bytes, void** hptr, void** dptr);
+// Result hand-back without holding the context lock while the GPU works:
+//   { lock; result_acquire(); launch...; result_enqueue_copy(); }   // D2H + event on the op stream
+//   result_wait();                                                     // no lock held
+//   copy out of *hptr; result_release();
+// result_acquire may drop and retake `lk` while it waits for a free slot.
+int result_acquire(std::unique_lock<std::mutex>& lk, size_t bytes, int* slot, void** hptr, void** dptr);
+int result_enqueue_copy(int slot, size_t bytes);
+int result_wait(int slot);
+void result_release(int slot);          // takes the context lock
+void result_release_locked(int slot);   // caller holds it
+struct ResultGuard {   // releases the slot on every exit path
+  int slot = -1;
+  bool lock_held = false;   // true when the guard dies inside the caller's locked region
+  ~ResultGuard() {
+    if (slot < 0) return;
+    if (lock_held) result_release_locked(slot); else result_release(slot);
+  }
+};
 
 // ---------------------------------------------------------------- descriptors
 struct alignas(16) Req {

@@ -451,21 +451,26 @@ static int reduce_common(int op, int pre, int ew_op, bool fused, int dtype, int 
     if (fused && !q.in1 && !scalar) { set_error("bci_reduce_fused: request %d has neither in1 nor scalar", i); return BCI_ERR_INVALID; }
   }
   Ctx& c = ctx();
-  std::lock_guard<std::mutex> lk(c.mu);
   void *h = nullptr, *d = nullptr;
-  int rc = result_get((size_t)B * 8, &h, &d);
-  if (rc != BCI_OK) return rc;
-  BCI_CUDA(cudaMemsetAsync(d, 0, (size_t)B * 8, c.stream));  // empty sums stay 0
-  unsigned long long* dres = reinterpret_cast<unsigned long long*>(d);
-  switch (dtype) {
-    case BCI_F32: rc = dispatch_red<float>(op, pre, fused, reqs.data(), B, dres); break;
-    case BCI_F64: rc = dispatch_red<double>(op, pre, fused, reqs.data(), B, dres); break;
-    case BCI_I32: rc = dispatch_red<int>(op, pre, fused, reqs.data(), B, dres); break;
-    case BCI_I64: rc = dispatch_red<long long>(op, pre, fused, reqs.data(), B, dres); break;
+  ResultGuard guard;
+  {
+    std::unique_lock<std::mutex> lk(c.mu);
+    int rc = result_acquire(lk, (size_t)B * 8, &guard.slot, &h, &d);
+    if (rc != BCI_OK) return rc;
+    BCI_CUDA(cudaMemsetAsync(d, 0, (size_t)B * 8, c.stream));  // empty sums stay 0
+    unsigned long long* dres = reinterpret_cast<unsigned long long*>(d);
+    switch (dtype) {
+      case BCI_F32: rc = dispatch_red<float>(op, pre, fused, reqs.data(), B, dres); break;
+      case BCI_F64: rc = dispatch_red<double>(op, pre, fused, reqs.data(), B, dres); break;
+      case BCI_I32: rc = dispatch_red<int>(op, pre, fused, reqs.data(), B, dres); break;
+      case BCI_I64: rc = dispatch_red<long long>(op, pre, fused, reqs.data(), B, dres); break;
+    }
+    if (rc != BCI_OK) return rc;
+    if ((rc = result_enqueue_copy(guard.slot, (size_t)B * 8)) != BCI_OK) return rc;
   }
+  // the lock is free while the GPU works: the next call (another broker thread) launches behind us
+  int rc = result_wait(guard.slot);
   if (rc != BCI_OK) return rc;
-  BCI_CUDA(cudaMemcpyAsync(h, d, (size_t)B * 8, cudaMemcpyDeviceToHost, c.stream));
-  BCI_CUDA(cudaStreamSynchronize(c.stream));
   memcpy(host_out, h, (size_t)B * 8);
   return BCI_OK;
 }
@@ -527,20 +532,24 @@ extern "C" int bci_argext(int op, int dtype, int B, const void* const* in, const
     if (!in[i]) { set_error("bci_argext: NULL buffer in request %d", i); return BCI_ERR_INVALID; }
   }
   Ctx& c = ctx();
-  std::lock_guard<std::mutex> lk(c.mu);
   void *h = nullptr, *d = nullptr;
-  int rc = result_get((size_t)B * 8, &h, &d);
-  if (rc != BCI_OK) return rc;
-  unsigned long long* dres = reinterpret_cast<unsigned long long*>(d);
-  switch (dtype) {
-    case BCI_F32: rc = launch_argext<float>(op, reqs.data(), B, dres); break;
-    case BCI_F64: rc = launch_argext<double>(op, reqs.data(), B, dres); break;
-    case BCI_I32: rc = launch_argext<int>(op, reqs.data(), B, dres); break;
-    case BCI_I64: rc = launch_argext<long long>(op, reqs.data(), B, dres); break;
+  ResultGuard guard;
+  {
+    std::unique_lock<std::mutex> lk(c.mu);
+    int rc = result_acquire(lk, (size_t)B * 8, &guard.slot, &h, &d);
+    if (rc != BCI_OK) return rc;
+    unsigned long long* dres = reinterpret_cast<unsigned long long*>(d);
+    switch (dtype) {
+      case BCI_F32: rc = launch_argext<float>(op, reqs.data(), B, dres); break;
+      case BCI_F64: rc = launch_argext<double>(op, reqs.data(), B, dres); break;
+      case BCI_I32: rc = launch_argext<int>(op, reqs.data(), B, dres); break;
+      case BCI_I64: rc = launch_argext<long long>(op, reqs.data(), B, dres); break;
+    }
+    if (rc != BCI_OK) return rc;
+    if ((rc = result_enqueue_copy(guard.slot, (size_t)B * 8)) != BCI_OK) return rc;
   }
+  int rc = result_wait(guard.slot);
   if (rc != BCI_OK) return rc;
-  BCI_CUDA(cudaMemcpyAsync(h, d, (size_t)B * 8, cudaMemcpyDeviceToHost, c.stream));
-  BCI_CUDA(cudaStreamSynchronize(c.stream));
   memcpy(host_out, h, (size_t)B * 8);
   return BCI_OK;
 }

@@ -75,22 +75,56 @@ int scratch_get(size_t bytes, void** dptr) {
   return BCI_OK;
 }
 
-int result_get(size_t bytes, void** hptr, void** dptr) {
+int result_acquire(std::unique_lock<std::mutex>& lk, size_t bytes, int* slot, void** hptr, void** dptr) {
   Ctx& c = ctx();
-  if (bytes > c.result_bytes) {
-    BCI_CUDA(cudaStreamSynchronize(c.stream));
-    if (c.h_result) cudaFreeHost(c.h_result);
-    if (c.d_result) cudaFree(c.d_result);
-    c.h_result = nullptr; c.d_result = nullptr; c.result_bytes = 0;
-    size_t nb = (bytes * 2 + 4095) & ~size_t(4095);
-    BCI_CUDA(cudaHostAlloc((void**)&c.h_result, nb, cudaHostAllocDefault));
-    BCI_CUDA(cudaMalloc((void**)&c.d_result, nb));
-    c.result_bytes = nb;
+  int s = -1;
+  for (;;) {
+    for (int i = 0; i < Ctx::kResultSlots; ++i)
+      if (!c.rslot[i].busy) { s = i; break; }
+    if (s >= 0) break;
+    lk.unlock();               // every slot is in flight: let their owners finish
+    std::this_thread::yield();
+    lk.lock();
   }
-  *hptr = c.h_result;
-  *dptr = c.d_result;
+  Ctx::ResultSlot& r = c.rslot[s];
+  if (bytes > r.bytes) {
+    // the slot is free, so nothing on the stream refers to its buffers any more
+    if (r.h) cudaFreeHost(r.h);
+    if (r.d) cudaFree(r.d);
+    r.h = nullptr; r.d = nullptr; r.bytes = 0;
+    size_t nb = (bytes * 2 + 4095) & ~size_t(4095);
+    BCI_CUDA(cudaHostAlloc((void**)&r.h, nb, cudaHostAllocDefault));
+    BCI_CUDA(cudaMalloc((void**)&r.d, nb));
+    r.bytes = nb;
+  }
+  if (!r.done) BCI_CUDA(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
+  r.busy = true;
+  *slot = s;
+  *hptr = r.h;
+  *dptr = r.d;
   return BCI_OK;
 }
+
+int result_enqueue_copy(int slot, size_t bytes) {
+  Ctx& c = ctx();
+  Ctx::ResultSlot& r = c.rslot[slot];
+  BCI_CUDA(cudaMemcpyAsync(r.h, r.d, bytes, cudaMemcpyDeviceToHost, c.stream));
+  BCI_CUDA(cudaEventRecord(r.done, c.stream));
+  return BCI_OK;
+}
+
+int result_wait(int slot) {
+  BCI_CUDA(cudaEventSynchronize(ctx().rslot[slot].done));
+  return BCI_OK;
+}
+
+void result_release(int slot) {
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  c.rslot[slot].busy = false;
+}
+
+void result_release_locked(int slot) { ctx().rslot[slot].busy = false; }
 
 int upload_batch(Req* host_reqs, int B, size_t tile_elems, Batch* out) {
   // one upload: [Req x B][tile_start x (B+1)]
@@ -181,11 +215,15 @@ void bci_shutdown(void) {
   if (c.h_stage) cudaFreeHost(c.h_stage);
   if (c.d_stage) cudaFree(c.d_stage);
   if (c.scratch) cudaFree(c.scratch);
-  if (c.h_result) cudaFreeHost(c.h_result);
-  if (c.d_result) cudaFree(c.d_result);
+  for (auto& r : c.rslot) {
+    if (r.h) cudaFreeHost(r.h);
+    if (r.d) cudaFree(r.d);
+    if (r.done) cudaEventDestroy(r.done);
+    r = Ctx::ResultSlot();
+  }
   if (c.flush) cudaFree(c.flush);
-  c.h_stage = c.d_stage = c.scratch = c.h_result = c.d_result = c.flush = nullptr;
-  c.stage_bytes = c.scratch_bytes = c.result_bytes = c.flush_bytes = 0;
+  c.h_stage = c.d_stage = c.scratch = c.flush = nullptr;
+  c.stage_bytes = c.scratch_bytes = c.flush_bytes = 0;
   cudaEventDestroy(c.ev0);
   cudaEventDestroy(c.ev1);
   if (c.own_stream) cudaStreamDestroy(c.stream);

@@ -476,7 +476,8 @@ struct alignas(16) PipeStage {
 template <typename T>
 __global__ void __launch_bounds__(kWsThreads, 1)
 scan_pipe_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
-                 unsigned long long total_tiles, ulonglong2* __restrict__ st, uint32_t* __restrict__ counter) {
+                 unsigned long long total_tiles, ulonglong2* __restrict__ st, uint32_t* __restrict__ counter,
+                 unsigned int prefetch_dist) {
   using A = typename ScanTypes<T>::Acc;
   using O = typename ScanTypes<T>::Out;
   constexpr int VN = 32 / sizeof(T);
@@ -509,7 +510,8 @@ scan_pipe_kernel(const Req* __restrict__ reqs, const unsigned long long* __restr
 
   if (warp == NW) {
     // ------------------------------------------------------------------ producer
-    int r = 0;  // request of the last tile fetched (tile ids only grow)
+    int r = 0;   // request of the last tile fetched (tile ids only grow)
+    int r2 = 0;  // request of the last tile prefetched
     int tail = 0;  // end markers written: one per look-back warp, so each of them meets one
     for (unsigned it = 0;; ++it) {
       const int s = (int)(it % STAGES);
@@ -555,6 +557,29 @@ scan_pipe_kernel(const Req* __restrict__ reqs, const unsigned long long* __restr
         for (unsigned e = lane; e < (unsigned)TILE; e += 32) dst[e] = e < rem ? a[e] : T(0);
         __syncwarp();
         if (lane == 0) sc_mbar_arrive(&full[s]);
+      }
+      // L2 prefetch of the tile `prefetch_dist` ids ahead (whoever takes it): with the ring full
+      // all the time a bulk copy waits ~9 us in the HBM queue (bytes in flight / bandwidth), which
+      // is most of a stage's residence; a copy that hits L2 frees the stage sooner, and the bytes
+      // in flight towards HBM are no longer bounded by shared memory.
+      const unsigned long long ahead = tile + prefetch_dist;
+      if (prefetch_dist != 0 && ahead < total_tiles) {
+        for (;;) {
+          const int i = r2 + 1 + lane;
+          const bool le = i < B && __ldg(tile_start + i) <= ahead;
+          const int cnt = __popc(__ballot_sync(0xffffffffu, le));
+          r2 += cnt;
+          if (cnt < 32) break;
+        }
+        if (lane == 0) {
+          const Req q2 = reqs[r2];
+          const size_t base2 = (size_t)(ahead - q2.tile_start) * TILE;
+          const size_t rem2 = (size_t)q2.n - base2;
+          const T* a2 = reinterpret_cast<const T*>(q2.in0) + base2;
+          const uint32_t bytes2 = (uint32_t)((rem2 < TILE ? rem2 : TILE) * sizeof(T)) & ~15u;
+          if (bytes2 != 0 && (reinterpret_cast<uintptr_t>(a2) & 15) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a2), "r"(bytes2) : "memory");
+        }
       }
     }
   } else if (warp == NW + 1) {
@@ -715,7 +740,11 @@ static int launch_cumsum_pipe(Req* reqs, int B) {
   }
   unsigned long long grid = (unsigned long long)c.sm_count;
   if (grid > bt.total_tiles) grid = bt.total_tiles;
-  scan_pipe_kernel<T><<<(unsigned)grid, kWsThreads, Pipe<T>::SMEM, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, bt.total_tiles, st, counter);
+  // prefetch distance: one ring's worth of tiles over all SMs by default (BCI_SCAN_PREFETCH=tiles, 0 = off)
+  unsigned int prefetch_dist = (unsigned int)(c.sm_count * Pipe<T>::STAGES);
+  if (const char* pd = getenv("BCI_SCAN_PREFETCH")) prefetch_dist = (unsigned int)atoi(pd);
+  scan_pipe_kernel<T><<<(unsigned)grid, kWsThreads, Pipe<T>::SMEM, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, bt.total_tiles, st, counter,
+                                                                              prefetch_dist);
   BCI_CHECK_LAUNCH();
   return BCI_OK;
 }

@@ -223,14 +223,18 @@ sha256_thread_kernel(const ShaMsg* __restrict__ msgs, int B, uint32_t* __restric
 }
 
 // Runs one launch over `B` prepared messages; states come back to `h_states` (B x 8 words).
-static int sha_launch(std::vector<ShaMsg>& msgs, uint32_t* h_states) {
+// Called with the context lock held (`lk`); the digest read-back waits under the lock as before —
+// a hashing launch occupies the op stream for its whole duration anyway.
+static int sha_launch(std::unique_lock<std::mutex>& lk, std::vector<ShaMsg>& msgs, uint32_t* h_states) {
   Ctx& c = ctx();
   const int B = (int)msgs.size();
   void* d_msgs = nullptr;
   int rc = stage_upload(msgs.data(), sizeof(ShaMsg) * (size_t)B, &d_msgs);
   if (rc != BCI_OK) return rc;
   void *h = nullptr, *d = nullptr;
-  rc = result_get((size_t)B * 32, &h, &d);
+  ResultGuard guard;
+  guard.lock_held = true;
+  rc = result_acquire(lk, (size_t)B * 32, &guard.slot, &h, &d);
   if (rc != BCI_OK) return rc;
   // many small messages: thread-per-message fills the lanes; few large: warp-per-message
   const int warp_slots = c.sm_count * 4 * 2;
@@ -243,8 +247,8 @@ static int sha_launch(std::vector<ShaMsg>& msgs, uint32_t* h_states) {
         reinterpret_cast<const ShaMsg*>(d_msgs), B, reinterpret_cast<uint32_t*>(d));
   }
   BCI_CHECK_LAUNCH();
-  BCI_CUDA(cudaMemcpyAsync(h, d, (size_t)B * 32, cudaMemcpyDeviceToHost, c.stream));
-  BCI_CUDA(cudaStreamSynchronize(c.stream));
+  if ((rc = result_enqueue_copy(guard.slot, (size_t)B * 32)) != BCI_OK) return rc;
+  if ((rc = result_wait(guard.slot)) != BCI_OK) return rc;
   memcpy(h_states, h, (size_t)B * 32);
   return BCI_OK;
 }
@@ -267,7 +271,7 @@ extern "C" int bci_sha256(int B, const void* const* data, const size_t* len, int
   BCI_REQUIRE_INIT();
   if (B <= 0 || !data || !len || !digests) { set_error("bci_sha256: bad arguments"); return BCI_ERR_INVALID; }
   Ctx& c = ctx();
-  std::lock_guard<std::mutex> lk(c.mu);
+  std::unique_lock<std::mutex> lk(c.mu);
   std::vector<ShaMsg> msgs((size_t)B);
   uint8_t* staging = nullptr;
   if (!on_device) {
@@ -303,7 +307,7 @@ extern "C" int bci_sha256(int B, const void* const* data, const size_t* len, int
     m.finalize = 1;
   }
   std::vector<uint32_t> states((size_t)B * 8);
-  int rc = sha_launch(msgs, states.data());
+  int rc = sha_launch(lk, msgs, states.data());
   if (staging) cudaFreeAsync(staging, c.stream);
   if (rc != BCI_OK) return rc;
   for (int i = 0; i < B; ++i) state_to_digest(&states[(size_t)i * 8], digests + (size_t)i * 32);
@@ -324,7 +328,7 @@ extern "C" int bci_sha256_init(bci_sha256_state* st) {
 static int sha_absorb(int B, bci_sha256_state* const* st, const void* const* host_data,
                       const size_t* len, bool finalize, uint8_t* digests) {
   Ctx& c = ctx();
-  std::lock_guard<std::mutex> lk(c.mu);
+  std::unique_lock<std::mutex> lk(c.mu);
   // lay out each writer's bytes (buffered head + new data) contiguously in device staging
   std::vector<size_t> offs((size_t)B), take((size_t)B);
   size_t total = 0;
@@ -383,7 +387,7 @@ static int sha_absorb(int B, bci_sha256_state* const* st, const void* const* hos
   int rc = BCI_OK;
   if (!msgs.empty()) {
     std::vector<uint32_t> states(msgs.size() * 8);
-    rc = sha_launch(msgs, states.data());
+    rc = sha_launch(lk, msgs, states.data());
     if (rc == BCI_OK) {
       for (size_t k = 0; k < msgs.size(); ++k) memcpy(st[who[k]]->h, &states[k * 8], 32);
     }

@@ -445,7 +445,9 @@ def main():
     ap.add_argument("--n", type=int, default=10**8, help="array elements per request (benchmark-numpy.py: 1e8)")
     ap.add_argument("--requests", type=int, default=PER_GPU_BATCH, help="requests per GPU per step")
     ap.add_argument("--wave", type=int, default=64, help="requests resident on the GPU at once")
-    ap.add_argument("--e2e-requests", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--e2e-requests", type=int, default=-1,
+                    help="requests per GPU in the e2e arm (-1 = min(steps, 4) batches of 1024: a single batch lasts ~0.3 s, "
+                         "which is mostly ramp-up and tail)")
     ap.add_argument("--e2e-inflight", type=int, default=32)
     ap.add_argument("--e2e-workers", type=int, default=0, help="service processes per GPU in the e2e arm (0 = auto)")
     ap.add_argument("--e2e-zygotes", type=int, default=0, help="warm interpreters per service process (0 = auto)")
@@ -456,14 +458,26 @@ def main():
     ap.add_argument("--ref-budget", type=float, default=150.0)
     args = ap.parse_args()
     world = env_int("WORLD_SIZE", 1)
+    if args.e2e_requests < 0:
+        args.e2e_requests = PER_GPU_BATCH * max(1, min(args.steps, 4))
     if args.gpus != world and world == 1 and args.gpus > 1:
         print("bench.py: --gpus %d needs torchrun (one process per GPU); running 1 GPU" % args.gpus, file=sys.stderr)
     if args.e2e_worker:
         e2e_worker(args)
         return
-    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    # stdout carries ONE line, the JSON: whatever libraries print meanwhile (NCCL's version banner,
+    # torchrun notices) is sent to stderr at the descriptor level
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if out is not None:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
