@@ -740,8 +740,9 @@ static int launch_cumsum_pipe(Req* reqs, int B) {
   }
   unsigned long long grid = (unsigned long long)c.sm_count;
   if (grid > bt.total_tiles) grid = bt.total_tiles;
-  // prefetch distance: one ring's worth of tiles over all SMs by default (BCI_SCAN_PREFETCH=tiles, 0 = off)
-  unsigned int prefetch_dist = (unsigned int)(c.sm_count * Pipe<T>::STAGES);
+  // prefetch distance in tiles (BCI_SCAN_PREFETCH, 0 = off).  Measured, int64 1e7 x 32: off 0.79,
+  // 74 tiles 0.86, 148-592 0.88 (flat), 888 0.81, 1776 0.67 (evicted before use) -> 2 x SMs
+  unsigned int prefetch_dist = (unsigned int)(c.sm_count * 2);
   if (const char* pd = getenv("BCI_SCAN_PREFETCH")) prefetch_dist = (unsigned int)atoi(pd);
   scan_pipe_kernel<T><<<(unsigned)grid, kWsThreads, Pipe<T>::SMEM, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, bt.total_tiles, st, counter,
                                                                               prefetch_dist);
