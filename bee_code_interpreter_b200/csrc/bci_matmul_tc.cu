@@ -72,6 +72,10 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -167,7 +171,7 @@ struct GemmOut { float* C; };
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-              const GemmOut* __restrict__ outs, int N, int K, int raster_group) {
+              const GemmOut* __restrict__ outs, int N, int K, int raster_group, int prefetch_kb) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -230,6 +234,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         tma_load_3d(st + 1 * kTileBytes, &map_a_lo, &full_bar[s], kb * TBK, m0, req);
         tma_load_3d(st + 2 * kTileBytes, &map_b_hi, &full_bar[s], kb * TBK, n0, req);
         tma_load_3d(st + 3 * kTileBytes, &map_b_lo, &full_bar[s], kb * TBK, n0, req);
+        // the 3-stage ring covers ~1.6 us of operand latency; pull the k-block `prefetch_kb` ahead
+        // into L2 now so that its own load is an L2 hit by the time a stage frees up
+        if (prefetch_kb > 0 && kb + prefetch_kb < num_kb) {
+          const int kp = (kb + prefetch_kb) * TBK;
+          tma_prefetch_3d(&map_a_hi, kp, m0, req);
+          tma_prefetch_3d(&map_a_lo, kp, m0, req);
+          tma_prefetch_3d(&map_b_hi, kp, n0, req);
+          tma_prefetch_3d(&map_b_lo, kp, n0, req);
+        }
       }
     }
   } else if (warp == 1) {
@@ -380,6 +393,11 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
   // operand loads of the GEMM by what it saves.)
   int raster_group = 8;
   if (const char* g = getenv("BCI_GEMM_GROUP")) raster_group = atoi(g);
+  // L2 prefetch of the k-block `prefetch_kb` ahead (cp.async.bulk.prefetch.tensor): measured
+  // 4096^3 x 8: off 204 TFLOP/s, 4/8/16/32 ahead 196 — the extra TMA traffic costs more than the
+  // shorter load latency returns, so it stays off (kept as an experiment switch)
+  int prefetch_kb = 0;
+  if (const char* g = getenv("BCI_GEMM_PREFETCH")) prefetch_kb = atoi(g);
   for (int b0 = 0; b0 < B; b0 += slice) {
     const int nb = B - b0 < slice ? B - b0 : slice;
     std::vector<SplitReq> sreq((size_t)nb);
@@ -405,7 +423,7 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
     if ((rc = make_map(&m_bh, bt_hi, N, K, nb)) != BCI_OK) return rc;
     if ((rc = make_map(&m_bl, bt_lo, N, K, nb)) != BCI_OK) return rc;
     gemm3x_kernel<<<dim3((unsigned)(N / TBN), (unsigned)(M / TBM), (unsigned)nb), kGemmThreads, kGemmSmem, c.stream>>>(
-        m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K, raster_group);
+        m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K, raster_group, prefetch_kb);
     BCI_CHECK_LAUNCH();
   }
   return BCI_OK;
