@@ -104,12 +104,30 @@ __device__ __forceinline__ void load_block(const ShaMsg& m, unsigned long long b
     h = t1 + t2;                                              \
   }
 
+// Same round with every addition written as x * one + y, `one` being a kernel argument equal to
+// 1 that ptxas cannot fold (it turns a literal `mad.lo x, 1, y` back into IADD3).  One warp per SM
+// sub-partition makes the round chain ALU-pipe bound (6 SHF + 4 LOP3 + 2 IADD3, two issue cycles
+// each, ncu: ALU pipe 79 %); IMAD issues on the FMA pipe, so the additions move there and 10 ALU
+// instructions per round are left.
+// The dependent chain per round is e -> Sig1(e) (SHF, LOP3) -> ONE three-input add -> new e:
+// everything else that goes into the new e (d + h + W+K) and into the new a (Sig0 + Maj - d) is
+// known a round earlier and is summed off the chain on the FMA pipe.
+#define SHA_ROUND_FMA(a, b, c, d, e, f, g, h, wk, one)                        \
+  {                                                                           \
+    const uint32_t p = d * (one##_b) + (h * (one##_c) + (wk));               \
+    const uint32_t r = d * (one##_m) + (Sig0(a) * (one) + Maj(a, b, c));     \
+    const uint32_t en = Sig1(e) + Ch(e, f, g) + p;                            \
+    h = en * (one) + r;                                                       \
+    d = en;                                                                   \
+  }
+
 // ---- kernel A: warp per message ----------------------------------------------------
 constexpr int kShaWarps = 4;          // warps (= messages) per CTA
 constexpr int kShaRow = 68;           // words per block row in smem: 64 + 4 pad (keeps LDS.128 aligned)
 
 __global__ void __launch_bounds__(kShaWarps * 32)
-sha256_warp_kernel(const ShaMsg* __restrict__ msgs, int B, uint32_t* __restrict__ out_state) {
+sha256_warp_kernel(const ShaMsg* __restrict__ msgs, int B, uint32_t* __restrict__ out_state, uint32_t one,
+                   uint32_t one_b, uint32_t one_c, uint32_t one_m) {  // 1, 1, 1, -1: distinct arguments so the sums cannot be factored
   __shared__ __align__(16) uint32_t swk[kShaWarps][32 * kShaRow];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mi = blockIdx.x * kShaWarps + warp;
@@ -164,14 +182,14 @@ sha256_warp_kernel(const ShaMsg* __restrict__ msgs, int B, uint32_t* __restrict_
 #pragma unroll
       for (int t = 0; t < 64; t += 8) {
         const uint4 x = row[t / 4], y = row[t / 4 + 1];
-        SHA_ROUND(a, b, c, d, e, f, g, h, x.x)
-        SHA_ROUND(h, a, b, c, d, e, f, g, x.y)
-        SHA_ROUND(g, h, a, b, c, d, e, f, x.z)
-        SHA_ROUND(f, g, h, a, b, c, d, e, x.w)
-        SHA_ROUND(e, f, g, h, a, b, c, d, y.x)
-        SHA_ROUND(d, e, f, g, h, a, b, c, y.y)
-        SHA_ROUND(c, d, e, f, g, h, a, b, y.z)
-        SHA_ROUND(b, c, d, e, f, g, h, a, y.w)
+        SHA_ROUND_FMA(a, b, c, d, e, f, g, h, x.x, one)
+        SHA_ROUND_FMA(h, a, b, c, d, e, f, g, x.y, one)
+        SHA_ROUND_FMA(g, h, a, b, c, d, e, f, x.z, one)
+        SHA_ROUND_FMA(f, g, h, a, b, c, d, e, x.w, one)
+        SHA_ROUND_FMA(e, f, g, h, a, b, c, d, y.x, one)
+        SHA_ROUND_FMA(d, e, f, g, h, a, b, c, y.y, one)
+        SHA_ROUND_FMA(c, d, e, f, g, h, a, b, y.z, one)
+        SHA_ROUND_FMA(b, c, d, e, f, g, h, a, y.w, one)
       }
       s0 += a; s1 += b; s2 += c; s3 += d; s4 += e; s5 += f; s6 += g; s7 += h;
     }
@@ -244,7 +262,7 @@ static int sha_launch(std::unique_lock<std::mutex>& lk, std::vector<ShaMsg>& msg
         reinterpret_cast<const ShaMsg*>(d_msgs), B, reinterpret_cast<uint32_t*>(d));
   } else {
     sha256_warp_kernel<<<(B + kShaWarps - 1) / kShaWarps, kShaWarps * 32, 0, c.stream>>>(
-        reinterpret_cast<const ShaMsg*>(d_msgs), B, reinterpret_cast<uint32_t*>(d));
+        reinterpret_cast<const ShaMsg*>(d_msgs), B, reinterpret_cast<uint32_t*>(d), 1u, 1u, 1u, 0xffffffffu);
   }
   BCI_CHECK_LAUNCH();
   if ((rc = result_enqueue_copy(guard.slot, (size_t)B * 32)) != BCI_OK) return rc;
