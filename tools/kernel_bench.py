@@ -190,7 +190,7 @@ def main():
         dev.h2d(k[i], np.roll(hk, i * 1001))
     dev.sync()
     add("argmax f32 (K6)", f"C5 n=1e7 x{B5}", 4 * n5 * B5, timed(k_argext(L.ARGMAX, np.float32, v, ns)))
-    add("cumsum i64 (K7)", f"C5 n=1e7 x{B5}", 16 * n5 * B5, timed(k_inout("bci_cumsum", np.int64, k, ko, ns)), moved_bytes=24 * n5 * B5)
+    add("cumsum i64 (K7)", f"C5 n=1e7 x{B5}", 16 * n5 * B5, timed(k_inout("bci_cumsum", np.int64, k, ko, ns)), moved_bytes=16 * n5 * B5)   # default = single-pass kernel: moves what it must
     for mode in ("legacy", "lookback", "pipe"):
         os.environ["BCI_SCAN"] = mode
         add(f"cumsum i64 [{mode}] (K7)", f"C5 n=1e7 x{B5}", 16 * n5 * B5, timed(k_inout("bci_cumsum", np.int64, k, ko, ns)))
