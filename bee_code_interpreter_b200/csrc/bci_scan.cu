@@ -456,7 +456,7 @@ constexpr int kWsScanWarps = kThreads / 32;              // 8
 constexpr int kWsLbWarps = 4;                            // look-backs of consecutive tiles overlap
 constexpr int kWsThreads = kThreads + (2 + kWsLbWarps) * 32;  // + producer, aggregate, look-back warps
 template <typename T> struct Pipe {
-  static constexpr int SUB = sizeof(T) == 8 ? 4 : 2;                        // 32 / 16 KiB of input per tile
+  static constexpr int SUB = 4;                                              // 32 KiB of input per tile (4096 or 8192 elements)
   static constexpr size_t TILE = (size_t)kThreads * SUB * (32 / sizeof(T)); // 4096 elements
   static constexpr size_t TILE_BYTES = TILE * sizeof(T);
   static constexpr int STAGES = (192 * 1024) / TILE_BYTES > 8 ? 8 : (int)((192 * 1024) / TILE_BYTES);
