@@ -8,7 +8,7 @@
 // => 3 passes of traffic for 2 algorithmic; no inter-CTA waiting, deterministic: the form used
 // for float inputs (0.67 of the algorithmic roofline, 6.6 TB/s of traffic).  Integer inputs take
 // the warp-specialised single-pass kernel further down (`scan_pipe_kernel`, BCI_SCAN=pipe: 2
-// passes, 0.78).  The plain one-tile-per-CTA chained scan (BCI_SCAN=lookback, 0.59) is kept as
+// passes, int64 0.88 / int32 0.86).  The plain one-tile-per-CTA chained scan (BCI_SCAN=lookback, 0.59) is kept as
 // the reference point of that design.  BCI_SCAN=legacy forces the three-pass form.
 // Accumulation type: int32/int64 -> int64 (bit-exact with numpy, two's complement wrap),
 // float64 -> float64, float32 -> float64 rounded once on store (numpy accumulates float32
@@ -754,7 +754,7 @@ template <typename T>
 static int launch_cumsum(Req* reqs, int B) {
   {
     // Measured on B200, int64 1e7 x 32 (tools/prof_scan.py): three-pass 4.42 TB/s algorithmic
-    // (0.67), one-tile-per-CTA look-back 3.88 (0.59), warp-specialised pipeline 5.15 (0.78).
+    // (0.67), one-tile-per-CTA look-back 3.88 (0.59), warp-specialised pipeline 5.15 (0.78), 5.75 (0.88) with the L2 prefetch.
     const char* force = getenv("BCI_SCAN");
     if (force && strcmp(force, "lookback") == 0) return launch_cumsum_lookback<T>(reqs, B);
     if (force && strcmp(force, "pipe") == 0) return launch_cumsum_pipe<T>(reqs, B);
