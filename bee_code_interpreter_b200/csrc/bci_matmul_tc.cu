@@ -10,8 +10,8 @@
 //  1. split_kernel   : A -> A_hi, A_lo (row-major MxK, K contiguous); B -> Bt_hi, Bt_lo
 //                      TRANSPOSED to NxK so that both MMA operands are K-major.  HBM-bound,
 //                      (M*K + K*N) * 12 bytes per request.
-//  2. gemm3x_kernel  : one CTA per 128x128 output tile, K walked in 32-element (128-byte)
-//                      blocks through a 3-stage shared-memory ring:
+//  2. gemm3x_kernel  : one CTA per 128x256 (or 128x128) output tile, K walked in 32-element
+//                      (128-byte) blocks through a 2- (or 3-) stage shared-memory ring:
 //        warp 0  (1 thread) TMA producer: 4 x cp.async.bulk.tensor (A_hi, A_lo, Bt_hi, Bt_lo
 //                 tiles of 128 rows x 128 B, SWIZZLE_128B) per stage, mbarrier complete_tx;
 //        warp 1  (1 thread) MMA issuer: 12 x tcgen05.mma.cta_group::1.kind::tf32 per stage
@@ -24,8 +24,9 @@
 //      Tensor maps are 3-D (k, row, request) over the split planes, which this file lays
 //      out itself, so ONE launch covers every request of the slice (grid.z = request).
 // Tensor-pipe bound in principle (137.4 GFLOP algorithmic per 4096^3 request, x3 issued);
-// this first version is L2-bandwidth limited (64 KiB of operands per 128x128x32 step) — the
-// 2-CTA 256x256 tile with the split done in shared memory is the planned next step.
+// the 128x128 tile was limited by operand delivery (64 KiB per 128x128x32 step, 3 stages = 1.6 us
+// of latency cover: tensor pipe 65 % busy); the 128x256 tile (GemmCfg<256>) moves 25 % fewer
+// operand bytes per flop and runs the GEMM launches at 0.95 of the 3xTF32 ceiling.
 #include "bci_common.cuh"
 #include <cuda.h>
 #include <vector>
@@ -42,6 +43,21 @@ constexpr int kTmemCols = 256;                         // two 128-column accumul
 constexpr int kChunkKB = 4;                            // k-blocks (K=128, 48 MMAs) accumulated inside TMEM before a flush
 constexpr int kGemmThreads = 192;
 constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// The GEMM kernel exists for two CTA tiles.  128x128: 3 stages of 64 KiB.  128x256: one A tile
+// feeds twice the MMA work, i.e. 96 KiB of operands per 128x256x32 step instead of 128 KiB for the
+// same flops (-25 % L2->SM traffic), at the price of a 2-stage ring; 8 epilogue warps (the TMEM
+// lane quadrant is warp % 4, the two warps of a quadrant take 128 columns each).
+template <int BN> struct GemmCfg {
+  static constexpr int kStg = BN == 128 ? 3 : 2;
+  static constexpr int kATile = TBM * TBK * 4;
+  static constexpr int kBTile = BN * TBK * 4;
+  static constexpr int kStage = 2 * kATile + 2 * kBTile;
+  static constexpr int kTmem = 2 * BN;
+  static constexpr int kEpiWarps = BN / 32;
+  static constexpr int kThr = 64 + 32 * kEpiWarps;
+  static constexpr size_t kSmem = (size_t)kStg * kStage + 1024 + 256;
+};
 
 // ---------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,10 +184,15 @@ split_kernel(const SplitReq* __restrict__ reqs, float* __restrict__ a_hi, float*
 // ---------------------------------------------------------------- kernel 2: 3xTF32 GEMM
 struct GemmOut { float* C; };
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN>
+__global__ void __launch_bounds__(GemmCfg<BN>::kThr, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
               const GemmOut* __restrict__ outs, int N, int K, int raster_group, int prefetch_kb) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStg;
+  constexpr int kStageBytes = Cfg::kStage;
+  constexpr int kOffAlo = Cfg::kATile, kOffBhi = 2 * Cfg::kATile, kOffBlo = 2 * Cfg::kATile + Cfg::kBTile;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -198,7 +219,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tile_m = first_m + (lin % per_group) % rows;
     tile_n = (lin % per_group) / rows;
   }
-  const int n0 = tile_n * TBN, m0 = tile_m * TBM, req = blockIdx.z;
+  const int n0 = tile_n * BN, m0 = tile_m * TBM, req = blockIdx.z;
   const int num_kb = K / TBK;
 
   if (warp == 0 && lane == 0) {
@@ -210,11 +231,11 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], Cfg::kEpiWarps); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(Cfg::kTmem) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -230,10 +251,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         mbar_wait(&empty_bar[s], ph ^ 1u);
         uint8_t* st = smem + (size_t)s * kStageBytes;
         mbar_expect_tx(&full_bar[s], kStageBytes);
-        tma_load_3d(st + 0 * kTileBytes, &map_a_hi, &full_bar[s], kb * TBK, m0, req);
-        tma_load_3d(st + 1 * kTileBytes, &map_a_lo, &full_bar[s], kb * TBK, m0, req);
-        tma_load_3d(st + 2 * kTileBytes, &map_b_hi, &full_bar[s], kb * TBK, n0, req);
-        tma_load_3d(st + 3 * kTileBytes, &map_b_lo, &full_bar[s], kb * TBK, n0, req);
+        tma_load_3d(st, &map_a_hi, &full_bar[s], kb * TBK, m0, req);
+        tma_load_3d(st + kOffAlo, &map_a_lo, &full_bar[s], kb * TBK, m0, req);
+        tma_load_3d(st + kOffBhi, &map_b_hi, &full_bar[s], kb * TBK, n0, req);
+        tma_load_3d(st + kOffBlo, &map_b_lo, &full_bar[s], kb * TBK, n0, req);
         // the 3-stage ring covers ~1.6 us of operand latency; pull the k-block `prefetch_kb` ahead
         // into L2 now so that its own load is an L2 hit by the time a stage frees up
         if (prefetch_kb > 0 && kb + prefetch_kb < num_kb) {
@@ -247,7 +268,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TBM, TBN);
+      const uint32_t idesc = umma_idesc_tf32(TBM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
@@ -264,9 +285,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t st = smem_u32(smem + (size_t)s * kStageBytes);
-        const uint64_t a_hi = umma_desc_sw128(st + 0 * kTileBytes), a_lo = umma_desc_sw128(st + 1 * kTileBytes);
-        const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * TBN);
+        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kOffAlo);
+        const uint64_t b_hi = umma_desc_sw128(st + kOffBhi), b_lo = umma_desc_sw128(st + kOffBlo);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
 #pragma unroll
         for (int k = 0; k < TBK / 8; ++k) {
           const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);  // 32 bytes per K-step of 8, in 16-byte units
@@ -279,21 +300,24 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
       }
     }
   } else {
-    // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+    // epilogue warps 2..: TMEM lane quadrant = warp % 4; with 8 of them the two warps of a
+    // quadrant split the accumulator's columns in halves of 128
     const int quad = warp & 3;
+    const int col0 = ((warp - 2) >> 2) * 128;
+    constexpr int EN = 128;  // columns per epilogue thread
     const int num_chunks = (num_kb + kChunkKB - 1) / kChunkKB;
-    float acc[TBN];
+    float acc[EN];
 #pragma unroll
-    for (int j = 0; j < TBN; ++j) acc[j] = 0.f;
+    for (int j = 0; j < EN; ++j) acc[j] = 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < num_chunks; ++ch) {
       const int buf = ch & 1;
       mbar_wait(&tmem_full_bar[buf], ((uint32_t)ch >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < TBN / 32; ++c) {
+      for (int c = 0; c < EN / 32; ++c) {
         uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * TBN + c * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN + col0 + c * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -314,16 +338,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     }
     float* __restrict__ C = outs[req].C;
     const int row = m0 + quad * 32 + lane;
-    float* crow = C + (size_t)row * N + n0;
+    float* crow = C + (size_t)row * N + n0 + col0;
 #pragma unroll
-    for (int j = 0; j < TBN; j += 4)
+    for (int j = 0; j < EN; j += 4)
       *reinterpret_cast<float4*>(crow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::kTmem) : "memory");
   }
 }
 
@@ -347,12 +371,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 3-D map over a [nb][rows][K] float plane: box = 32 (k) x 128 (rows) x 1, 128-byte swizzle
-static int make_map(CUtensorMap* map, float* base, int rows, int K, int nb) {
+static int make_map(CUtensorMap* map, float* base, int rows, int K, int nb, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable in this driver"); return BCI_ERR_CUDA; }
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nb};
   const cuuint64_t strides[2] = {(cuuint64_t)K * 4, (cuuint64_t)rows * K * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)TBM, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -372,7 +396,8 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
   Ctx& c = ctx();
   static bool attr_set = false;
   if (!attr_set) {
-    BCI_CUDA(cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    BCI_CUDA(cudaFuncSetAttribute(gemm3x_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<128>::kSmem));
+    BCI_CUDA(cudaFuncSetAttribute(gemm3x_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<256>::kSmem));
     attr_set = true;
   }
   // slice the batch so the split planes (12 bytes per input element) stay within ~8 GiB of scratch
@@ -398,6 +423,11 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
   // shorter load latency returns, so it stays off (kept as an experiment switch)
   int prefetch_kb = 0;
   if (const char* g = getenv("BCI_GEMM_PREFETCH")) prefetch_kb = atoi(g);
+  // CTA tile width: 256 whenever N allows (measured 4096^3 x 8: 230.5 vs 205.9 TFLOP/s algorithmic
+  // for the 128-wide tile; the GEMM launches alone run at 267 = 0.95 of the 3xTF32 ceiling, the
+  // rest is the split pass); BCI_GEMM_TILE_N=128 forces the narrow tile
+  int tile_n = N % 256 == 0 ? 256 : 128;
+  if (const char* g = getenv("BCI_GEMM_TILE_N")) tile_n = (atoi(g) == 256 && N % 256 == 0) ? 256 : 128;
   for (int b0 = 0; b0 < B; b0 += slice) {
     const int nb = B - b0 < slice ? B - b0 : slice;
     std::vector<SplitReq> sreq((size_t)nb);
@@ -418,12 +448,17 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
         reinterpret_cast<const SplitReq*>(d_sreq), a_hi, a_lo, bt_hi, bt_lo, M, N, K, ta);
     BCI_CHECK_LAUNCH();
     CUtensorMap m_ah, m_al, m_bh, m_bl;
-    if ((rc = make_map(&m_ah, a_hi, M, K, nb)) != BCI_OK) return rc;
-    if ((rc = make_map(&m_al, a_lo, M, K, nb)) != BCI_OK) return rc;
-    if ((rc = make_map(&m_bh, bt_hi, N, K, nb)) != BCI_OK) return rc;
-    if ((rc = make_map(&m_bl, bt_lo, N, K, nb)) != BCI_OK) return rc;
-    gemm3x_kernel<<<dim3((unsigned)(N / TBN), (unsigned)(M / TBM), (unsigned)nb), kGemmThreads, kGemmSmem, c.stream>>>(
-        m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K, raster_group, prefetch_kb);
+    if ((rc = make_map(&m_ah, a_hi, M, K, nb, TBM)) != BCI_OK) return rc;
+    if ((rc = make_map(&m_al, a_lo, M, K, nb, TBM)) != BCI_OK) return rc;
+    if ((rc = make_map(&m_bh, bt_hi, N, K, nb, tile_n)) != BCI_OK) return rc;
+    if ((rc = make_map(&m_bl, bt_lo, N, K, nb, tile_n)) != BCI_OK) return rc;
+    const dim3 grid((unsigned)(N / tile_n), (unsigned)(M / TBM), (unsigned)nb);
+    if (tile_n == 256)
+      gemm3x_kernel<256><<<grid, GemmCfg<256>::kThr, GemmCfg<256>::kSmem, c.stream>>>(
+          m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K, raster_group, prefetch_kb);
+    else
+      gemm3x_kernel<128><<<grid, GemmCfg<128>::kThr, GemmCfg<128>::kSmem, c.stream>>>(
+          m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K, raster_group, prefetch_kb);
     BCI_CHECK_LAUNCH();
   }
   return BCI_OK;
