@@ -400,22 +400,6 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
     BCI_CUDA(cudaFuncSetAttribute(gemm3x_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<256>::kSmem));
     attr_set = true;
   }
-  // slice the batch so the split planes (12 bytes per input element) stay within ~8 GiB of scratch
-  const size_t per_req = ((size_t)M * K + (size_t)N * K) * 8;
-  int slice = (int)((8ull << 30) / (per_req ? per_req : 1));
-  if (slice < 1) slice = 1;
-  if (slice > B) slice = B;
-  if (slice > 65535) slice = 65535;
-  void* sc = nullptr;
-  int rc = scratch_get(per_req * (size_t)slice + 4096, &sc);
-  if (rc != BCI_OK) return rc;
-  float* a_hi = reinterpret_cast<float*>(sc);
-  float* a_lo = a_hi + (size_t)slice * M * K;
-  float* bt_hi = a_lo + (size_t)slice * M * K;
-  float* bt_lo = bt_hi + (size_t)slice * N * K;
-  // (Running the split of slice i+1 on a second stream under the GEMM of slice i was tried: no
-  // gain, 5.35 vs 5.31 ms for 8 x 4096^3 — the HBM-saturating split slows the latency-sensitive
-  // operand loads of the GEMM by what it saves.)
   int raster_group = 8;
   if (const char* g = getenv("BCI_GEMM_GROUP")) raster_group = atoi(g);
   // L2 prefetch of the k-block `prefetch_kb` ahead (cp.async.bulk.prefetch.tensor): measured
@@ -428,25 +412,81 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
   // rest is the split pass); BCI_GEMM_TILE_N=128 forces the narrow tile
   int tile_n = N % 256 == 0 ? 256 : 128;
   if (const char* g = getenv("BCI_GEMM_TILE_N")) tile_n = (atoi(g) == 256 && N % 256 == 0) ? 256 : 128;
-  for (int b0 = 0; b0 < B; b0 += slice) {
-    const int nb = B - b0 < slice ? B - b0 : slice;
-    std::vector<SplitReq> sreq((size_t)nb);
-    std::vector<GemmOut> outs((size_t)nb);
-    for (int i = 0; i < nb; ++i) {
-      sreq[i].A = reinterpret_cast<const float*>(A[b0 + i]);
-      sreq[i].Bm = reinterpret_cast<const float*>(Bm[b0 + i]);
-      outs[i].C = reinterpret_cast<float*>(C[b0 + i]);
+  // Optional two-deep pipeline over slices of the batch (BCI_GEMM_PIPE=1): split(i+1) on a second
+  // stream under gemm(i).  Measured slower both times it was tried (8 x 4096^3: 5.35 vs 5.31 ms
+  // with the 128-wide tile, 5.35 vs 4.75 ms with the 256-wide one): one-matrix slices leave a
+  // 3.46-wave tail per GEMM launch and the HBM-saturating split delays the operand loads.  Off.
+  bool pipe = false;
+  if (const char* g = getenv("BCI_GEMM_PIPE")) pipe = atoi(g) != 0;
+
+  // split planes: hi + lo of A and of B^T, 8 bytes per input element; two buffers when pipelined,
+  // at most ~8 GiB of scratch in total
+  const size_t per_req = ((size_t)M * K + (size_t)N * K) * 8;
+  int cap = (int)((4ull << 30) / (per_req ? per_req : 1));
+  if (cap < 1) cap = 1;
+  int slice = pipe ? (B + 7) / 8 : B;
+  if (slice > cap) slice = cap;
+  if (slice > 65535) slice = 65535;
+  const int n_slices = (B + slice - 1) / slice;
+  const int n_bufs = (pipe && n_slices > 1) ? 2 : 1;
+  void* sc = nullptr;
+  int rc = scratch_get(per_req * (size_t)slice * n_bufs + 4096, &sc);
+  if (rc != BCI_OK) return rc;
+  float* plane0 = reinterpret_cast<float*>(sc);
+  const size_t buf_floats = per_req * (size_t)slice / 4;
+
+  static cudaStream_t split_stream = nullptr;
+  static cudaEvent_t ev_in = nullptr, ev_split[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr};
+  static int pipe_device = -1;
+  if (n_bufs == 2 && pipe_device != c.device) {
+    int lo = 0, hi = 0;
+    BCI_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    BCI_CUDA(cudaStreamCreateWithPriority(&split_stream, cudaStreamNonBlocking, hi));
+    BCI_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+      BCI_CUDA(cudaEventCreateWithFlags(&ev_split[b], cudaEventDisableTiming));
+      BCI_CUDA(cudaEventCreateWithFlags(&ev_gemm[b], cudaEventDisableTiming));
     }
-    void *d_sreq = nullptr, *d_outs = nullptr;
-    rc = stage_upload(sreq.data(), sizeof(SplitReq) * (size_t)nb, &d_sreq);
-    if (rc != BCI_OK) return rc;
-    rc = stage_upload(outs.data(), sizeof(GemmOut) * (size_t)nb, &d_outs);
-    if (rc != BCI_OK) return rc;
-    const unsigned ta = (unsigned)(((size_t)M * K + 4095) / 4096);
-    const unsigned tb = (unsigned)((size_t)(K / 32) * (N / 32));
-    split_kernel<<<dim3(ta + tb, 1, (unsigned)nb), 256, 0, c.stream>>>(
-        reinterpret_cast<const SplitReq*>(d_sreq), a_hi, a_lo, bt_hi, bt_lo, M, N, K, ta);
+    pipe_device = c.device;
+  }
+
+  // every descriptor goes up front: an upload queued behind gemm(i) would serialise split(i+1)
+  std::vector<SplitReq> sreq((size_t)B);
+  std::vector<GemmOut> outs((size_t)B);
+  for (int i = 0; i < B; ++i) {
+    sreq[i].A = reinterpret_cast<const float*>(A[i]);
+    sreq[i].Bm = reinterpret_cast<const float*>(Bm[i]);
+    outs[i].C = reinterpret_cast<float*>(C[i]);
+  }
+  void *d_sreq = nullptr, *d_outs = nullptr;
+  rc = stage_upload(sreq.data(), sizeof(SplitReq) * (size_t)B, &d_sreq);
+  if (rc != BCI_OK) return rc;
+  rc = stage_upload(outs.data(), sizeof(GemmOut) * (size_t)B, &d_outs);
+  if (rc != BCI_OK) return rc;
+  cudaStream_t sstream = c.stream;
+  if (n_bufs == 2) {
+    sstream = split_stream;
+    BCI_CUDA(cudaEventRecord(ev_in, c.stream));   // inputs, descriptors, earlier users of the scratch
+    BCI_CUDA(cudaStreamWaitEvent(split_stream, ev_in, 0));
+  }
+  const unsigned ta = (unsigned)(((size_t)M * K + 4095) / 4096);
+  const unsigned tb = (unsigned)((size_t)(K / 32) * (N / 32));
+  for (int idx = 0; idx < n_slices; ++idx) {
+    const int b0 = idx * slice;
+    const int nb = B - b0 < slice ? B - b0 : slice;
+    const int buf = idx % n_bufs;
+    float* a_hi = plane0 + (size_t)buf * buf_floats;
+    float* a_lo = a_hi + (size_t)slice * M * K;
+    float* bt_hi = a_lo + (size_t)slice * M * K;
+    float* bt_lo = bt_hi + (size_t)slice * N * K;
+    if (n_bufs == 2 && idx >= 2) BCI_CUDA(cudaStreamWaitEvent(split_stream, ev_gemm[buf], 0));  // planes free again
+    split_kernel<<<dim3(ta + tb, 1, (unsigned)nb), 256, 0, sstream>>>(
+        reinterpret_cast<const SplitReq*>(d_sreq) + b0, a_hi, a_lo, bt_hi, bt_lo, M, N, K, ta);
     BCI_CHECK_LAUNCH();
+    if (n_bufs == 2) {
+      BCI_CUDA(cudaEventRecord(ev_split[buf], split_stream));
+      BCI_CUDA(cudaStreamWaitEvent(c.stream, ev_split[buf], 0));
+    }
     CUtensorMap m_ah, m_al, m_bh, m_bl;
     if ((rc = make_map(&m_ah, a_hi, M, K, nb, TBM)) != BCI_OK) return rc;
     if ((rc = make_map(&m_al, a_lo, M, K, nb, TBM)) != BCI_OK) return rc;
@@ -455,11 +495,12 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
     const dim3 grid((unsigned)(N / tile_n), (unsigned)(M / TBM), (unsigned)nb);
     if (tile_n == 256)
       gemm3x_kernel<256><<<grid, GemmCfg<256>::kThr, GemmCfg<256>::kSmem, c.stream>>>(
-          m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K, raster_group, prefetch_kb);
+          m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs) + b0, N, K, raster_group, prefetch_kb);
     else
       gemm3x_kernel<128><<<grid, GemmCfg<128>::kThr, GemmCfg<128>::kSmem, c.stream>>>(
-          m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs), N, K, raster_group, prefetch_kb);
+          m_ah, m_al, m_bh, m_bl, reinterpret_cast<const GemmOut*>(d_outs) + b0, N, K, raster_group, prefetch_kb);
     BCI_CHECK_LAUNCH();
+    if (n_bufs == 2) BCI_CUDA(cudaEventRecord(ev_gemm[buf], c.stream));
   }
   return BCI_OK;
 }
