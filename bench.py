@@ -102,25 +102,41 @@ def c1_step(dev, L, n: int, requests: int, wave: int, seed0: int, timing: dict |
     Per wave: alloc -> ONE rand launch -> ONE fused sum(square) launch -> 8 B/request D2H."""
     import numpy as np
 
-    results = []
-    for w0 in range(0, requests, wave):
+    # Software-pipelined by one wave: the rand launch of wave i+1 is queued BEFORE the host blocks
+    # on wave i's results, so the frees / allocations / descriptor uploads between two waves
+    # (~1 ms of driver calls per 64 requests) happen while the GPU is busy.  Two waves are resident.
+    def launch_rand(w0):
         b = min(wave, requests - w0)
         ptrs = [dev.alloc(n * 8) for _ in range(b)]
-        ns = [n] * b
         if timing is not None:
             dev.event_record(0)
-        dev.rand_f64(ptrs, ns, [seed0 + w0 + j for j in range(b)])
+        dev.rand_f64(ptrs, [n] * b, [seed0 + w0 + j for j in range(b)])
         if timing is not None:
             dev.event_record(1)
-        res = dev.reduce(L.RED_SUM, np.float64, ptrs, ns, pre=L.PRE_SQUARE)
+        return ptrs
+
+    results = []
+    starts = list(range(0, requests, wave))
+    cur = launch_rand(starts[0])
+    for k, w0 in enumerate(starts):
+        rand_ms = dev.event_elapsed(0, 1) if timing is not None and k == 0 else None
+        nxt = launch_rand(starts[k + 1]) if k + 1 < len(starts) else None
         if timing is not None:
             dev.event_record(2)
-            timing["rand_ms"].append(dev.event_elapsed(0, 1))
-            timing["sumsq_ms"].append(dev.event_elapsed(1, 2))
-            timing["wave_b"].append(b)
-        for p in ptrs:
+        res = dev.reduce(L.RED_SUM, np.float64, cur, [n] * len(cur), pre=L.PRE_SQUARE)
+        if timing is not None:
+            dev.event_record(3)
+            # events 0/1 now bracket the NEXT wave's rand launch (read after the reduce has waited)
+            timing["sumsq_ms"].append(dev.event_elapsed(2, 3))
+            timing["wave_b"].append(len(cur))
+            if rand_ms is not None:
+                timing["rand_ms"].append(rand_ms)
+            if nxt is not None:
+                timing["rand_ms"].append(dev.event_elapsed(0, 1))
+        for p in cur:
             dev.free(p)
         results.extend(res.tolist())
+        cur = nxt
     return results
 
 
@@ -143,7 +159,7 @@ def run_ours(args) -> dict | None:
     n = args.n
     requests = args.requests
     free_b, _total = dev.mem_info()
-    wave = max(1, min(args.wave, int(free_b * 0.8) // (n * 8), requests))
+    wave = max(1, min(args.wave, int(free_b * 0.8) // (2 * n * 8), requests))   # two waves are resident
 
     def barrier():
         dev.sync()
