@@ -65,6 +65,14 @@ struct Broker {
   std::condition_variable cv_jobs, cv_done;
   std::deque<Job*> queue;
   std::atomic<uint64_t> n_jobs{0}, n_batches{0}, max_batch{0}, n_conn{0};
+  // connection workers: a fixed pool fed by the acceptor.  One script process = one connection, so
+  // connections arrive at the request rate; creating a thread per connection inside a process
+  // that holds a CUDA context (a very large address space) was the broker's per-request ceiling.
+  static constexpr int kConnWorkers = 384;
+  std::vector<std::thread> conn_workers;
+  std::mutex conn_mu;
+  std::condition_variable cv_conn;
+  std::deque<int> conn_fds;
 };
 
 Broker g;
@@ -455,7 +463,25 @@ void accept_loop() {
       break;
     }
     g.n_conn++;
-    std::thread(serve, fd).detach();
+    {
+      std::lock_guard<std::mutex> lk(g.conn_mu);
+      g.conn_fds.push_back(fd);
+    }
+    g.cv_conn.notify_one();
+  }
+}
+
+void conn_worker_loop() {
+  for (;;) {
+    int fd = -1;
+    {
+      std::unique_lock<std::mutex> lk(g.conn_mu);
+      g.cv_conn.wait(lk, [] { return !g.conn_fds.empty() || !g.running.load(); });
+      if (g.conn_fds.empty()) return;  // stopping
+      fd = g.conn_fds.front();
+      g.conn_fds.pop_front();
+    }
+    serve(fd);
   }
 }
 
@@ -485,6 +511,8 @@ extern "C" int bci_broker_start(const char* socket_path, int coalesce_us) {
   g.coalesce_us = coalesce_us;
   g.running = true;
   for (auto& d : g.dispatcher) d = std::thread(dispatch_loop);
+  g.conn_workers.clear();
+  for (int i = 0; i < Broker::kConnWorkers; ++i) g.conn_workers.emplace_back(conn_worker_loop);
   g.acceptor = std::thread(accept_loop);
   return BCI_OK;
 }
@@ -497,6 +525,18 @@ extern "C" void bci_broker_stop(void) {
   if (g.acceptor.joinable()) g.acceptor.join();
   for (auto& d : g.dispatcher)
     if (d.joinable()) d.join();
+  {
+    // wake idle workers; a worker still serving a connection returns when its client goes away
+    std::lock_guard<std::mutex> lk(g.conn_mu);
+    for (int fd : g.conn_fds) ::close(fd);
+    g.conn_fds.clear();
+  }
+  g.cv_conn.notify_all();
+  for (auto& w : g.conn_workers) {
+    if (!w.joinable()) continue;
+    w.detach();   // never block shutdown on a client that keeps its socket open
+  }
+  g.conn_workers.clear();
   ::unlink(g.path.c_str());
 }
 

@@ -274,12 +274,17 @@ def measure_e2e(args, dist, rank, world, local, n):
     # forking processes box-wide: the kernel's fork path peaks at 16-32 of them and degrades beyond
     # (profiles/r1_fork_scale.md), so the warm interpreters per service process shrink with world size
     zygotes = args.e2e_zygotes if args.e2e_zygotes > 0 else max(1, min(4, 32 // (world * workers)))
+    # admission: the fork / set-up phase of a request stretches from ~3 ms to ~25 ms when 128 script
+    # processes are alive at once, so throughput FALLS with the number admitted (tools/e2e_trace.py,
+    # 4 service processes on one GPU: 16 in flight 3.42 k req/s, 32: 3.22 k, 64: 2.88 k, 128: 2.35 k);
+    # 16 per GPU keeps the GPU fed (two dispatch groups) without crowding the host
+    inflight = args.e2e_inflight if args.e2e_inflight > 0 else max(2, 16 // workers)
     broker = BrokerProcess(device=local)
     procs = []
     try:
         for i in range(workers):
             cmd = [sys.executable, str(ROOT / "bench.py"), "--e2e-worker", "--broker-socket", broker.socket_path,
-                   "--n", str(n), "--e2e-requests", str(per_worker[i]), "--e2e-inflight", str(args.e2e_inflight),
+                   "--n", str(n), "--e2e-requests", str(per_worker[i]), "--e2e-inflight", str(inflight),
                    "--e2e-zygotes", str(zygotes)]
             procs.append(subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True))
         for p in procs:
@@ -312,7 +317,7 @@ def measure_e2e(args, dist, rank, world, local, n):
     lat = sorted(x for o in outs for x in o["latencies"])
     src_bytes = len(W.benchmark_numpy_source(n).encode())
     return {"value": args.e2e_requests * world / dt, "unit": "requests/s", "requests_per_gpu": args.e2e_requests,
-            "service_workers_per_gpu": workers, "inflight_per_worker": args.e2e_inflight,
+            "service_workers_per_gpu": workers, "inflight_per_worker": inflight,
             "h2d_bytes_per_step": src_bytes * args.e2e_requests, "d2h_bytes_per_step": 8 * args.e2e_requests,
             "p50_latency_s": lat[len(lat) // 2] if lat else None,
             "parity_6sigma": all(o["parity"] for o in outs),
@@ -346,7 +351,7 @@ def e2e_worker(args):
     async def batch(k):
         return await asyncio.gather(*(one() for _ in range(k)))
 
-    asyncio.run(batch(min(requests, 2 * args.e2e_inflight)))  # warm-up: zygotes, pool growth, page cache
+    asyncio.run(batch(min(requests, max(64, 2 * args.e2e_inflight))))  # warm-up: zygotes, pool growth, page cache
     lat.clear()
     print("ready", flush=True)
     sys.stdin.readline()
@@ -464,7 +469,8 @@ def main():
     ap.add_argument("--e2e-requests", type=int, default=-1,
                     help="requests per GPU in the e2e arm (-1 = min(steps, 4) batches of 1024: a single batch lasts ~0.3 s, "
                          "which is mostly ramp-up and tail)")
-    ap.add_argument("--e2e-inflight", type=int, default=32)
+    ap.add_argument("--e2e-inflight", type=int, default=0,
+                    help="admitted requests per service process (0 = auto: 16 in flight per GPU)")
     ap.add_argument("--e2e-workers", type=int, default=0, help="service processes per GPU in the e2e arm (0 = auto)")
     ap.add_argument("--e2e-zygotes", type=int, default=0, help="warm interpreters per service process (0 = auto)")
     ap.add_argument("--e2e-worker", action="store_true", help=argparse.SUPPRESS)
