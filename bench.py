@@ -278,7 +278,8 @@ def measure_e2e(args, dist, rank, world, local, n):
     # processes are alive at once, so throughput FALLS with the number admitted (tools/e2e_trace.py,
     # 4 service processes on one GPU: 16 in flight 3.42 k req/s, 32: 3.22 k, 64: 2.88 k, 128: 2.35 k);
     # 16 per GPU keeps the GPU fed (two dispatch groups) without crowding the host
-    inflight = args.e2e_inflight if args.e2e_inflight > 0 else max(2, 16 // workers)
+    # and box-wide: 4 GPUs, 64 admitted in total 6.4 k req/s, 32 in total 7.4 k -> 8 per GPU beyond 2 GPUs
+    inflight = args.e2e_inflight if args.e2e_inflight > 0 else max(2, (16 if world <= 2 else 8) // workers)
     broker = BrokerProcess(device=local)
     procs = []
     try:
