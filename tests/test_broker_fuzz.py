@@ -62,8 +62,10 @@ def test_garbage_and_truncated_frames(broker):
     assert _healthy(broker)
 
 
-def test_hostile_but_well_framed_requests(broker):
-    s = _raw(broker.socket_path)
+def hostile_requests(socket_path):
+    """The well-framed but hostile sequence; also run against the native broker on the GPU box
+    (tests/test_gpu_executor.py)."""
+    s = _raw(socket_path)
 
     def call(op, **kw):
         s.sendall(W.pack_req(op, **kw))
@@ -84,6 +86,10 @@ def test_hostile_but_well_framed_requests(broker):
     assert call(W.SHA256_FINAL, payload=b"\1" * 5)[0] != L.OK                           # short hash state
     assert call(W.PING)[0] == L.OK                                                       # the connection still works
     s.close()
+
+
+def test_hostile_but_well_framed_requests(broker):
+    hostile_requests(broker.socket_path)
     for _ in range(100):
         if fake_device.live_buffers() == 0:
             break

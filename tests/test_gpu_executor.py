@@ -161,3 +161,16 @@ def test_seeded_script_gets_numpys_stream_from_the_gpu(executor):
     assert lines[1] == f"{float(x[0])!r} {float(x[1_500_000])!r} {float(x[-1])!r}"
     assert lines[2] == f"{a.tolist()!r} {b.tolist()!r}"
     assert lines[3] == f"{float(np.max(x))!r} {int(np.argmax(x))}"
+
+
+def test_native_broker_survives_hostile_requests(executor):
+    """Same hostile sequence as the CPU test of the Python stand-in, against libbci.so's broker."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from test_broker_fuzz import hostile_requests
+
+    hostile_requests(executor.broker.socket_path)
+    r = asyncio.run(executor.execute(W.benchmark_numpy_source(1_000_000)))
+    assert r.exit_code == 0 and r.stdout.startswith("Result:")
