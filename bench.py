@@ -8,9 +8,12 @@ A "step" = one batch of 1024 requests per GPU, each request the reference's metr
 (examples/benchmark-numpy.py:18-22): x = rand(1e8) float64; sum(square(x)).  Requests are
 sharded round-robin (request i -> GPU i mod N), no data-path collective; per-GPU work is
 fixed as N grows ("weak").  `value` times the batch-first C ABI with everything device
-resident; `e2e` times the same requests through the executor backend's public
-`execute(source_code, files, env)` call (source text in, stdout text out).  Rank 0 prints
-ONE JSON line.  See DESIGN.md §Measurement.
+resident (waves of 64 requests, the next wave's launch queued before the host waits for the
+current one); `e2e` times the same requests through the executor backend's public
+`execute(source_code, files, env)` call (source text in, stdout text out) from several service
+processes per GPU sharing that GPU's broker, with 16 (8 beyond 2 GPUs) requests admitted per GPU
+at a time and up to 4 batches per GPU so that the window is seconds, not a burst.  Rank 0 prints
+ONE JSON line on stdout (everything else goes to stderr).  See DESIGN.md §Measurement.
 """
 from __future__ import annotations
 
