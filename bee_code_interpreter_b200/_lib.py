@@ -16,6 +16,7 @@ OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_OOM, ERR_NOT_INIT = 0, 1, 2, 3, 
 F32, F64, I32, I64 = 0, 1, 2, 3
 EW_ADD, EW_SUB, EW_MUL, EW_DIV, EW_MAXIMUM, EW_MINIMUM, EW_RSUB, EW_RDIV = range(8)
 EW_SQUARE, EW_ABS, EW_NEG, EW_SQRT, EW_EXP, EW_LOG = 32, 33, 34, 35, 36, 37
+EW_SIN, EW_COS, EW_TANH, EW_FLOOR, EW_CEIL, EW_LOG1P, EW_EXPM1 = 38, 39, 40, 41, 42, 43, 44
 RED_SUM, RED_MEAN, RED_MAX, RED_MIN = 0, 1, 2, 3
 PRE_NONE, PRE_SQUARE, PRE_ABS = 0, 1, 2
 ARGMAX, ARGMIN = 0, 1

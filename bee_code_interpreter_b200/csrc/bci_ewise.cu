@@ -99,6 +99,13 @@ static int dispatch_op(int op, Req* reqs, int B) {
       case BCI_EW_SQRT: return launch_ewise<T, BCI_EW_SQRT>(reqs, B);
       case BCI_EW_EXP: return launch_ewise<T, BCI_EW_EXP>(reqs, B);
       case BCI_EW_LOG: return launch_ewise<T, BCI_EW_LOG>(reqs, B);
+      case BCI_EW_SIN: return launch_ewise<T, BCI_EW_SIN>(reqs, B);
+      case BCI_EW_COS: return launch_ewise<T, BCI_EW_COS>(reqs, B);
+      case BCI_EW_TANH: return launch_ewise<T, BCI_EW_TANH>(reqs, B);
+      case BCI_EW_FLOOR: return launch_ewise<T, BCI_EW_FLOOR>(reqs, B);
+      case BCI_EW_CEIL: return launch_ewise<T, BCI_EW_CEIL>(reqs, B);
+      case BCI_EW_LOG1P: return launch_ewise<T, BCI_EW_LOG1P>(reqs, B);
+      case BCI_EW_EXPM1: return launch_ewise<T, BCI_EW_EXPM1>(reqs, B);
       default: break;
     }
   }

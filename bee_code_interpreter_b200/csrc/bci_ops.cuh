@@ -81,6 +81,13 @@ template <typename T, int OP> __device__ __forceinline__ T ew_apply(T a, T b) {
     else if constexpr (OP == BCI_EW_SQRT) return sqrt(a);  // IEEE (-prec-sqrt=true default)
     else if constexpr (OP == BCI_EW_EXP) return exp(a);
     else if constexpr (OP == BCI_EW_LOG) return log(a);
+    else if constexpr (OP == BCI_EW_SIN) return sin(a);     // full-range libdevice paths (no -use_fast_math)
+    else if constexpr (OP == BCI_EW_COS) return cos(a);
+    else if constexpr (OP == BCI_EW_TANH) return tanh(a);
+    else if constexpr (OP == BCI_EW_FLOOR) return floor(a);
+    else if constexpr (OP == BCI_EW_CEIL) return ceil(a);
+    else if constexpr (OP == BCI_EW_LOG1P) return log1p(a);
+    else if constexpr (OP == BCI_EW_EXPM1) return expm1(a);
     else return a;
   } else {
     return a;

@@ -31,8 +31,11 @@ BINARY_UFUNCS = {np.add: L.EW_ADD, np.subtract: L.EW_SUB, np.multiply: L.EW_MUL,
 REVERSED = {L.EW_SUB: L.EW_RSUB, L.EW_DIV: L.EW_RDIV}  # scalar on the left
 COMMUTATIVE = {L.EW_ADD, L.EW_MUL, L.EW_MAXIMUM, L.EW_MINIMUM}
 UNARY_UFUNCS = {np.square: L.EW_SQUARE, np.absolute: L.EW_ABS, np.fabs: L.EW_ABS, np.negative: L.EW_NEG,
-                np.sqrt: L.EW_SQRT, np.exp: L.EW_EXP, np.log: L.EW_LOG}
-FLOAT_ONLY = {L.EW_DIV, L.EW_RDIV, L.EW_SQRT, L.EW_EXP, L.EW_LOG}
+                np.sqrt: L.EW_SQRT, np.exp: L.EW_EXP, np.log: L.EW_LOG, np.sin: L.EW_SIN, np.cos: L.EW_COS,
+                np.tanh: L.EW_TANH, np.floor: L.EW_FLOOR, np.ceil: L.EW_CEIL, np.log1p: L.EW_LOG1P,
+                np.expm1: L.EW_EXPM1}
+FLOAT_ONLY = {L.EW_DIV, L.EW_RDIV, L.EW_SQRT, L.EW_EXP, L.EW_LOG, L.EW_SIN, L.EW_COS, L.EW_TANH, L.EW_FLOOR,
+              L.EW_CEIL, L.EW_LOG1P, L.EW_EXPM1}
 FUSABLE_PRODUCERS = {L.EW_ADD, L.EW_SUB, L.EW_MUL, L.EW_MAXIMUM, L.EW_MINIMUM, L.EW_RSUB}
 PRE_OF = {L.EW_SQUARE: L.PRE_SQUARE, L.EW_ABS: L.PRE_ABS}
 REDUCE_UFUNCS = {np.add: L.RED_SUM, np.maximum: L.RED_MAX, np.minimum: L.RED_MIN}
@@ -320,7 +323,8 @@ class DeviceArray(NDArrayOperatorsMixin):
 
 
 _UNARY_NP = {L.EW_SQUARE: np.square, L.EW_ABS: np.absolute, L.EW_NEG: np.negative, L.EW_SQRT: np.sqrt,
-             L.EW_EXP: np.exp, L.EW_LOG: np.log}
+             L.EW_EXP: np.exp, L.EW_LOG: np.log, L.EW_SIN: np.sin, L.EW_COS: np.cos, L.EW_TANH: np.tanh,
+             L.EW_FLOOR: np.floor, L.EW_CEIL: np.ceil, L.EW_LOG1P: np.log1p, L.EW_EXPM1: np.expm1}
 _BINARY_NP = {L.EW_ADD: np.add, L.EW_SUB: np.subtract, L.EW_MUL: np.multiply, L.EW_DIV: np.divide,
               L.EW_MAXIMUM: np.maximum, L.EW_MINIMUM: np.minimum,
               L.EW_RSUB: lambda a, s: np.subtract(s, a), L.EW_RDIV: lambda a, s: np.divide(s, a)}

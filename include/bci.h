@@ -68,6 +68,13 @@ extern "C" {
 #define BCI_EW_SQRT 35    /* numpy.sqrt  (float dtypes only) */
 #define BCI_EW_EXP 36     /* numpy.exp   (float dtypes only) */
 #define BCI_EW_LOG 37     /* numpy.log   (float dtypes only) */
+#define BCI_EW_SIN 38     /* numpy.sin   (float dtypes only) */
+#define BCI_EW_COS 39     /* numpy.cos   (float dtypes only) */
+#define BCI_EW_TANH 40    /* numpy.tanh  (float dtypes only) */
+#define BCI_EW_FLOOR 41   /* numpy.floor (float dtypes only; exact) */
+#define BCI_EW_CEIL 42    /* numpy.ceil  (float dtypes only; exact) */
+#define BCI_EW_LOG1P 43   /* numpy.log1p (float dtypes only) */
+#define BCI_EW_EXPM1 44   /* numpy.expm1 (float dtypes only) */
 
 /* ---- full reductions (axis=None) ----------------------------------------- */
 #define BCI_RED_SUM 0   /* numpy.sum   : f32->f32, f64->f64, i32->i64, i64->i64 */

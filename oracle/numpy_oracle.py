@@ -38,6 +38,8 @@ EWISE = {
     "add": np.add, "subtract": np.subtract, "multiply": np.multiply, "divide": np.divide,
     "maximum": np.maximum, "minimum": np.minimum, "square": np.square, "absolute": np.absolute,
     "negative": np.negative, "sqrt": np.sqrt, "exp": np.exp, "log": np.log,
+    "sin": np.sin, "cos": np.cos, "tanh": np.tanh, "floor": np.floor, "ceil": np.ceil,
+    "log1p": np.log1p, "expm1": np.expm1,
 }
 
 

@@ -23,7 +23,8 @@ BIN = {L.EW_ADD: np.add, L.EW_SUB: np.subtract, L.EW_MUL: np.multiply, L.EW_DIV:
        L.EW_MAXIMUM: np.maximum, L.EW_MINIMUM: np.minimum,
        L.EW_RSUB: lambda a, s: np.subtract(s, a), L.EW_RDIV: lambda a, s: np.divide(s, a)}
 UN = {L.EW_SQUARE: np.square, L.EW_ABS: np.absolute, L.EW_NEG: np.negative, L.EW_SQRT: np.sqrt,
-      L.EW_EXP: np.exp, L.EW_LOG: np.log}
+      L.EW_EXP: np.exp, L.EW_LOG: np.log, L.EW_SIN: np.sin, L.EW_COS: np.cos, L.EW_TANH: np.tanh,
+      L.EW_FLOOR: np.floor, L.EW_CEIL: np.ceil, L.EW_LOG1P: np.log1p, L.EW_EXPM1: np.expm1}
 RED = {L.RED_SUM: np.sum, L.RED_MEAN: np.mean, L.RED_MAX: np.max, L.RED_MIN: np.min}
 PRE = {L.PRE_NONE: lambda a: a, L.PRE_SQUARE: np.square, L.PRE_ABS: np.absolute}
 

@@ -59,8 +59,9 @@ BINARY = [(L.EW_ADD, "add"), (L.EW_SUB, "subtract"), (L.EW_MUL, "multiply"), (L.
           (L.EW_MINIMUM, "minimum")]
 UNARY = [(L.EW_SQUARE, "square"), (L.EW_ABS, "absolute"), (L.EW_NEG, "negative")]
 FLOAT_BINARY = [(L.EW_DIV, "divide")]
-FLOAT_UNARY_EXACT = [(L.EW_SQRT, "sqrt")]
-FLOAT_UNARY_ULP = [(L.EW_EXP, "exp"), (L.EW_LOG, "log")]
+FLOAT_UNARY_EXACT = [(L.EW_SQRT, "sqrt"), (L.EW_FLOOR, "floor"), (L.EW_CEIL, "ceil")]
+FLOAT_UNARY_ULP = [(L.EW_EXP, "exp"), (L.EW_LOG, "log"), (L.EW_SIN, "sin"), (L.EW_COS, "cos"), (L.EW_TANH, "tanh"),
+                   (L.EW_LOG1P, "log1p"), (L.EW_EXPM1, "expm1")]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
