@@ -93,6 +93,7 @@ SIGNATURES = {
     "bci_sort": (C.c_int, [C.c_int, C.c_int, _VPP, _VPP, _SZP]),
     "bci_argsort": (C.c_int, [C.c_int, C.c_int, _VPP, _VPP, _SZP]),
     "bci_rand_f64": (C.c_int, [C.c_int, _VPP, _SZP, C.POINTER(C.c_uint64)]),
+    "bci_rand_normal_f64": (C.c_int, [C.c_int, _VPP, _SZP, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bci_rand_mt19937_f64": (C.c_int, [C.c_int, _VPP, _SZP, C.POINTER(C.c_uint32)]),
     "bci_matmul_f32": (C.c_int, [C.c_int, _VPP, _VPP, _VPP, C.c_int, C.c_int, C.c_int]),
     "bci_sha256": (C.c_int, [C.c_int, _VPP, _SZP, C.c_int, C.c_void_p]),

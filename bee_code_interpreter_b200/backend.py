@@ -36,6 +36,9 @@ class LocalBackend:
     def rand(self, n, seed):
         return self._new(n * 8, lambda out: self.dev.rand_f64([out], [n], [seed]))
 
+    def rand_normal(self, n, seed, loc, scale):
+        return self._new(n * 8, lambda out: self.dev.rand_normal_f64([out], [n], [seed], [loc], [scale]))
+
     def rand_mt19937(self, n, state):
         """-> (buffer, state after); `state` = 625 uint32 (key + pos)."""
         box = {}

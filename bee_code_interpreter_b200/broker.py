@@ -152,6 +152,9 @@ class GpuBroker:
         if kind == W.RAND:
             dev.rand_f64(col(0), col(1), col(2))
             return [None] * len(argl)
+        if kind == W.RAND_NORMAL:
+            dev.rand_normal_f64(col(0), col(1), col(2), col(3), col(4))
+            return [None] * len(argl)
         if kind == W.RAND_MT:
             return list(dev.rand_mt19937(col(0), col(1), np.stack(col(2))))
         if kind == W.EWISE:
@@ -254,6 +257,10 @@ class GpuBroker:
         if op == W.RAND:
             p = new(n * 8)
             self.submit((W.RAND,), (p, n, s0))
+            return p, b""
+        if op == W.RAND_NORMAL:
+            p = new(n * 8)
+            self.submit((W.RAND_NORMAL,), (p, n, ints[0], W.scalar_from_bits(s0, True), W.scalar_from_bits(s1, True)))
             return p, b""
         if op == W.RAND_MT:
             if len(payload) != 4 * W.MT_STATE_WORDS:

@@ -145,6 +145,10 @@ class RemoteBackend:
     def rand(self, n, seed):
         return self._call(W.RAND, n=int(n), s0=int(seed) & 0xFFFFFFFFFFFFFFFF)[0]
 
+    def rand_normal(self, n, seed, loc, scale):
+        return self._call(W.RAND_NORMAL, n=int(n), i0=int(seed) & 0x7FFFFFFFFFFFFFFF, s0=W.scalar_bits(loc, True),
+                          s1=W.scalar_bits(scale, True))[0]
+
     def rand_mt19937(self, n, state):
         st = np.ascontiguousarray(state, dtype="<u4")
         if st.size != W.MT_STATE_WORDS:

@@ -116,6 +116,16 @@ int run_group(std::vector<Job*>& grp) {
       for (int i = 0; i < B; ++i) seeds[i] = grp[i]->rq.s0;
       return bci_rand_f64(B, out.data(), n.data(), seeds.data());
     }
+    case BRK_RAND_NORMAL: {
+      std::vector<uint64_t> seeds(B);
+      std::vector<double> loc(B), scale(B);
+      for (int i = 0; i < B; ++i) {
+        seeds[i] = (uint64_t)grp[i]->rq.i0;
+        loc[i] = scalar_of(grp[i]->rq.s0).f;
+        scale[i] = scalar_of(grp[i]->rq.s1).f;
+      }
+      return bci_rand_normal_f64(B, out.data(), n.data(), seeds.data(), loc.data(), scale.data());
+    }
     case BRK_RAND_MT: {
       std::vector<uint32_t> st((size_t)B * BCI_MT19937_STATE_WORDS);
       for (int i = 0; i < B; ++i) memcpy(&st[(size_t)i * BCI_MT19937_STATE_WORDS], grp[i]->mt_state, 4 * BCI_MT19937_STATE_WORDS);
@@ -359,14 +369,14 @@ void serve(int fd) {
         }
         break;
       }
-      case BRK_RAND: case BRK_EWISE: case BRK_CUMSUM: case BRK_SORT: case BRK_ARGSORT: case BRK_MATMUL:
+      case BRK_RAND: case BRK_RAND_NORMAL: case BRK_EWISE: case BRK_CUMSUM: case BRK_SORT: case BRK_ARGSORT: case BRK_MATMUL:
       case BRK_REDUCE: case BRK_REDUCE_FUSED: case BRK_ARGEXT: case BRK_SHA256_DEV: {
         Job job;
         job.rq = rq;
         // ownership + sizes
         bool valid = true;
         size_t in_bytes = (size_t)rq.n * es, out_bytes = 0;
-        if (rq.op == BRK_RAND) { in_bytes = 0; out_bytes = (size_t)rq.n * 8; }
+        if (rq.op == BRK_RAND || rq.op == BRK_RAND_NORMAL) { in_bytes = 0; out_bytes = (size_t)rq.n * 8; }
         else if (rq.op == BRK_SHA256_DEV) { in_bytes = (size_t)rq.n; valid = owns(rq.p0, in_bytes); }
         else if (rq.op == BRK_MATMUL) {
           valid = rq.i0 > 0 && rq.i1 > 0 && rq.i2 > 0 && owns(rq.p0, (size_t)rq.i0 * rq.i2 * 4) && owns(rq.p1, (size_t)rq.i2 * rq.i1 * 4);
@@ -379,7 +389,7 @@ void serve(int fd) {
         }
         if (!valid) { ok = reply_err(fd, BCI_ERR_INVALID, "buffer does not belong to this request"); break; }
         const bool inplace = rq.op == BRK_SORT && (rq.flags & BRK_F_INPLACE);
-        const bool needs_out = !inplace && (rq.op == BRK_RAND || rq.op == BRK_EWISE || rq.op == BRK_CUMSUM ||
+        const bool needs_out = !inplace && (rq.op == BRK_RAND || rq.op == BRK_RAND_NORMAL || rq.op == BRK_EWISE || rq.op == BRK_CUMSUM ||
                                             rq.op == BRK_SORT || rq.op == BRK_ARGSORT || rq.op == BRK_MATMUL);
         if (inplace) job.out_ptr = rq.p0;
         if (needs_out) {

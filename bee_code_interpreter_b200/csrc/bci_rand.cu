@@ -59,6 +59,21 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return __fma_rn(hi, 7.450580596923828125e-09, __dmul_rn(lo, 1.1102230246251565404e-16));
 }
 
+// Standard normals by Box-Muller on the same counter layout (third counter word = 1, so the
+// normal stream of a seed is not the uniform one): pair p -> u_a, u_b ->
+//   r = sqrt(-2 ln(1 - u_a)),  z[2p] = r cos(2 pi u_b),  z[2p+1] = r sin(2 pi u_b);
+// out = loc + scale * z with numpy's two roundings (multiply, then add).  numpy's legacy
+// normal() is the polar method on MT19937 and unseeded, so only the distribution is a parity
+// target; the stream itself is pinned against oracle/philox.c.
+__device__ __forceinline__ void box_muller(const Philox4& p, double loc, double scale, double& z0, double& z1) {
+  const double ua = u53(p.x, p.y), ub = u53(p.z, p.w);
+  const double r = sqrt(-2.0 * log(1.0 - ua));
+  double s, c;
+  sincospi(2.0 * ub, &s, &c);
+  z0 = __dadd_rn(loc, __dmul_rn(scale, r * c));
+  z1 = __dadd_rn(loc, __dmul_rn(scale, r * s));
+}
+
 constexpr int kRandUnroll = 4;
 constexpr size_t kRandTile = (size_t)kThreads * kRandUnroll * 4;  // doubles
 
@@ -99,9 +114,74 @@ rand_f64_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   }
 }
 
+__global__ void __launch_bounds__(kThreads)
+rand_normal_f64_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B) {
+  const unsigned long long tile = blockIdx.x;
+  const int r = find_req(tile_start, B, tile);
+  const Req q = reqs[r];
+  const size_t base = (size_t)(tile - q.tile_start) * kRandTile;
+  const size_t rem = (size_t)q.n - base;
+  double* __restrict__ o = reinterpret_cast<double*>(q.out) + base;
+  const PhiloxKeys keys = philox_keys((uint32_t)((unsigned long long)q.s1.i), (uint32_t)((unsigned long long)q.s1.i >> 32));
+  const double loc = q.s0.f;
+  double scale;
+  memcpy(&scale, &q.aux, 8);
+  if (rem >= kRandTile && is_aligned32(o)) {
+#pragma unroll
+    for (int u = 0; u < kRandUnroll; ++u) {
+      const uint32_t off = (uint32_t)(u * kThreads + threadIdx.x) * 4u;
+      const uint32_t plo = (uint32_t)(base >> 1) | (off >> 1), phi = (uint32_t)(base >> 33);
+      const Philox4 a = philox4x32_10(plo, phi, 1u, 0u, keys);
+      const Philox4 b = philox4x32_10(plo | 1u, phi, 1u, 0u, keys);
+      VecOf<double> v;
+      box_muller(a, loc, scale, v.v[0], v.v[1]);
+      box_muller(b, loc, scale, v.v[2], v.v[3]);
+      stg256(o + ((size_t)u * kThreads + threadIdx.x) * 4, v.u);
+    }
+  } else {
+    const size_t m = rem < kRandTile ? rem : kRandTile;
+    for (size_t i = threadIdx.x; i < m; i += kThreads) {
+      const size_t e = base + i;
+      const unsigned long long p = e >> 1;
+      const Philox4 a = philox4x32_10((uint32_t)p, (uint32_t)(p >> 32), 1u, 0u, keys);
+      double z0, z1;
+      box_muller(a, loc, scale, z0, z1);
+      o[i] = (e & 1) ? z1 : z0;
+    }
+  }
+}
+
 }  // namespace bci
 
 using namespace bci;
+
+extern "C" int bci_rand_normal_f64(int B, void* const* out, const size_t* n, const uint64_t* seed,
+                                   const double* loc, const double* scale) {
+  BCI_REQUIRE_INIT();
+  if (B <= 0 || !out || !n || !seed || !loc || !scale) { set_error("bci_rand_normal_f64: bad arguments"); return BCI_ERR_INVALID; }
+  std::vector<Req> reqs((size_t)B);
+  for (int i = 0; i < B; ++i) {
+    Req& q = reqs[i];
+    memset(&q, 0, sizeof q);
+    q.out = out[i];
+    q.n = n[i];
+    q.s1.i = (int64_t)seed[i];
+    q.s0.f = loc[i];
+    memcpy(&q.aux, &scale[i], 8);
+    if (n[i] && !out[i]) { set_error("bci_rand_normal_f64: NULL buffer in request %d", i); return BCI_ERR_INVALID; }
+  }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  Batch bt;
+  int rc = upload_batch(reqs.data(), B, kRandTile, &bt);
+  if (rc != BCI_OK) return rc;
+  if (bt.total_tiles == 0) return BCI_OK;
+  if (bt.total_tiles > 0x7fffffffull) { set_error("bci_rand_normal_f64: batch too large for one launch"); return BCI_ERR_INVALID; }
+  rand_normal_f64_kernel<<<(unsigned)bt.total_tiles, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B);
+  BCI_CHECK_LAUNCH();
+  return BCI_OK;
+}
+
 
 extern "C" int bci_rand_f64(int B, void* const* out, const size_t* n, const uint64_t* seed) {
   BCI_REQUIRE_INIT();

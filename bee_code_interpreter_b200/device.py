@@ -276,6 +276,15 @@ def rand_f64(out_ptrs: Sequence[int], ns: Sequence[int], seeds: Iterable[int]) -
     _lib.check(_lib.load().bci_rand_f64(len(out_ptrs), _lib.ptr_array(out_ptrs), _lib.size_array(ns), arr))
 
 
+def rand_normal_f64(out_ptrs: Sequence[int], ns: Sequence[int], seeds: Iterable[int], locs: Sequence[float],
+                    scales: Sequence[float]) -> None:
+    seeds = [int(s) & 0xFFFFFFFFFFFFFFFF for s in seeds]
+    B = len(out_ptrs)
+    _lib.check(_lib.load().bci_rand_normal_f64(B, _lib.ptr_array(out_ptrs), _lib.size_array(ns), (C.c_uint64 * B)(*seeds),
+                                               (C.c_double * B)(*[float(v) for v in locs]),
+                                               (C.c_double * B)(*[float(v) for v in scales])))
+
+
 def rand_mt19937(out_ptrs: Sequence[int], ns: Sequence[int], states: np.ndarray) -> np.ndarray:
     """numpy's legacy generator: `states` is (B, 625) uint32 = key[624] + pos per request
     (numpy.random.get_state()); returns the states after drawing ns[i] doubles into out_ptrs[i]."""

@@ -123,8 +123,40 @@ def _build_view():
         _state["seeded"] = True  # from here on the legacy stream is deterministic: numpy owns it
         return real_random.seed(*a, **kw)
 
+    def _device_normal(shape, loc, scale, fallback):
+        # unseeded only: the seeded legacy normal is MT19937 + polar rejection, numpy keeps that stream
+        try:
+            plain = all(isinstance(v, (int, float)) and not isinstance(v, bool) for v in (loc, scale))
+            if (_state["seeded"] or not plain or scale < 0 or _size_of(shape) < _state["min_rand"]
+                    or not all(isinstance(s, (int, real_np.integer)) for s in shape)):
+                return fallback()
+            return P.device_normal(_backend(), tuple(int(s) for s in shape), int.from_bytes(os.urandom(8), "little"),
+                                   loc, scale)
+        except Exception as e:
+            if os.environ.get("BCI_DEBUG_FALLBACK"):
+                print(f"[bci] device normal fell back to numpy: {e!r}", file=sys.stderr)
+            return fallback()
+
+    def randn(*shape):
+        if not shape:
+            return real_random.randn()
+        return _device_normal(shape, 0.0, 1.0, lambda: real_random.randn(*shape))
+
+    def standard_normal(size=None):
+        if size is None:
+            return real_random.standard_normal()
+        shape = (size,) if isinstance(size, (int, real_np.integer)) else tuple(size)
+        return _device_normal(shape, 0.0, 1.0, lambda: real_random.standard_normal(size))
+
+    def normal(loc=0.0, scale=1.0, size=None):
+        if size is None:
+            return real_random.normal(loc, scale)
+        shape = (size,) if isinstance(size, (int, real_np.integer)) else tuple(size)
+        return _device_normal(shape, loc, scale, lambda: real_random.normal(loc, scale, size))
+
     random_view = _ModuleView(real_random, {"rand": rand, "random": random_sample, "random_sample": random_sample,
-                                            "ranf": random_sample, "sample": random_sample, "seed": seed})
+                                            "ranf": random_sample, "sample": random_sample, "seed": seed,
+                                            "randn": randn, "standard_normal": standard_normal, "normal": normal})
 
     def _offloading(device_fn, real_fn, n_arrays):
         def wrapper(*args, **kwargs):

@@ -569,6 +569,14 @@ def device_rand(backend, shape, seed: int) -> DeviceArray:
     return DeviceArray(backend, backend.rand(n, seed), shape, np.float64)
 
 
+def device_normal(backend, shape, seed: int, loc: float = 0.0, scale: float = 1.0) -> DeviceArray:
+    """numpy.random.normal / randn / standard_normal for an unseeded legacy generator."""
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return DeviceArray(backend, backend.rand_normal(n, seed, float(loc), float(scale)), shape, np.float64)
+
+
 def device_rand_legacy(backend, shape, random_module) -> DeviceArray:
     """numpy.random.rand / random_sample on the SEEDED global generator: the MT19937 state goes
     to the device, the same stream comes back bit for bit, and the advanced state is put back so

@@ -6,7 +6,7 @@ from __future__ import annotations
 import struct
 
 ALLOC, FREE, RAND, EWISE, REDUCE, REDUCE_FUSED, ARGEXT, CUMSUM, SORT, ARGSORT, MATMUL, COPY, UPLOAD, DOWNLOAD, \
-    SHA256_DEV, SHA256_FILE, SHA256_BYTES, SHA256_UPDATE, SHA256_FINAL, PING, RAND_MT = range(1, 22)
+    SHA256_DEV, SHA256_FILE, SHA256_BYTES, SHA256_UPDATE, SHA256_FINAL, PING, RAND_MT, RAND_NORMAL = range(1, 23)
 MT_STATE_WORDS = 625   # MT19937 key[624] + pos, little-endian uint32
 
 F_IN1, F_ADDEND, F_INPLACE, F_SHM, F_STATE = 1, 2, 4, 8, 16

@@ -174,6 +174,12 @@ int bci_argsort(int dtype, int B, const void* const* in, int64_t* const* out_idx
  * (same 53-bit construction and distribution, not the MT19937 stream). */
 int bci_rand_f64(int B, void* const* out, const size_t* n, const uint64_t* seed);
 
+/* ---- K8c numpy.random.normal / randn / standard_normal, unseeded: Box-Muller on the Philox stream
+ * (third counter word 1), out = loc[i] + scale[i] * z.  Same distribution as numpy's legacy
+ * normal() (examples/using_imports.py:21-22 draws normals), not its MT19937 polar-method stream. */
+int bci_rand_normal_f64(int B, void* const* out, const size_t* n, const uint64_t* seed,
+                        const double* loc, const double* scale);
+
 /* ---- K8b the SEEDED legacy generator, bit-exact: numpy.random.seed(s); numpy.random.rand(n)
  * (examples/using_imports.py:20-22 seeds the global MT19937).  states = B x 625 uint32 in host
  * memory, each numpy's get_state(): key[624] followed by pos (0..624); on return it is the

@@ -55,6 +55,7 @@ int bci_broker_stats(uint64_t stats[4]);
 #define BRK_SHA256_UPDATE 18 /* payload = [state (sizeof bci_sha256_state) if flag STATE] + chunk -> payload = state */
 #define BRK_SHA256_FINAL 19 /* payload = state                    -> payload = digest */
 #define BRK_PING 20         /*                                    -> payload = 4 x u64 stats */
+#define BRK_RAND_NORMAL 22  /* n = elements, i0 = seed, s0 = loc bits, s1 = scale bits -> value = new f64 buffer */
 #define BRK_RAND_MT 21      /* n = elements; payload = MT19937 state (625 x u32) -> value = new f64 buffer, payload = state after */
 
 #define BRK_F_IN1 1u      /* p1 is an array operand (else scalar s0) */

@@ -29,6 +29,8 @@ def clib() -> C.CDLL:
         lib.oracle_philox4x32_10.restype = None
         lib.oracle_rand_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64]
         lib.oracle_rand_f64.restype = None
+        lib.oracle_rand_normal_f64.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.c_double, C.c_double]
+        lib.oracle_rand_normal_f64.restype = None
         _LIB = lib
     return _LIB
 
@@ -93,6 +95,15 @@ def matmul_f64(a: np.ndarray, b: np.ndarray) -> np.ndarray:
 def rand_f64(n: int, seed: int) -> np.ndarray:
     out = np.empty(int(n), dtype=np.float64)
     clib().oracle_rand_f64(out.ctypes.data, int(n), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF))
+    return out
+
+
+def rand_normal_f64(n: int, seed: int, loc: float = 0.0, scale: float = 1.0) -> np.ndarray:
+    """Box-Muller normals on the Philox stream (counter word 2 = 1): restates bci_rand.cu with libm;
+    the device agrees to a few ulp of the transcendental functions, not bit for bit."""
+    out = np.empty(int(n), dtype=np.float64)
+    clib().oracle_rand_normal_f64(out.ctypes.data, int(n), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF),
+                                  C.c_double(loc), C.c_double(scale))
     return out
 
 

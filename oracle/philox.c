@@ -48,3 +48,19 @@ void oracle_rand_f64(double* out, size_t n, uint64_t seed) {
     if (2 * p + 1 < n) out[2 * p + 1] = u53(r[2], r[3]);
   }
 }
+
+/* Box-Muller normals on counter (p, 0, 1, 0): z[2p] = r cos(2 pi u_b), z[2p+1] = r sin(2 pi u_b),
+ * r = sqrt(-2 ln(1 - u_a)); out = loc + scale * z.  Restates bci_rand.cu:box_muller with libm. */
+#include <math.h>
+void oracle_rand_normal_f64(double* out, size_t n, uint64_t seed, double loc, double scale) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (size_t p = 0; 2 * p < n; ++p) {
+    uint32_t ctr[4] = {(uint32_t)p, (uint32_t)((uint64_t)p >> 32), 1, 0}, r[4];
+    oracle_philox4x32_10(ctr, key, r);
+    double ua = u53(r[0], r[1]), ub = u53(r[2], r[3]);
+    double rad = sqrt(-2.0 * log(1.0 - ua));
+    double ang = 2.0 * 3.14159265358979323846 * ub;
+    out[2 * p] = loc + scale * (rad * cos(ang));
+    if (2 * p + 1 < n) out[2 * p + 1] = loc + scale * (rad * sin(ang));
+  }
+}

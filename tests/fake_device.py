@@ -183,6 +183,12 @@ def rand_f64(out_ptrs, ns, seeds):
         _view(p, n, np.float64)[:] = O.rand_f64(n, s)
 
 
+def rand_normal_f64(out_ptrs, ns, seeds, locs, scales):
+    calls.append(("rand_normal", len(out_ptrs), None))
+    for p, n, s, lo, sc in zip(out_ptrs, ns, seeds, locs, scales):
+        _view(p, n, np.float64)[:] = O.rand_normal_f64(n, s, lo, sc)
+
+
 def rand_mt19937(out_ptrs, ns, states):
     """numpy's own MT19937 is the oracle here: set_state -> random_sample -> get_state."""
     calls.append(("rand_mt", len(out_ptrs), None))
