@@ -467,7 +467,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=10**8, help="array elements per request (benchmark-numpy.py: 1e8)")
+    ap.add_argument("--n", "--array-elems", dest="n", type=int, default=10**8,
+                    help="array elements per request (benchmark-numpy.py: 1e8); use the long form under torchrun, "
+                         "whose own parser treats --n as an abbreviation")
     ap.add_argument("--requests", type=int, default=PER_GPU_BATCH, help="requests per GPU per step")
     ap.add_argument("--wave", type=int, default=64, help="requests resident on the GPU at once")
     ap.add_argument("--e2e-requests", type=int, default=-1,
