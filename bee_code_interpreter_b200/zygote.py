@@ -10,7 +10,7 @@ The zygote is single-threaded and holds no CUDA context, so fork() is safe.  Pro
 stream socket, one connection per request):
     client -> zygote : 4-byte length + request dict (pickle from ZygoteClient, JSON from
                        csrc/bci_executor_server.cpp)
-    zygote -> client : 4-byte pid of the forked child          (zygote then closes its copy)
+    child  -> client : 4-byte pid, first thing after the fork  (the zygote closes its copy)
     child  -> client : 4-byte exit code, just before os._exit  (absent if the child was killed
                        or crashed: the client maps EOF to -1, like server.rs:165)
 Children are auto-reaped (SIGCHLD ignored).
@@ -80,6 +80,9 @@ def serve(socket_path: str) -> None:
                 srv.close()
                 code = 1
                 try:
+                    # the CHILD announces its pid: if the parent did, a short script could finish and
+                    # write its exit code first, and the client would read the two words swapped
+                    conn.sendall(struct.pack("<i", os.getpid()))
                     code = script_runner.run_in_child(req)
                 finally:
                     try:
@@ -87,7 +90,6 @@ def serve(socket_path: str) -> None:
                     except OSError:
                         pass
                     os._exit(code & 0xFF)
-            conn.sendall(struct.pack("<i", pid))
         except Exception:
             pass
         finally:
@@ -133,10 +135,11 @@ class ZygoteClient:
             try:
                 tail = _recv_exact(conn, 4)
             except socket.timeout:
-                try:
-                    os.kill(pid, signal.SIGKILL)
-                except ProcessLookupError:
-                    pass
+                if pid > 1:   # never signal 0 / -1 (process groups) on a garbled reply
+                    try:
+                        os.kill(pid, signal.SIGKILL)
+                    except ProcessLookupError:
+                        pass
                 return None
             if len(tail) < 4:
                 return -1

@@ -250,3 +250,18 @@ def test_live_replay_of_the_api_fixtures_through_the_wire_contract(tmp_path, bui
         finally:
             s.close()
     assert store and b"Hello, World!" in store.values()
+
+
+def test_zygote_pid_and_exit_code_never_swap(built, tmp_path):
+    """The child announces its own pid before it runs the script: with the parent announcing it, a
+    script that finishes first could get its exit code read as the pid (and the pid as the code)."""
+    from bee_code_interpreter_b200.zygote import ZygoteClient
+
+    z = ZygoteClient()
+    try:
+        req = {"source_code": "import sys\nsys.exit(3)", "workspace": str(tmp_path), "env": {}, "stdout_path": str(tmp_path / "o"),
+               "stderr_path": str(tmp_path / "e"), "broker_socket": "/nonexistent", "min_rand_elems": None}
+        codes = {z.run(req, 30) for _ in range(400)}
+        assert codes == {3}
+    finally:
+        z.close()
