@@ -574,7 +574,32 @@ bool run_via_exec(const std::string& source, const std::map<std::string, std::st
   return true;
 }
 
-void changed_files(const struct timespec& since, std::vector<std::string>& out) {
+// What a change to a file cannot leave untouched.
+struct FileSig {
+  ino_t ino; off_t size; long long mtime_ns, ctime_ns;
+  bool operator==(const FileSig& o) const { return ino == o.ino && size == o.size && mtime_ns == o.mtime_ns && ctime_ns == o.ctime_ns; }
+};
+static FileSig sig_of(const struct stat& st) {
+  return FileSig{st.st_ino, st.st_size, (long long)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec,
+                 (long long)st.st_ctim.tv_sec * 1000000000ll + st.st_ctim.tv_nsec};
+}
+
+void snapshot_workspace(std::map<std::string, FileSig>& snap) {
+  DIR* d = opendir(g_cfg.workspace.c_str());
+  if (!d) return;
+  while (struct dirent* e = readdir(d)) {
+    if (!strcmp(e->d_name, ".") || !strcmp(e->d_name, "..")) continue;
+    struct stat st;
+    if (stat((g_cfg.workspace + "/" + e->d_name).c_str(), &st) == 0 && S_ISREG(st.st_mode)) snap[e->d_name] = sig_of(st);
+  }
+  closedir(d);
+}
+
+// server.rs:98-118: regular files directly in the workspace whose ctime is later than the start of
+// the request.  The reference's script needs >= 80 ms to start, ours ~2 ms — inside one tick of the
+// coarse clock the kernel stamps ctime with — so a file written right away can carry a ctime just
+// BEFORE `since`.  Hence also: anything new or different from the snapshot taken at the start.
+void changed_files(const struct timespec& since, const std::map<std::string, FileSig>& before, std::vector<std::string>& out) {
   DIR* d = opendir(g_cfg.workspace.c_str());
   if (!d) return;
   while (struct dirent* e = readdir(d)) {
@@ -582,7 +607,9 @@ void changed_files(const struct timespec& since, std::vector<std::string>& out) 
     std::string p = g_cfg.workspace + "/" + e->d_name;
     struct stat st;
     if (stat(p.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) continue;   // follows symlinks like Path::is_file
-    if (st.st_ctim.tv_sec > since.tv_sec || (st.st_ctim.tv_sec == since.tv_sec && st.st_ctim.tv_nsec > since.tv_nsec))
+    const bool later = st.st_ctim.tv_sec > since.tv_sec || (st.st_ctim.tv_sec == since.tv_sec && st.st_ctim.tv_nsec > since.tv_nsec);
+    auto it = before.find(e->d_name);
+    if (later || it == before.end() || !(it->second == sig_of(st)))
       out.push_back((g_cfg.report_as.empty() ? g_cfg.workspace : g_cfg.report_as) + "/" + e->d_name);
   }
   closedir(d);
@@ -628,6 +655,8 @@ int handle_execute(const std::string& payload, std::string& body) {
 
   struct timespec start;
   clock_gettime(CLOCK_REALTIME, &start);
+  std::map<std::string, FileSig> before;
+  snapshot_workspace(before);
   std::string tmpl = g_cfg.scratch + "/bci-exec-XXXXXX";
   std::vector<char> tb(tmpl.begin(), tmpl.end());
   tb.push_back('\0');
@@ -642,7 +671,7 @@ int handle_execute(const std::string& payload, std::string& body) {
   remove_tree_flat(dir);
   if (!ok) { body = error; return 500; }
   std::vector<std::string> files;
-  changed_files(start, files);
+  changed_files(start, before, files);
   body = "{\"stdout\":";
   json_string(body, oc.out);
   body += ",\"stderr\":";

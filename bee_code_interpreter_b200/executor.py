@@ -109,10 +109,11 @@ class LocalGpuExecutor:
                     target.parent.mkdir(parents=True, exist_ok=True)
                     target.write_bytes(await self.file_storage.read(object_id))
                 start_ns = time.time_ns()
+                before = _snapshot(workspace)
                 stdout, stderr, exit_code = await loop.run_in_executor(
                     self._pool, self._run_process, source_code, str(workspace), dict(env), capture)
                 stored = {}
-                names = _changed_files(workspace, start_ns)
+                names = _changed_files(workspace, start_ns, before)
                 if names:
                     ids = await asyncio.gather(*(self._store(workspace / n) for n in names))
                     stored = {WORKSPACE_PREFIX + n: i for n, i in zip(names, ids)}
@@ -168,10 +169,28 @@ def _read_text(path: str) -> str:
         return ""
 
 
-def _changed_files(workspace: Path, since_ns: int) -> list[str]:
+def _snapshot(workspace: Path) -> dict:
+    """Top-level regular files with what a change cannot leave untouched."""
+    snap = {}
+    for entry in os.scandir(workspace):
+        if entry.is_file():
+            st = entry.stat()
+            snap[entry.name] = (st.st_ino, st.st_size, st.st_mtime_ns, st.st_ctime_ns)
+    return snap
+
+
+def _changed_files(workspace: Path, since_ns: int, before: dict | None = None) -> list[str]:
+    """server.rs:98-118: top-level regular files whose ctime is later than the start of the request.
+    The reference's script takes >= 80 ms to start, ours ~2 ms — inside one tick of the coarse clock
+    the kernel stamps ctime with — so a file written right away could carry a ctime just BEFORE
+    `since_ns`.  Hence also: anything new or different from the snapshot taken at the start."""
     out = []
     for entry in os.scandir(workspace):
-        if entry.is_file() and entry.stat().st_ctime_ns > since_ns:
+        if not entry.is_file():
+            continue
+        st = entry.stat()
+        if st.st_ctime_ns > since_ns or (before is not None and
+                                         before.get(entry.name) != (st.st_ino, st.st_size, st.st_mtime_ns, st.st_ctime_ns)):
             out.append(entry.name)
     return sorted(out)
 

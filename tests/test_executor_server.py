@@ -265,3 +265,14 @@ def test_zygote_pid_and_exit_code_never_swap(built, tmp_path):
         assert codes == {3}
     finally:
         z.close()
+
+
+def test_files_written_in_the_first_millisecond_are_reported(server):
+    """Many immediate writers: none may be lost to the coarse-clock ctime of the kernel."""
+    for i in range(60):
+        r = server.execute(f"open('early{i}.txt', 'w').write('x')")
+        assert r["files"] == [str(server.workspace / f"early{i}.txt")], (i, r)
+    r = server.execute("open('early0.txt', 'w').write('y')")              # same size, rewritten: still reported
+    assert r["files"] == [str(server.workspace / "early0.txt")]
+    r = server.execute("pass")
+    assert r["files"] == []

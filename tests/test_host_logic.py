@@ -429,3 +429,23 @@ def test_var_std_and_vector_dot_run_as_fused_reductions(be):
     assert np.var(k) == np.var(np.arange(100)) and np.dot(k, k) == np.dot(np.arange(100), np.arange(100))
     k32 = P.DeviceArray.from_host(be, np.arange(100, dtype=np.int32))
     assert np.dot(k32, k32) == np.dot(np.arange(100, dtype=np.int32), np.arange(100, dtype=np.int32))
+
+
+def test_changed_files_do_not_depend_on_the_coarse_clock(tmp_path):
+    """_changed_files: a file written within the same kernel tick as the request start is still
+    reported (snapshot comparison), untouched inputs are not."""
+    import os
+    import time
+
+    from bee_code_interpreter_b200 import executor as E
+
+    ws = tmp_path
+    (ws / "input.txt").write_text("in")
+    before = E._snapshot(ws)
+    start = time.time_ns() + 50_000_000          # pretend the clock comparison alone would miss everything
+    (ws / "new.txt").write_text("n")
+    (ws / "input2.txt").write_text("x")
+    assert E._changed_files(ws, start, before) == ["input2.txt", "new.txt"]
+    os.utime(ws / "input.txt")                   # touched: ctime / mtime move
+    assert "input.txt" in E._changed_files(ws, start, before)
+    assert E._changed_files(ws, start, E._snapshot(ws)) == []
