@@ -28,6 +28,12 @@ def run_in_child(req: dict) -> int:
         os.environ.update(env)
     if req.get("broker_socket"):
         os.environ["BCI_BROKER_SOCKET"] = req["broker_socket"]
+    # stdin is /dev/null, as for the reference's `Command::output()` child (server.rs:153-156): a script
+    # that calls input() gets EOFError, it must never read the service's terminal
+    null_fd = os.open(os.devnull, os.O_RDONLY)
+    os.dup2(null_fd, 0)
+    os.close(null_fd)
+    sys.stdin = os.fdopen(0, "r", closefd=False)
     out_fd = os.open(req["stdout_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
     err_fd = os.open(req["stderr_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
     os.dup2(out_fd, 1)

@@ -82,6 +82,7 @@ def serve(socket_path: str) -> None:
                 try:
                     # the CHILD announces its pid: if the parent did, a short script could finish and
                     # write its exit code first, and the client would read the two words swapped
+                    os.setsid()   # own process group: a timeout (and the end of the request) reaps what the script spawned
                     conn.sendall(struct.pack("<i", os.getpid()))
                     code = script_runner.run_in_child(req)
                 finally:
@@ -98,6 +99,17 @@ def serve(socket_path: str) -> None:
         os.unlink(socket_path)
     except OSError:
         pass
+
+
+def _kill_group(pid: int) -> None:
+    """SIGKILL to the script's process group (the child called setsid, so pgid == pid)."""
+    if pid <= 1:          # never signal 0 / -1 on a garbled reply
+        return
+    for fn in (os.killpg, os.kill):
+        try:
+            fn(pid, signal.SIGKILL)
+        except (ProcessLookupError, PermissionError):
+            pass
 
 
 class ZygoteClient:
@@ -135,12 +147,9 @@ class ZygoteClient:
             try:
                 tail = _recv_exact(conn, 4)
             except socket.timeout:
-                if pid > 1:   # never signal 0 / -1 (process groups) on a garbled reply
-                    try:
-                        os.kill(pid, signal.SIGKILL)
-                    except ProcessLookupError:
-                        pass
+                _kill_group(pid)
                 return None
+            _kill_group(pid)   # whatever the script left running goes with the request (the reference deletes the pod)
             if len(tail) < 4:
                 return -1
             return struct.unpack("<i", tail)[0]

@@ -1,0 +1,67 @@
+"""What a request may not leave behind or reach: stdin is /dev/null (server.rs runs the script
+through Command::output(), which does not inherit stdin), and processes the script started die
+with the request — on timeout and on normal completion — where the reference deletes the pod."""
+import os
+import sys
+import time
+from pathlib import Path
+
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+
+
+def _alive(pid):
+    try:
+        os.kill(pid, 0)
+    except ProcessLookupError:
+        return False
+    except PermissionError:
+        return True
+    try:  # a zombie still "exists": look at its state
+        return open(f"/proc/{pid}/stat").read().split(")")[1].split()[0] != "Z"
+    except OSError:
+        return False
+
+
+@pytest.fixture
+def zyg(built, tmp_path):
+    from bee_code_interpreter_b200.zygote import ZygoteClient
+
+    z = ZygoteClient()
+    yield z, tmp_path
+    z.close()
+
+
+def _req(tmp_path, src):
+    return {"source_code": src, "workspace": str(tmp_path), "env": {}, "stdout_path": str(tmp_path / "o"),
+            "stderr_path": str(tmp_path / "e"), "broker_socket": "/nonexistent", "min_rand_elems": None}
+
+
+def test_stdin_is_dev_null(zyg):
+    z, d = zyg
+    assert z.run(_req(d, "import sys\nprint(repr(sys.stdin.read()))"), 30) == 0
+    assert (d / "o").read_text() == "''\n"
+    assert z.run(_req(d, "input()"), 30) == 1
+    assert "EOFError" in (d / "e").read_text()
+
+
+def test_background_processes_die_with_the_request(zyg):
+    z, d = zyg
+    spawn = ("import subprocess, sys\n"
+             "p = subprocess.Popen([sys.executable, '-c', 'import time; time.sleep(300)'])\n"
+             "open('child.pid', 'w').write(str(p.pid))\n")
+    assert z.run(_req(d, spawn), 30) == 0                                   # normal completion
+    pid = int((d / "child.pid").read_text())
+    for _ in range(100):
+        if not _alive(pid):
+            break
+        time.sleep(0.02)
+    assert not _alive(pid)
+    assert z.run(_req(d, spawn + "import time\ntime.sleep(300)\n"), 1.0) is None   # timeout
+    pid = int((d / "child.pid").read_text())
+    for _ in range(100):
+        if not _alive(pid):
+            break
+        time.sleep(0.02)
+    assert not _alive(pid)
