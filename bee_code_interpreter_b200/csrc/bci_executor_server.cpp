@@ -467,6 +467,8 @@ bool recv_exact(int fd, void* p, size_t n, long long deadline_ms, bool* timed_ou
   return true;
 }
 
+static bool write_script(const std::string& script, const std::string& source, std::string& error);
+
 // The zygote's child calls setsid(): its pid is the id of the script's process group.
 static void kill_script_group(int32_t pid) {
   if (pid <= 1) return;  // never signal 0 / -1 on a garbled reply
@@ -476,7 +478,10 @@ static void kill_script_group(int32_t pid) {
 
 // Warm path: ask the zygote (zygote.py protocol, JSON flavour) to fork a child for the script.
 bool run_via_zygote(const std::string& source, const std::map<std::string, std::string>& env, unsigned long long timeout_s,
-                    const std::string& out_path, const std::string& err_path, Outcome& oc, std::string& error) {
+                    const std::string& dir, const std::string& out_path, const std::string& err_path, Outcome& oc,
+                    std::string& error) {
+  const std::string script_path = dir + "/script.py";
+  if (!write_script(script_path, source, error)) return false;
   int fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
   if (fd < 0) { error = "socket(): " + std::string(strerror(errno)); return false; }
   struct sockaddr_un sa;
@@ -490,6 +495,7 @@ bool run_via_zygote(const std::string& source, const std::map<std::string, std::
   req += ",\"workspace\":"; json_string(req, g_cfg.workspace);
   req += ",\"stdout_path\":"; json_string(req, out_path);
   req += ",\"stderr_path\":"; json_string(req, err_path);
+  req += ",\"script_path\":"; json_string(req, script_path);
   if (!g_cfg.broker_socket.empty()) { req += ",\"broker_socket\":"; json_string(req, g_cfg.broker_socket); }
   req += ",\"env\":{";
   bool first = true;
@@ -532,19 +538,27 @@ bool run_via_zygote(const std::string& source, const std::map<std::string, std::
   return true;
 }
 
+// server.rs:124: the source goes into a file of the request's scratch directory.
+static bool write_script(const std::string& script, const std::string& source, std::string& error) {
+  int fd = open(script.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0600);
+  if (fd < 0) { error = "cannot write script: " + std::string(strerror(errno)); return false; }
+  const char* p = source.data();
+  size_t n = source.size();
+  while (n) {
+    ssize_t w = write(fd, p, n);
+    if (w < 0) { if (errno == EINTR) continue; close(fd); error = "cannot write script"; return false; }
+    p += w; n -= (size_t)w;
+  }
+  close(fd);
+  return true;
+}
+
 // Cold path: `$BCI_PYTHON script.py` as a child process, cwd = workspace.
 bool run_via_exec(const std::string& source, const std::map<std::string, std::string>& env, unsigned long long timeout_s,
                   const std::string& dir, const std::string& out_path, const std::string& err_path, Outcome& oc,
                   std::string& error) {
   const std::string script = dir + "/script.py";
-  {
-    int fd = open(script.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0600);
-    if (fd < 0) { error = "cannot write script: " + std::string(strerror(errno)); return false; }
-    const char* p = source.data();
-    size_t n = source.size();
-    while (n) { ssize_t w = write(fd, p, n); if (w < 0) { if (errno == EINTR) continue; close(fd); error = "cannot write script"; return false; } p += w; n -= (size_t)w; }
-    close(fd);
-  }
+  if (!write_script(script, source, error)) return false;
   pid_t pid = fork();
   if (pid < 0) { error = "fork(): " + std::string(strerror(errno)); return false; }
   if (pid == 0) {
@@ -676,7 +690,7 @@ int handle_execute(const std::string& payload, std::string& body) {
   std::string error;
   bool ok = g_cfg.zygote_socket.empty()
                 ? run_via_exec(src->str, env, timeout_s, dir, out_path, err_path, oc, error)
-                : run_via_zygote(src->str, env, timeout_s, out_path, err_path, oc, error);
+                : run_via_zygote(src->str, env, timeout_s, dir, out_path, err_path, oc, error);
   remove_tree_flat(dir);
   if (!ok) { body = error; return 500; }
   std::vector<std::string> files;

@@ -149,9 +149,12 @@ class LocalGpuExecutor:
 
     def _run_process(self, source_code: str, workspace: str, env: dict, capture: Path):
         out_path, err_path = str(capture / "stdout"), str(capture / "stderr")
+        script_path = str(capture / "script.py")
+        with open(script_path, "w", encoding="utf-8", errors="surrogatepass") as f:
+            f.write(source_code)
         req = {"source_code": source_code, "workspace": workspace, "env": env, "stdout_path": out_path,
                "stderr_path": err_path, "broker_socket": self.broker.socket_path,
-               "min_rand_elems": self.min_rand_elems}
+               "min_rand_elems": self.min_rand_elems, "script_path": script_path}
         self._rr = (self._rr + 1) % len(self._zygotes)
         code = self._zygotes[self._rr].run(req, self.timeout)
         if code is None:

@@ -21,6 +21,16 @@ from . import broker_client, numpy_hook, numpy_proxy  # noqa: F401  (everything 
 numpy_hook.numpy_view()  # build the agent-facing numpy view once; children inherit it
 
 
+def _finish_like_an_interpreter() -> None:
+    """What Py_Finalize does before a script's process ends and os._exit() skips: wait for the
+    script's non-daemon threads, then run the atexit callbacks."""
+    import atexit
+    import threading
+
+    threading._shutdown()
+    atexit._run_exitfuncs()
+
+
 def run_in_child(req: dict) -> int:
     os.chdir(req["workspace"])
     env = req.get("env")
@@ -42,13 +52,16 @@ def run_in_child(req: dict) -> int:
     os.close(err_fd)
     sys.stdout = os.fdopen(1, "w", buffering=1, closefd=False)
     sys.stderr = os.fdopen(2, "w", buffering=1, closefd=False)
-    sys.argv = ["script.py"]
+    # the service wrote the source next to the capture files (server.rs:124 writes script.py into a
+    # temp dir): tracebacks quote the failing line and inspect / multiprocessing find a real file
+    script = req.get("script_path") or "script.py"
+    sys.argv = [script]
     numpy_hook.reset_request_state()
     numpy_hook.install(min_rand_elems=req.get("min_rand_elems"))
     code = 0
     try:
-        compiled = compile(req["source_code"], "script.py", "exec")
-        exec(compiled, {"__name__": "__main__", "__builtins__": builtins, "__file__": "script.py"})
+        compiled = compile(req["source_code"], script, "exec")
+        exec(compiled, {"__name__": "__main__", "__builtins__": builtins, "__file__": script})
     except SystemExit as e:
         if e.code is None:
             code = 0
@@ -61,6 +74,10 @@ def run_in_child(req: dict) -> int:
         traceback.print_exc()
         code = 1
     finally:
+        try:
+            _finish_like_an_interpreter()      # also after sys.exit() / an uncaught exception, like CPython
+        except BaseException:
+            pass
         try:
             sys.stdout.flush()
             sys.stderr.flush()

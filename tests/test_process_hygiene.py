@@ -65,3 +65,29 @@ def test_background_processes_die_with_the_request(zyg):
             break
         time.sleep(0.02)
     assert not _alive(pid)
+
+
+def test_script_ends_like_an_interpreter(zyg):
+    """Non-daemon threads are joined and atexit callbacks run before the process ends (os._exit
+    alone would cut both short); tracebacks quote the failing source line."""
+    z, d = zyg
+    src = ("import atexit, threading, time\n"
+           "def late():\n"
+           "    time.sleep(0.3)\n"
+           "    open('from_thread.txt', 'w').write('t')\n"
+           "threading.Thread(target=late).start()\n"
+           "atexit.register(lambda: open('from_atexit.txt', 'w').write('a'))\n"
+           "print('main done')\n")
+    script = d / "script.py"
+    script.write_text(src)
+    req = dict(_req(d, src), script_path=str(script))
+    assert z.run(req, 30) == 0
+    assert (d / "from_thread.txt").read_text() == "t" and (d / "from_atexit.txt").read_text() == "a"
+    src = "import sys\nx = 1\nsys.exit(5)\n"
+    assert z.run(_req(d, "import atexit\natexit.register(lambda: open('after_exit.txt', 'w').write('e'))\n" + src), 30) == 5
+    assert (d / "after_exit.txt").read_text() == "e"                       # also after sys.exit()
+    bad = "def f():\n    return 1 / 0\nf()\n"
+    script.write_text(bad)
+    assert z.run(dict(_req(d, bad), script_path=str(script)), 30) == 1
+    err = (d / "e").read_text()
+    assert "return 1 / 0" in err and "ZeroDivisionError" in err and str(script) in err
