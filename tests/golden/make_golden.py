@@ -16,6 +16,9 @@
                     `executor_pod()` is overridden, to hand out 127.0.0.1 instead of asking
                     kubectl for a pod; one fresh server + workspace per request, like a fresh
                     pod).  Same request bodies as http_replay.json.
+  examples_replay.json  the reference's example scripts under plain CPython (stdout / exit code /
+                    last stderr line / files written): replayed through the native executor
+                    server in both of its modes (tests/test_executor_server.py).
   numeric.npz       seeded inputs and the results stock numpy (the reference's arithmetic)
                     gives for every op class of SURVEY.md §8a; numpy version recorded.
 """
@@ -153,6 +156,32 @@ def pod_replay():
     print("pod_replay.json:", len(cases), "cases")
 
 
+def examples_replay():
+    """The reference's example scripts (examples/*.py, the inputs of its e2e tests and health check)
+    run by PLAIN CPython in an empty directory: stdout, exit code and the last stderr line are what
+    any executor of this path must reproduce.  Skipped: the benchmarks (minutes of CPU), fib.py
+    (a minute of recursion), cowsay.py (module absent here), tcp.py (needs a peer)."""
+    import os
+    import subprocess
+
+    cases = []
+    prev_ws = None
+    for name in ["crash", "escaping", "files", "hello_world_write_file", "hello_world_read_file", "ls", "using_imports"]:
+        src = Path(f"/root/reference/examples/{name}.py").read_text()
+        ws = prev_ws if name == "hello_world_read_file" else tempfile.mkdtemp(prefix="bci-golden-ex-")
+        r = subprocess.run([sys.executable, "-c", src], cwd=ws, capture_output=True, text=True,
+                           env=dict(os.environ, HELLO="h", WORLD="w"))
+        cases.append({"name": name, "source_code": src, "env": {"HELLO": "h", "WORLD": "w"},
+                      "needs_files_of": "hello_world_write_file" if name == "hello_world_read_file" else None,
+                      "stdout": r.stdout.replace(ws, "{WORKSPACE}"), "exit_code": r.returncode,
+                      "stderr_last_line": r.stderr.strip().splitlines()[-1:] or [],
+                      "files": sorted(f for f in os.listdir(ws) if os.path.isfile(os.path.join(ws, f)))})
+        prev_ws = ws
+    (OUT / "examples_replay.json").write_text(json.dumps({"generated_with": {"python": sys.version.split()[0], "numpy": np.__version__},
+                                                            "cases": cases}, indent=1))
+    print("examples_replay.json:", len(cases), "cases")
+
+
 def numeric():
     data = {}
     for name, dt in [("f32", np.float32), ("f64", np.float64), ("i32", np.int32), ("i64", np.int64)]:
@@ -187,10 +216,12 @@ def numeric():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["http", "pod", "numeric"]
+    which = sys.argv[1:] or ["http", "pod", "examples", "numeric"]
     if "http" in which:
         http_replay()
     if "pod" in which:
         pod_replay()
+    if "examples" in which:
+        examples_replay()
     if "numeric" in which:
         numeric()

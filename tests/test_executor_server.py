@@ -276,3 +276,47 @@ def test_files_written_in_the_first_millisecond_are_reported(server):
     assert r["files"] == [str(server.workspace / "early0.txt")]
     r = server.execute("pass")
     assert r["files"] == []
+
+
+@pytest.mark.parametrize("mode", ["exec", "zygote"])
+def test_reference_example_scripts_behave_as_under_plain_python(tmp_path, built, mode):
+    """examples_replay.json = the reference's examples/*.py under plain CPython.  Through the native
+    server (import hook active, seeded numpy stream, pandas / scipy importing the REAL numpy) the
+    stdout, exit code, last stderr line and written files must be the same."""
+    cases = json.loads((GOLDEN / "examples_replay.json").read_text())["cases"]
+    z = None
+    if mode == "zygote":
+        from bee_code_interpreter_b200.zygote import ZygoteClient
+
+        z = ZygoteClient()
+    try:
+        kept = None
+        for case in cases:
+            d = kept if case["needs_files_of"] else tmp_path / case["name"]
+            if not case["needs_files_of"]:
+                d.mkdir()
+                s = Server(d, zygote_socket=z.socket_path if z else None)
+            try:
+                if case["needs_files_of"]:
+                    s = Server.__new__(Server)          # same workspace as the previous case: a new server on it
+                    s.workspace = kept / "workspace"
+                    env = dict(os.environ, APP_LISTEN_ADDR="127.0.0.1:0", APP_WORKSPACE=str(s.workspace), BCI_PYTHON=sys.executable,
+                               PYTHONPATH=str(PKG / "site"), BCI_SCRATCH=str(kept))
+                    if z:
+                        env["BCI_ZYGOTE_SOCKET"] = z.socket_path
+                    from bee_code_interpreter_b200 import build
+
+                    s.proc = subprocess.Popen([str(build.build_server())], env=env, stdout=subprocess.PIPE, text=True)
+                    s.port = int(s.proc.stdout.readline().split()[2].rsplit(":", 1)[1])
+                r = s.execute(case["source_code"], env=case["env"])
+                assert r["stdout"] == case["stdout"].replace("{WORKSPACE}", str(s.workspace)), case["name"]
+                assert r["exit_code"] == case["exit_code"], case["name"]
+                assert r["stderr"].strip().splitlines()[-1:] == case["stderr_last_line"], case["name"]
+                on_disk = sorted(f.name for f in s.workspace.iterdir() if f.is_file())
+                assert on_disk == case["files"], case["name"]
+            finally:
+                s.close()
+            kept = d
+    finally:
+        if z:
+            z.close()
