@@ -91,3 +91,16 @@ def test_script_ends_like_an_interpreter(zyg):
     assert z.run(dict(_req(d, bad), script_path=str(script)), 30) == 1
     err = (d / "e").read_text()
     assert "return 1 / 0" in err and "ZeroDivisionError" in err and str(script) in err
+
+
+def test_files_map_cannot_leave_the_workspace(tmp_path):
+    from bee_code_interpreter_b200 import executor as E
+
+    ws = tmp_path / "workspace"
+    ws.mkdir()
+    assert E._workspace_target(ws, "/workspace/a/b.txt") == ws / "a" / "b.txt"
+    assert E._workspace_target(ws, "/etc/passwd") == ws / "etc" / "passwd"        # server.rs joins strings: stays inside
+    assert E._workspace_target(ws, "/workspace//x") == ws / "x"
+    for bad in ("/workspace/../evil", "/workspace/a/../../evil", "/..", "/workspace/"):
+        with pytest.raises(ValueError):
+            E._workspace_target(ws, bad)
