@@ -320,3 +320,26 @@ def test_reference_example_scripts_behave_as_under_plain_python(tmp_path, built,
     finally:
         if z:
             z.close()
+
+
+def test_json_round_trip_of_arbitrary_text(server):
+    """Random unicode through both directions of the server's own JSON code: request strings
+    arrive \\u-escaped (surrogate pairs included) or as raw UTF-8, stdout goes back escaped by the
+    server; what the script prints must be what was sent."""
+    from hypothesis import given, settings, strategies as st
+
+    alphabet = st.characters(blacklist_categories=("Cs",))            # no lone surrogates: not encodable as UTF-8
+
+    @settings(max_examples=40, deadline=None)
+    @given(text=st.text(alphabet=alphabet, max_size=200), ascii_escapes=st.booleans())
+    def run(text, ascii_escapes):
+        src = "import sys\nsys.stdout.write(" + repr(text) + ")\nsys.stderr.write(" + repr(text[::-1]) + ")"
+        body = json.dumps({"source_code": src, "env": {"T": text.replace("\x00", "")}}, ensure_ascii=ascii_escapes)
+        status, headers, data = server.request("POST", "/execute", body.encode("utf-8"), {"content-type": "application/json"})
+        assert status == 200, data
+        r = json.loads(data)
+        # text mode translates "\r" and "\r\n" on neither side here: the script writes through sys.stdout in
+        # universal-newlines-off mode for output, so the bytes are the text's UTF-8
+        assert r["stdout"] == text and r["stderr"] == text[::-1] and r["exit_code"] == 0
+
+    run()
