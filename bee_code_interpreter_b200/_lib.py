@@ -20,6 +20,8 @@ EW_SIN, EW_COS, EW_TANH, EW_FLOOR, EW_CEIL, EW_LOG1P, EW_EXPM1 = 38, 39, 40, 41,
 RED_SUM, RED_MEAN, RED_MAX, RED_MIN = 0, 1, 2, 3
 PRE_NONE, PRE_SQUARE, PRE_ABS = 0, 1, 2
 ARGMAX, ARGMIN = 0, 1
+PCG_F64, PCG_F32, PCG_U32, PCG_BOUNDED32_I64, PCG_BOUNDED32_I32 = range(5)
+FILL_CONST, FILL_ARANGE, FILL_LINSPACE = 0, 1, 2
 ABI_VERSION = 1
 
 
@@ -46,6 +48,11 @@ class DevInfo(C.Structure):
         ("total_mem", C.c_size_t),
         ("name", C.c_char * 64),
     ]
+
+
+class Pcg64Gen(C.Structure):
+    _fields_ = [("state_lo", C.c_uint64), ("state_hi", C.c_uint64), ("inc_lo", C.c_uint64), ("inc_hi", C.c_uint64),
+                ("low", C.c_int64), ("range", C.c_uint64)]
 
 
 class Sha256State(C.Structure):
@@ -77,6 +84,8 @@ SIGNATURES = {
     "bci_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "bci_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "bci_memset": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t]),
+    "bci_h2d_fd": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_size_t]),
+    "bci_d2h_fd": (C.c_int, [C.c_int, C.c_uint64, C.c_void_p, C.c_size_t]),
     "bci_sync": (C.c_int, []),
     "bci_timer_begin": (C.c_int, []),
     "bci_timer_end": (C.c_int, [C.POINTER(C.c_float)]),
@@ -95,6 +104,10 @@ SIGNATURES = {
     "bci_rand_f64": (C.c_int, [C.c_int, _VPP, _SZP, C.POINTER(C.c_uint64)]),
     "bci_rand_normal_f64": (C.c_int, [C.c_int, _VPP, _SZP, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bci_rand_mt19937_f64": (C.c_int, [C.c_int, _VPP, _SZP, C.POINTER(C.c_uint32)]),
+    "bci_rand_pcg64": (C.c_int, [C.c_int, C.c_int, _VPP, _SZP, C.POINTER(Pcg64Gen), C.POINTER(C.c_uint32)]),
+    "bci_reduce_rand_f64": (C.c_int, [C.c_int, C.c_int, C.c_int, _SZP, C.POINTER(C.c_uint64), C.c_void_p]),
+    "bci_fill": (C.c_int, [C.c_int, C.c_int, C.c_int, _VPP, _SZP, C.POINTER(Scalar), C.POINTER(Scalar), C.POINTER(Scalar)]),
+    "bci_cast": (C.c_int, [C.c_int, C.c_int, C.c_int, _VPP, _VPP, _SZP]),
     "bci_matmul_f32": (C.c_int, [C.c_int, _VPP, _VPP, _VPP, C.c_int, C.c_int, C.c_int]),
     "bci_sha256": (C.c_int, [C.c_int, _VPP, _SZP, C.c_int, C.c_void_p]),
     "bci_sha256_init": (C.c_int, [C.POINTER(Sha256State)]),

@@ -36,6 +36,47 @@ class LocalBackend:
     def rand(self, n, seed):
         return self._new(n * 8, lambda out: self.dev.rand_f64([out], [n], [seed]))
 
+    def rand_pcg(self, kind, n, state, inc, low=0, span=0):
+        """-> (buffer, draws numpy would have rejected)."""
+        box = {}
+        odt = self.dev.PCG_OUT_DTYPE[kind]
+
+        def run(out):
+            box["rej"] = int(self.dev.rand_pcg64(kind, [out], [n], [(state, inc, low, span)])[0])
+        return self._new(n * odt.itemsize, run), box["rej"]
+
+    def reduce_rand(self, op, n, seed, pre=L.PRE_NONE):
+        return self.dev.reduce_rand_f64(op, [n], [seed], pre=pre)[0]
+
+    def fill_new(self, kind, dtype, n, a, b=None, c=None):
+        dtype = np.dtype(dtype)
+        return self._new(n * dtype.itemsize, lambda out: self.dev.fill(
+            kind, dtype, [out], [n], [a], [b] if b is not None else None, [c] if c is not None else None))
+
+    def cast_new(self, src_dtype, dst_dtype, ptr, n):
+        return self._new(n * np.dtype(dst_dtype).itemsize,
+                         lambda out: self.dev.cast(src_dtype, dst_dtype, [ptr], [out], [n]))
+
+    def upload_fd(self, fd, offset, nbytes):
+        return self._new(nbytes, lambda out: self.dev.h2d_fd(out, fd, offset, nbytes))
+
+    def export(self, ptr, nbytes, fd, header=b""):
+        """Array -> file behind `header`, digest of header||array computed on the device."""
+        import os
+
+        msg = self.dev.alloc(len(header) + nbytes)
+        try:
+            if header:
+                self.dev.h2d(msg, np.frombuffer(header, dtype=np.uint8))
+                self.dev.sync()
+            self.dev.d2d(msg + len(header), ptr, nbytes)
+            digest = self.dev.sha256_device([msg], [len(header) + nbytes])[0]
+            self.dev.d2h_fd(fd, 0, msg, len(header) + nbytes)
+            os.ftruncate(fd, len(header) + nbytes)
+        finally:
+            self.dev.free(msg)
+        return digest
+
     def rand_normal(self, n, seed, loc, scale):
         return self._new(n * 8, lambda out: self.dev.rand_normal_f64([out], [n], [seed], [loc], [scale]))
 

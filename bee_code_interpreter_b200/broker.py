@@ -157,6 +157,17 @@ class GpuBroker:
             return [None] * len(argl)
         if kind == W.RAND_MT:
             return list(dev.rand_mt19937(col(0), col(1), np.stack(col(2))))
+        if kind == W.RAND_PCG:
+            return [int(r) for r in dev.rand_pcg64(key[1], col(0), col(1), col(2))]
+        if kind == W.REDUCE_RAND:
+            return list(dev.reduce_rand_f64(key[1], col(0), col(1), pre=key[2]))
+        if kind == W.FILL:
+            _, fk, dt, has_c = key
+            dev.fill(fk, dt, col(0), col(1), col(2), col(3), col(4) if has_c else None)
+            return [None] * len(argl)
+        if kind == W.CAST:
+            dev.cast(key[1], key[2], col(0), col(1), col(2))
+            return [None] * len(argl)
         if kind == W.EWISE:
             _, op, dt, has_in1 = key
             dev.ewise(op, dt, col(0), col(1) if has_in1 else None, None if has_in1 else col(2), col(3), col(4))
@@ -215,18 +226,24 @@ class GpuBroker:
 
         try:
             while True:
+                fds: list[int] = []
                 try:
-                    head = W.recv_exact(conn, W.REQ.size)
+                    head = W.recv_exact_fds(conn, W.REQ.size, fds)
                     (op, code, dtc, pre, aux, flags, p0, p1, n, i0, i1, i2, s0, s1, plen, _r) = W.REQ.unpack(head)
-                    payload = W.recv_exact(conn, plen) if plen else b""
+                    payload = W.recv_exact_fds(conn, plen, fds) if plen else b""
                 except (EOFError, OSError):
+                    for f in fds:
+                        os.close(f)
                     break
                 if op == W.FREE:
                     if owned.pop(p0, None) is not None:
                         dev.free(p0)
                     continue
                 try:
-                    value, out = self._handle(op, code, dtc, pre, aux, flags, p0, p1, n, (i0, i1, i2), s0, s1, payload, need, new)
+                    if flags & W.F_FD and not fds:
+                        raise L.BciError(L.ERR_INVALID, "request announces a descriptor but none arrived")
+                    value, out = self._handle(op, code, dtc, pre, aux, flags, p0, p1, n, (i0, i1, i2), s0, s1, payload, need, new,
+                                              fds[0] if fds else None)
                     conn.sendall(W.REP.pack(L.OK, len(out), value & 0xFFFFFFFFFFFFFFFF) + out)
                 except L.BciError as e:
                     text = str(e).encode()
@@ -234,6 +251,9 @@ class GpuBroker:
                 except Exception as e:  # protocol misuse etc.
                     text = repr(e).encode()
                     conn.sendall(W.REP.pack(L.ERR_INVALID, len(text), 0) + text)
+                finally:
+                    for f in fds:
+                        os.close(f)
         except OSError:
             pass
         finally:
@@ -245,7 +265,7 @@ class GpuBroker:
             owned.clear()
             conn.close()
 
-    def _handle(self, op, code, dtc, pre, aux, flags, p0, p1, n, ints, s0, s1, payload, need, new):
+    def _handle(self, op, code, dtc, pre, aux, flags, p0, p1, n, ints, s0, s1, payload, need, new, fd=None):
         dev = self.dev
         dt = _DTYPE.get(dtc)
         isf = dtc in (L.F32, L.F64)
@@ -262,6 +282,28 @@ class GpuBroker:
             p = new(n * 8)
             self.submit((W.RAND_NORMAL,), (p, n, ints[0], W.scalar_from_bits(s0, True), W.scalar_from_bits(s1, True)))
             return p, b""
+        if op == W.RAND_PCG:
+            if len(payload) != 32 or code not in dev.PCG_OUT_DTYPE:
+                raise L.BciError(L.ERR_INVALID, "PCG64 state must be 4 words")
+            w = struct.unpack("<4Q", payload)
+            p = new(n * dev.PCG_OUT_DTYPE[code].itemsize)
+            rej = self.submit((W.RAND_PCG, code), (p, n, (w[0] | (w[1] << 64), w[2] | (w[3] << 64), ints[0], s0)))
+            return p, struct.pack("<I", rej)
+        if op == W.REDUCE_RAND:
+            return _result_bits(np.float64(self.submit((W.REDUCE_RAND, code, pre), (n, s0)))), b""
+        if op == W.FILL:
+            has_c = bool(flags & W.F_ADDEND)
+            out = new(n * dt.itemsize)
+            self.submit((W.FILL, code, dt, has_c), (out, n, W.scalar_from_bits(s0, isf), W.scalar_from_bits(s1, isf),
+                                                   W.scalar_from_bits(ints[0] & 0xFFFFFFFFFFFFFFFF, isf)))
+            return out, b""
+        if op == W.CAST:
+            ddt = _DTYPE.get(aux)
+            if dt is None or ddt is None:
+                raise L.BciError(L.ERR_INVALID, "unknown dtype")
+            out = new(n * ddt.itemsize)
+            self.submit((W.CAST, dt, ddt), (need(p0, n * dt.itemsize), out, n))
+            return out, b""
         if op == W.RAND_MT:
             if len(payload) != 4 * W.MT_STATE_WORDS:
                 raise L.BciError(L.ERR_INVALID, "MT19937 state must be 625 words")
@@ -307,25 +349,43 @@ class GpuBroker:
             dev.d2d(out, need(p0, n), n)
             return out, b""
         if op == W.UPLOAD:
-            data = np.fromfile(payload.decode(), dtype=np.uint8, count=n) if flags & W.F_SHM else np.frombuffer(payload, dtype=np.uint8, count=n)
             p = new(n)
             if n:
-                dev.h2d(p, data)
-                dev.sync()
+                if flags & W.F_FD:
+                    dev.h2d_fd(p, fd, ints[0], n)
+                else:
+                    dev.h2d(p, np.frombuffer(payload, dtype=np.uint8, count=n))
+                    dev.sync()
             return p, b""
         if op == W.DOWNLOAD:
-            host = dev.download(need(p0, n), n, np.uint8)
-            if flags & W.F_SHM:
-                mm = np.memmap(payload.decode(), dtype=np.uint8, mode="r+", shape=(n,))
-                mm[:] = host
-                mm.flush()
+            need(p0, n)
+            if flags & W.F_FD:
+                dev.d2h_fd(fd, ints[0], p0, n)
                 return 0, b""
-            return 0, host.tobytes()
+            return 0, dev.download(p0, n, np.uint8).tobytes()
+        if op == W.EXPORT:
+            if fd is None:
+                raise L.BciError(L.ERR_INVALID, "export needs a descriptor")
+            need(p0, n)
+            msg = new(len(payload) + n)
+            try:
+                if payload:
+                    dev.h2d(msg, np.frombuffer(payload, dtype=np.uint8))
+                dev.d2d(msg + len(payload), p0, n)
+                digest = self.submit((W.SHA256_DEV,), (msg, len(payload) + n))
+                dev.d2h_fd(fd, ints[0], msg, len(payload) + n)
+                if ints[0] == 0:
+                    os.ftruncate(fd, len(payload) + n)
+            finally:
+                dev.free(msg)
+            return 0, digest
         if op == W.SHA256_DEV:
             return 0, self.submit((W.SHA256_DEV,), (need(p0, n), n))
-        if op == W.SHA256_FILE:
-            path = os.fsdecode(payload)
-            data = np.memmap(path, dtype=np.uint8, mode="r") if os.path.getsize(path) else b""
+        if op == W.SHA256_FD:
+            if fd is None:
+                raise L.BciError(L.ERR_INVALID, "hashing a file needs its descriptor")
+            size = os.fstat(fd).st_size
+            data = os.pread(fd, size, 0) if size else b""
             return 0, self.submit((W.SHA256_BYTES,), (data,))
         if op == W.SHA256_BYTES:
             return 0, self.submit((W.SHA256_BYTES,), (payload,))

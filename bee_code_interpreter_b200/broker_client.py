@@ -41,6 +41,16 @@ def _decode_reduce(bits: int, op: int, code: int):
     return np.frombuffer(raw[: dt.itemsize], dtype=dt)[0]
 
 
+def _anon_file() -> int:
+    """An anonymous file in memory (memfd; an unlinked tmpfs file where memfd_create is missing)."""
+    try:
+        return os.memfd_create("bci-xfer", os.MFD_CLOEXEC)
+    except (AttributeError, OSError):
+        fd, path = tempfile.mkstemp(prefix="bci-xfer-", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        os.unlink(path)
+        return fd
+
+
 class RemoteBackend:
     def __init__(self, socket_path: str | None = None):
         self.socket_path = socket_path or os.environ.get(SOCKET_ENV)
@@ -61,13 +71,18 @@ class RemoteBackend:
             self._sock = s
         return self._sock
 
-    def _call(self, op, **kw):
-        """Returns (value, payload)."""
+    def _call(self, op, fd=None, **kw):
+        """Returns (value, payload).  `fd`: a descriptor that rides on the request (SCM_RIGHTS)."""
+        if fd is not None:
+            kw["flags"] = kw.get("flags", 0) | W.F_FD
         msg = W.pack_req(op, **kw)
         with self._lock:
             try:
                 s = self._connection()
-                s.sendall(msg)
+                if fd is not None:
+                    W.send_with_fd(s, msg, fd)
+                else:
+                    s.sendall(msg)
                 status, plen, value = W.REP.unpack(W.recv_exact(s, W.REP.size))
                 payload = W.recv_exact(s, plen) if plen else b""
             except (EOFError, OSError) as e:
@@ -116,27 +131,44 @@ class RemoteBackend:
         arr = np.ascontiguousarray(arr)
         if arr.nbytes <= W.INLINE_MAX:
             return self._call(W.UPLOAD, n=arr.nbytes, payload=arr.tobytes())[0]
-        fd, path = tempfile.mkstemp(prefix="bci-up-", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        fd = _anon_file()                      # the bytes cross in an anonymous memory file, the broker preads it
         try:
-            with os.fdopen(fd, "wb") as f:
-                f.write(memoryview(arr).cast("B"))
-            return self._call(W.UPLOAD, n=arr.nbytes, flags=W.F_SHM, payload=path.encode())[0]
+            view = memoryview(arr).cast("B")
+            done = 0
+            while done < arr.nbytes:
+                done += os.write(fd, view[done: done + (64 << 20)])
+            return self._call(W.UPLOAD, fd=fd, n=arr.nbytes)[0]
         finally:
-            os.unlink(path)
+            os.close(fd)
+
+    def upload_fd(self, fd: int, offset: int, nbytes: int):
+        """Device buffer filled straight from an open file (an input of the `files` map): no host copy here."""
+        return self._call(W.UPLOAD, fd=fd, n=int(nbytes), i0=int(offset))[0]
 
     def download(self, ptr, n, dtype):
         dtype = np.dtype(dtype)
         nbytes = int(n) * dtype.itemsize
         if nbytes <= W.INLINE_MAX:
             return np.frombuffer(self._call(W.DOWNLOAD, p0=ptr, n=nbytes)[1], dtype=dtype).copy()
-        fd, path = tempfile.mkstemp(prefix="bci-down-", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        fd = _anon_file()
         try:
-            os.ftruncate(fd, nbytes)
-            os.close(fd)
-            self._call(W.DOWNLOAD, p0=ptr, n=nbytes, flags=W.F_SHM, payload=path.encode())
-            return np.fromfile(path, dtype=dtype, count=int(n))
+            self._call(W.DOWNLOAD, fd=fd, p0=ptr, n=nbytes)
+            out = np.empty(int(n), dtype=dtype)
+            view = memoryview(out).cast("B")
+            done = 0
+            while done < nbytes:
+                got = os.preadv(fd, [view[done: done + (64 << 20)]], done)
+                if got <= 0:
+                    raise L.BciError(L.ERR_CUDA, "GPU broker wrote a short download")
+                done += got
+            return out
         finally:
-            os.unlink(path)
+            os.close(fd)
+
+    def export(self, ptr, nbytes: int, fd: int, header: bytes = b"") -> bytes:
+        """Array -> the open file `fd` behind `header` (pinned path in the broker); returns the SHA-256 of
+        header||array, computed on the device while the bytes are on their way out."""
+        return self._call(W.EXPORT, fd=fd, p0=ptr, n=int(nbytes), payload=bytes(header))[1]
 
     def copy_buffer(self, src, nbytes):
         return self._call(W.COPY, p0=src, n=int(nbytes))[0]
@@ -144,6 +176,28 @@ class RemoteBackend:
     # ---- ops (one request each; the broker packs concurrent requests into one launch) -------
     def rand(self, n, seed):
         return self._call(W.RAND, n=int(n), s0=int(seed) & 0xFFFFFFFFFFFFFFFF)[0]
+
+    def rand_pcg(self, kind, n, state, inc, low=0, span=0):
+        m64 = (1 << 64) - 1
+        payload = struct.pack("<4Q", state & m64, (state >> 64) & m64, inc & m64, (inc >> 64) & m64)
+        ptr, rep = self._call(W.RAND_PCG, code=int(kind), n=int(n), i0=int(low), s0=int(span) & m64, payload=payload)
+        return ptr, struct.unpack("<I", rep[:4])[0]
+
+    def reduce_rand(self, op, n, seed, pre=L.PRE_NONE):
+        bits = self._call(W.REDUCE_RAND, code=op, pre=pre, n=int(n), s0=int(seed) & 0xFFFFFFFFFFFFFFFF)[0]
+        return _decode_reduce(bits, op, L.F64)
+
+    def fill_new(self, kind, dtype, n, a, b=None, c=None):
+        code = _code(dtype)
+        isf = code in (L.F32, L.F64)
+        cbits = W.scalar_bits(c, isf)
+        if cbits >= 1 << 63:
+            cbits -= 1 << 64          # i0 is a signed field
+        return self._call(W.FILL, code=int(kind), dtype=code, n=int(n), s0=W.scalar_bits(a, isf), s1=W.scalar_bits(b, isf),
+                          i0=cbits, flags=W.F_ADDEND if c is not None else 0)[0]
+
+    def cast_new(self, src_dtype, dst_dtype, ptr, n):
+        return self._call(W.CAST, dtype=_code(src_dtype), aux=_code(dst_dtype), p0=ptr, n=int(n))[0]
 
     def rand_normal(self, n, seed, loc, scale):
         return self._call(W.RAND_NORMAL, n=int(n), i0=int(seed) & 0x7FFFFFFFFFFFFFFF, s0=W.scalar_bits(loc, True),
@@ -197,8 +251,9 @@ class RemoteBackend:
     def sha256(self, ptr, nbytes):
         return self._call(W.SHA256_DEV, p0=ptr, n=int(nbytes))[1]
 
-    def sha256_file(self, path: str) -> bytes:
-        return self._call(W.SHA256_FILE, payload=os.fsencode(path))[1]
+    def sha256_fd(self, fd: int) -> bytes:
+        """SHA-256 of an open regular file; the broker reads it through the descriptor."""
+        return self._call(W.SHA256_FD, fd=fd)[1]
 
     def sha256_bytes(self, data: bytes) -> bytes:
         return self._call(W.SHA256_BYTES, payload=bytes(data))[1]

@@ -10,6 +10,7 @@
 // partials in tile order, so the result is deterministic and independent of how
 // the batch was packed.  No float atomics.
 #include "bci_ops.cuh"
+#include "bci_philox.cuh"
 #include <vector>
 #include <cstring>
 #include <cmath>
@@ -207,6 +208,85 @@ reduce_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict
       }
     }
     results[r] = bits;
+  }
+}
+
+// ---- reductions over a generated operand (K1+K2+K8 fused) -------------------------------------------
+// `numpy.sum(numpy.square(numpy.random.rand(n)))` (examples/benchmark-numpy.py:20-21) with the
+// uniform stream of rand_f64_kernel produced in registers: tile, thread -> element mapping and
+// accumulator layout are those of reduce_kernel<double, OP, PRE, false> reading the materialised
+// array, element e of a request is word pair (e & 1) of Philox counter e >> 1, so the result is
+// bit-identical to bci_rand_f64 + bci_reduce — and no byte of the array touches HBM.
+// Bound: the 20 IMAD.WIDE of Philox4x32-10 per two doubles (fma pipe), not memory.
+template <int OP, int PRE>
+__global__ void __launch_bounds__(kThreads)
+reduce_rand_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
+                   double* __restrict__ partials, unsigned int* __restrict__ counters,
+                   unsigned long long* __restrict__ results) {
+  using P = Red<double, OP>;
+  constexpr int VN = 4;
+  constexpr size_t TILE = (size_t)kThreads * kRedUnroll * kRedRounds * VN;
+  const unsigned long long tile = blockIdx.x;
+  const int r = find_req(tile_start, B, tile);
+  const Req q = reqs[r];
+  const size_t base = (size_t)(tile - q.tile_start) * TILE;
+  const size_t rem = (size_t)q.n - base;
+  const PhiloxKeys keys = philox_keys((uint32_t)((unsigned long long)q.s1.i), (uint32_t)((unsigned long long)q.s1.i >> 32));
+
+  double acc[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) acc[j] = P::init();
+  bool bad = false;
+  if (rem >= TILE) {
+    const uint32_t phi = (uint32_t)(base >> 33);
+    const uint32_t pbase = (uint32_t)(base >> 1);      // TILE is a multiple of 2^14: the low 13 bits are free
+#pragma unroll 1
+    for (int it = 0; it < kRedRounds; ++it) {
+#pragma unroll
+      for (int u = 0; u < kRedUnroll; ++u) {
+        const uint32_t vec = (uint32_t)((it * kRedUnroll + u) * kThreads + threadIdx.x);   // 4 doubles = 2 counters
+        const uint32_t plo = pbase | (vec << 1);
+        const Philox4 a = philox4x32_10(plo, phi, 0u, 0u, keys);
+        const Philox4 b = philox4x32_10(plo | 1u, phi, 0u, 0u, keys);
+        P::accum(acc[0], pre_apply<double, PRE>(u53(a.x, a.y)), bad);
+        P::accum(acc[1], pre_apply<double, PRE>(u53(a.z, a.w)), bad);
+        P::accum(acc[2], pre_apply<double, PRE>(u53(b.x, b.y)), bad);
+        P::accum(acc[3], pre_apply<double, PRE>(u53(b.z, b.w)), bad);
+      }
+    }
+  } else {
+    for (size_t i = threadIdx.x; i < rem; i += kThreads) {
+      const size_t e = base + i;
+      const unsigned long long p = e >> 1;
+      const Philox4 a = philox4x32_10((uint32_t)p, (uint32_t)(p >> 32), 0u, 0u, keys);
+      P::accum(acc[0], pre_apply<double, PRE>((e & 1) ? u53(a.z, a.w) : u53(a.x, a.y)), bad);
+    }
+  }
+  double v = acc[0];
+#pragma unroll
+  for (int j = 1; j < VN; ++j) v = P::combine(v, acc[j]);
+  v = block_reduce<P>(v);
+
+  __shared__ bool is_last;
+  const unsigned long long t0 = q.tile_start;
+  const unsigned long long t1 = __ldg(tile_start + r + 1);
+  if (threadIdx.x == 0) {
+    partials[tile] = v;
+    __threadfence();
+    const unsigned int done = atomicAdd(&counters[r], 1u);
+    is_last = (done == (unsigned int)(t1 - t0 - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double f = P::init();
+  for (unsigned long long t = t0 + threadIdx.x; t < t1; t += kThreads)
+    f = P::combine(f, *reinterpret_cast<volatile double*>(&partials[t]));
+  f = block_reduce<P>(f);
+  if (threadIdx.x == 0) {
+    counters[r] = 0;
+    if (q.aux & kAuxMean) f = f / (double)q.n;
+    results[r] = (unsigned long long)__double_as_longlong(f);
   }
 }
 
@@ -501,9 +581,74 @@ static int launch_argext(int op, Req* reqs, int B, unsigned long long* d_results
   return BCI_OK;
 }
 
+template <int OP>
+static int launch_reduce_rand(int pre, Req* reqs, int B, unsigned long long* d_results) {
+  Ctx& c = ctx();
+  Batch bt;
+  int rc = upload_batch(reqs, B, red_tile_elems<double>(), &bt);
+  if (rc != BCI_OK) return rc;
+  if (bt.total_tiles == 0) return BCI_OK;
+  if (bt.total_tiles > 0x7fffffffull) { set_error("bci_reduce_rand_f64: batch too large for one launch"); return BCI_ERR_INVALID; }
+  void* partials = nullptr;
+  rc = scratch_get(bt.total_tiles * sizeof(double), &partials);
+  if (rc != BCI_OK) return rc;
+  unsigned int* counters = nullptr;
+  rc = counters_get((size_t)B, &counters);
+  if (rc != BCI_OK) return rc;
+  const unsigned grid = (unsigned)bt.total_tiles;
+  double* part = reinterpret_cast<double*>(partials);
+  switch (pre) {
+    case BCI_PRE_NONE: reduce_rand_kernel<OP, BCI_PRE_NONE><<<grid, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, part, counters, d_results); break;
+    case BCI_PRE_SQUARE: reduce_rand_kernel<OP, BCI_PRE_SQUARE><<<grid, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, part, counters, d_results); break;
+    case BCI_PRE_ABS: reduce_rand_kernel<OP, BCI_PRE_ABS><<<grid, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, part, counters, d_results); break;
+    default: set_error("bci_reduce_rand_f64: unknown pre-transform %d", pre); return BCI_ERR_INVALID;
+  }
+  BCI_CHECK_LAUNCH();
+  return BCI_OK;
+}
+
 }  // namespace bci
 
 using namespace bci;
+
+extern "C" int bci_reduce_rand_f64(int op, int pre, int B, const size_t* n, const uint64_t* seed, void* host_out) {
+  BCI_REQUIRE_INIT();
+  if (B <= 0 || !n || !seed || !host_out) { set_error("bci_reduce_rand_f64: bad arguments"); return BCI_ERR_INVALID; }
+  std::vector<Req> reqs((size_t)B);
+  for (int i = 0; i < B; ++i) {
+    Req& q = reqs[i];
+    memset(&q, 0, sizeof q);
+    q.n = n[i];
+    q.s1.i = (int64_t)seed[i];
+    if (op == BCI_RED_MEAN) q.aux |= kAuxMean;
+    if (n[i] == 0 && op != BCI_RED_SUM) {
+      set_error("bci_reduce_rand_f64: request %d is empty (numpy raises/returns nan here)", i);
+      return BCI_ERR_UNSUPPORTED;
+    }
+  }
+  Ctx& c = ctx();
+  void *h = nullptr, *d = nullptr;
+  ResultGuard guard;
+  {
+    std::unique_lock<std::mutex> lk(c.mu);
+    int rc = result_acquire(lk, (size_t)B * 8, &guard.slot, &h, &d);
+    if (rc != BCI_OK) return rc;
+    BCI_CUDA(cudaMemsetAsync(d, 0, (size_t)B * 8, c.stream));
+    unsigned long long* dres = reinterpret_cast<unsigned long long*>(d);
+    switch (op) {
+      case BCI_RED_SUM: case BCI_RED_MEAN: rc = launch_reduce_rand<BCI_RED_SUM>(pre, reqs.data(), B, dres); break;
+      case BCI_RED_MAX: rc = launch_reduce_rand<BCI_RED_MAX>(pre, reqs.data(), B, dres); break;
+      case BCI_RED_MIN: rc = launch_reduce_rand<BCI_RED_MIN>(pre, reqs.data(), B, dres); break;
+      default: set_error("bci_reduce_rand_f64: unknown op %d", op); return BCI_ERR_INVALID;
+    }
+    if (rc != BCI_OK) return rc;
+    if ((rc = result_enqueue_copy(guard.slot, (size_t)B * 8)) != BCI_OK) return rc;
+  }
+  int rc = result_wait(guard.slot);
+  if (rc != BCI_OK) return rc;
+  memcpy(host_out, h, (size_t)B * 8);
+  return BCI_OK;
+}
 
 extern "C" int bci_reduce(int op, int pre, int dtype, int B, const void* const* in, const size_t* n,
                           void* host_out) {

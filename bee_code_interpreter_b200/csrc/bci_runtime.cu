@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <condition_variable>
+#include <cerrno>
+#include <unistd.h>
 
 namespace bci {
 
@@ -337,6 +340,116 @@ int bci_memset(void* dst_dev, int byte, size_t bytes) {
   Ctx& c = ctx();
   std::lock_guard<std::mutex> lk(c.mu);
   BCI_CUDA(cudaMemsetAsync(dst_dev, byte, bytes, c.stream));
+  return BCI_OK;
+}
+
+// ---- pinned file <-> device transfers ---------------------------------------------------------
+namespace {
+constexpr size_t kLaneChunk = 8u << 20;
+constexpr int kLanes = 4;
+struct Lane {
+  cudaStream_t stream = nullptr;
+  uint8_t* buf[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  cudaEvent_t order = nullptr;
+  bool busy = false;
+};
+Lane g_lanes[kLanes];
+std::mutex g_lane_mu;
+std::condition_variable g_lane_cv;
+
+int lane_acquire(Lane** out) {
+  std::unique_lock<std::mutex> lk(g_lane_mu);
+  for (;;) {
+    for (auto& l : g_lanes) {
+      if (l.busy) continue;
+      if (!l.stream) {
+        BCI_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+          BCI_CUDA(cudaHostAlloc((void**)&l.buf[i], kLaneChunk, cudaHostAllocDefault));
+          BCI_CUDA(cudaEventCreateWithFlags(&l.done[i], cudaEventDisableTiming));
+        }
+        BCI_CUDA(cudaEventCreateWithFlags(&l.order, cudaEventDisableTiming));
+      }
+      l.busy = true;
+      *out = &l;
+      return BCI_OK;
+    }
+    g_lane_cv.wait(lk);
+  }
+}
+void lane_release(Lane* l) {
+  { std::lock_guard<std::mutex> lk(g_lane_mu); l->busy = false; }
+  g_lane_cv.notify_one();
+}
+struct LaneGuard { Lane* l = nullptr; ~LaneGuard() { if (l) { cudaStreamSynchronize(l->stream); lane_release(l); } } };
+
+// the lane's stream starts after everything already enqueued on the op stream
+int lane_order_after_ops(Lane* l) {
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lk(c.mu);
+  BCI_CUDA(cudaEventRecord(l->order, c.stream));
+  BCI_CUDA(cudaStreamWaitEvent(l->stream, l->order, 0));
+  return BCI_OK;
+}
+}  // namespace
+
+int bci_h2d_fd(void* dst_dev, int fd, uint64_t file_offset, size_t bytes) {
+  BCI_REQUIRE_INIT();
+  if (bytes == 0) return BCI_OK;
+  if (!dst_dev || fd < 0) { set_error("bci_h2d_fd: bad arguments"); return BCI_ERR_INVALID; }
+  LaneGuard g;
+  int rc = lane_acquire(&g.l);
+  if (rc != BCI_OK) return rc;
+  if ((rc = lane_order_after_ops(g.l)) != BCI_OK) return rc;
+  size_t done = 0;
+  for (int k = 0; done < bytes; ++k) {
+    const int b = k & 1;
+    if (k >= 2) BCI_CUDA(cudaEventSynchronize(g.l->done[b]));      // the DMA out of this bounce buffer has finished
+    const size_t want = bytes - done < kLaneChunk ? bytes - done : kLaneChunk;
+    size_t got = 0;
+    while (got < want) {
+      ssize_t r = ::pread(fd, g.l->buf[b] + got, want - got, (off_t)(file_offset + done + got));
+      if (r < 0 && errno == EINTR) continue;
+      if (r <= 0) { set_error("bci_h2d_fd: file ends %zu bytes short (%s)", bytes - done - got, r < 0 ? strerror(errno) : "EOF"); return BCI_ERR_INVALID; }
+      got += (size_t)r;
+    }
+    BCI_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst_dev) + done, g.l->buf[b], want, cudaMemcpyHostToDevice, g.l->stream));
+    BCI_CUDA(cudaEventRecord(g.l->done[b], g.l->stream));
+    done += want;
+  }
+  BCI_CUDA(cudaStreamSynchronize(g.l->stream));
+  return BCI_OK;
+}
+
+int bci_d2h_fd(int fd, uint64_t file_offset, const void* src_dev, size_t bytes) {
+  BCI_REQUIRE_INIT();
+  if (bytes == 0) return BCI_OK;
+  if (!src_dev || fd < 0) { set_error("bci_d2h_fd: bad arguments"); return BCI_ERR_INVALID; }
+  LaneGuard g;
+  int rc = lane_acquire(&g.l);
+  if (rc != BCI_OK) return rc;
+  if ((rc = lane_order_after_ops(g.l)) != BCI_OK) return rc;
+  const size_t chunks = (bytes + kLaneChunk - 1) / kLaneChunk;
+  auto issue = [&](size_t k) -> int {
+    const size_t off = k * kLaneChunk, want = bytes - off < kLaneChunk ? bytes - off : kLaneChunk;
+    BCI_CUDA(cudaMemcpyAsync(g.l->buf[k & 1], static_cast<const uint8_t*>(src_dev) + off, want, cudaMemcpyDeviceToHost, g.l->stream));
+    BCI_CUDA(cudaEventRecord(g.l->done[k & 1], g.l->stream));
+    return BCI_OK;
+  };
+  if ((rc = issue(0)) != BCI_OK) return rc;
+  for (size_t k = 0; k < chunks; ++k) {
+    if (k + 1 < chunks && (rc = issue(k + 1)) != BCI_OK) return rc;   // DMA of the next chunk runs while this one is written
+    BCI_CUDA(cudaEventSynchronize(g.l->done[k & 1]));
+    const size_t off = k * kLaneChunk, want = bytes - off < kLaneChunk ? bytes - off : kLaneChunk;
+    size_t put = 0;
+    while (put < want) {
+      ssize_t r = ::pwrite(fd, g.l->buf[k & 1] + put, want - put, (off_t)(file_offset + off + put));
+      if (r < 0 && errno == EINTR) continue;
+      if (r <= 0) { set_error("bci_d2h_fd: write failed: %s", strerror(errno)); return BCI_ERR_INVALID; }
+      put += (size_t)r;
+    }
+  }
   return BCI_OK;
 }
 

@@ -294,6 +294,61 @@ def rand_mt19937(out_ptrs: Sequence[int], ns: Sequence[int], states: np.ndarray)
     return st
 
 
+PCG_OUT_DTYPE = {_lib.PCG_F64: np.dtype(np.float64), _lib.PCG_F32: np.dtype(np.float32), _lib.PCG_U32: np.dtype(np.uint32),
+                 _lib.PCG_BOUNDED32_I64: np.dtype(np.int64), _lib.PCG_BOUNDED32_I32: np.dtype(np.int32)}
+
+
+def rand_pcg64(kind: int, out_ptrs: Sequence[int], ns: Sequence[int], gens: Sequence[tuple]) -> np.ndarray:
+    """numpy.random.Generator(PCG64) streams: gens[i] = (state, inc[, low, range]) with the 128-bit
+    integers of `bit_generator.state["state"]`.  Returns the per-request count of draws numpy would
+    have rejected (bounded kinds; 0 everywhere = the output IS numpy's stream)."""
+    B = len(out_ptrs)
+    arr = (_lib.Pcg64Gen * B)()
+    m64 = (1 << 64) - 1
+    for i, g in enumerate(gens):
+        state, inc = int(g[0]), int(g[1])
+        arr[i].state_lo, arr[i].state_hi = state & m64, (state >> 64) & m64
+        arr[i].inc_lo, arr[i].inc_hi = inc & m64, (inc >> 64) & m64
+        if len(g) > 2:
+            arr[i].low, arr[i].range = int(g[2]), int(g[3])
+    bounded = kind in (_lib.PCG_BOUNDED32_I64, _lib.PCG_BOUNDED32_I32)
+    rej = np.zeros(B, dtype=np.uint32)
+    _lib.check(_lib.load().bci_rand_pcg64(int(kind), B, _lib.ptr_array(out_ptrs), _lib.size_array(ns), arr,
+                                          rej.ctypes.data_as(C.POINTER(C.c_uint32)) if bounded else None))
+    return rej
+
+
+def reduce_rand_f64(op: int, ns: Sequence[int], seeds: Iterable[int], pre: int = _lib.PRE_NONE) -> np.ndarray:
+    """reduce_op(pre(rand(n))) with the operand generated in registers (same stream as rand_f64)."""
+    seeds = [int(s) & 0xFFFFFFFFFFFFFFFF for s in seeds]
+    B = len(seeds)
+    raw = np.zeros(B, dtype=np.uint64)
+    _lib.check(_lib.load().bci_reduce_rand_f64(op, pre, B, _lib.size_array(ns), (C.c_uint64 * B)(*seeds),
+                                               C.c_void_p(raw.ctypes.data)))
+    return raw.view(np.float64).copy()
+
+
+def fill(kind: int, dtype, out_ptrs: Sequence[int], ns: Sequence[int], a: Sequence, b: Sequence | None = None,
+         c: Sequence | None = None) -> None:
+    code = dtype_code(dtype)
+    B = len(out_ptrs)
+    _lib.check(_lib.load().bci_fill(int(kind), code, B, _lib.ptr_array(out_ptrs), _lib.size_array(ns),
+                                    _scalars(a, code, B), _scalars(b, code, B), _scalars(c, code, B)))
+
+
+def cast(src_dtype, dst_dtype, in_ptrs: Sequence[int], out_ptrs: Sequence[int], ns: Sequence[int]) -> None:
+    _lib.check(_lib.load().bci_cast(dtype_code(src_dtype), dtype_code(dst_dtype), len(in_ptrs), _lib.ptr_array(in_ptrs),
+                                    _lib.ptr_array(out_ptrs), _lib.size_array(ns)))
+
+
+def h2d_fd(dst_ptr: int, fd: int, offset: int, nbytes: int) -> None:
+    _lib.check(_lib.load().bci_h2d_fd(C.c_void_p(dst_ptr), int(fd), int(offset), int(nbytes)))
+
+
+def d2h_fd(fd: int, offset: int, src_ptr: int, nbytes: int) -> None:
+    _lib.check(_lib.load().bci_d2h_fd(int(fd), int(offset), C.c_void_p(src_ptr), int(nbytes)))
+
+
 def matmul_f32(a_ptrs: Sequence[int], b_ptrs: Sequence[int], c_ptrs: Sequence[int], M: int, N: int, K: int) -> None:
     _lib.check(_lib.load().bci_matmul_f32(len(a_ptrs), _lib.ptr_array(a_ptrs), _lib.ptr_array(b_ptrs),
                                           _lib.ptr_array(c_ptrs), int(M), int(N), int(K)))

@@ -107,7 +107,7 @@ class DeviceArray(NDArrayOperatorsMixin):
     @property
     def itemsize(self): return self._dtype.itemsize
     @property
-    def T(self): return self.__array__().T
+    def T(self): return self._expose_host().T
 
     def __len__(self):
         if not self._shape:
@@ -140,28 +140,48 @@ class DeviceArray(NDArrayOperatorsMixin):
         self._ptr = out
         self._deferred = None
 
-    def __array__(self, dtype=None, copy=None):
+    def _host_view(self) -> np.ndarray:
+        """The cached host copy for INTERNAL, read-only use (printing, fallbacks, indexing that
+        copies).  Anything that hands the cache out where agent code could write to it goes
+        through `_expose_host` instead."""
         if self._host is None:
             try:
                 ptr = self._device_ptr()
                 self._host = self._backend.download(ptr, self.size, self._dtype).reshape(self._shape)
             except L.BciError:
                 self._host = self._eval_on_host()
-        arr = self._host
-        if dtype is not None and np.dtype(dtype) != arr.dtype:
-            return arr.astype(dtype)
-        return arr.copy() if copy else arr
+        return self._host
+
+    def _expose_host(self) -> np.ndarray:
+        """The host copy is about to be handed out WRITABLE (np.asarray(x), a slice view, a
+        mutating ndarray method): from here on it is the single source of truth — the device
+        copy is dropped and uploaded again only if a later device op needs it."""
+        host = self._host_view()
+        if not host.flags.writeable:
+            host = self._host = host.copy()
+        self._before_mutation()
+        if self._ptr is not None:
+            self._backend.free(self._ptr)
+            self._ptr = None
+        self._deferred = None
+        return host
+
+    def __array__(self, dtype=None, copy=None):
+        if copy or (dtype is not None and np.dtype(dtype) != self._dtype):
+            arr = self._host_view()
+            return arr.astype(dtype) if dtype is not None and np.dtype(dtype) != arr.dtype else arr.copy()
+        return self._expose_host()
 
     def _eval_on_host(self) -> np.ndarray:
         """Deferred expression evaluated by numpy (device unavailable for it)."""
         d = self._deferred
         if d is None:
-            raise
+            raise L.BciError(L.ERR_CUDA, "device array lost: neither a host copy nor a producer to re-run")
         if d[0] == "unary":
-            return _UNARY_NP[d[1]](np.asarray(d[2]))
+            return _UNARY_NP[d[1]](_h(d[2]))
         _, op, a, b, scalar = d
-        rhs = np.asarray(b) if b is not None else self._dtype.type(scalar)
-        return _BINARY_NP[op](np.asarray(a), rhs)
+        rhs = _h(b) if b is not None else self._dtype.type(scalar)
+        return _BINARY_NP[op](_h(a), rhs)
 
     def _assign(self, value) -> None:
         """`self[...] = value` for a whole-array result (same shape): take its data over."""
@@ -173,7 +193,7 @@ class DeviceArray(NDArrayOperatorsMixin):
             self._ptr, value._ptr = ptr, None      # ownership moves; `value` is a dead temporary
             self._host, self._deferred = value._host, None
             return
-        host = np.asarray(value)
+        host = _h(value)
         if host.shape != self._shape:
             host = np.broadcast_to(host, self._shape)
         self._host = np.array(host, dtype=self._dtype)   # same-kind cast like numpy's out=
@@ -207,7 +227,10 @@ class DeviceArray(NDArrayOperatorsMixin):
                 if ufunc is np.matmul and len(inputs) == 2:
                     return matmul(inputs[0], inputs[1])
             if method == "reduce" and ufunc in REDUCE_UFUNCS and len(inputs) == 1:
-                if _plain_reduce_kwargs(kwargs):
+                # ufunc.reduce defaults to axis=0 (NOT a full reduction for ndim > 1)
+                axis = kwargs.get("axis", 0)
+                full = axis is None or (getattr(inputs[0], "ndim", 0) == 1 and axis in (0, -1))
+                if full and _plain_reduce_kwargs(kwargs):
                     return _reduce(REDUCE_UFUNCS[ufunc], inputs[0])
         except (_Fallback, L.Unsupported, L.BciError):
             pass
@@ -225,7 +248,7 @@ class DeviceArray(NDArrayOperatorsMixin):
                 return outs[0]
             if any(isinstance(o, DeviceArray) for o in outs):
                 return NotImplemented
-        host_inputs = tuple(np.asarray(x) if isinstance(x, DeviceArray) else x for x in inputs)
+        host_inputs = tuple(_h(x) if isinstance(x, DeviceArray) else x for x in inputs)
         return getattr(ufunc, method)(*host_inputs, **kwargs)
 
     def __array_function__(self, func, types, args, kwargs):
@@ -235,6 +258,8 @@ class DeviceArray(NDArrayOperatorsMixin):
                 return handler(*args, **kwargs)
             except (_Fallback, L.Unsupported, L.BciError, TypeError):
                 pass
+        if isinstance(kwargs.get("out"), DeviceArray):   # numpy writes into the host copy: it becomes the truth
+            kwargs = dict(kwargs, out=kwargs["out"]._expose_host())
         return func(*_to_host(args), **_to_host(kwargs))
 
     # ---- methods numpy's own wrappers and agent code call --------------------------------
@@ -249,24 +274,25 @@ class DeviceArray(NDArrayOperatorsMixin):
         try:
             return _dot(self, other)
         except (_Fallback, L.Unsupported, L.BciError):
-            return np.dot(np.asarray(self), np.asarray(other))
+            return np.dot(_h(self), _h(other))
 
     def var(self, axis=None, dtype=None, out=None, ddof=0, **kw):
         try:
             return _var(self, axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
         except (_Fallback, L.Unsupported, L.BciError):
-            return np.asarray(self).var(axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
+            return _h(self).var(axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
 
     def std(self, axis=None, dtype=None, out=None, ddof=0, **kw):
         try:
             return _std(self, axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
         except (_Fallback, L.Unsupported, L.BciError):
-            return np.asarray(self).std(axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
+            return _h(self).std(axis=axis, dtype=dtype, out=out, ddof=ddof, **kw)
 
     def astype(self, dtype, *a, **kw):
         if np.dtype(dtype) == self._dtype and not a and not kw:
             return self.copy()
-        return np.asarray(self).astype(dtype, *a, **kw)
+        out = _h(self).astype(dtype, *a, **kw)
+        return out.copy() if out is self._host else out   # astype(copy=False) must not leak the cache
 
     def copy(self, order="C"):
         out = self._backend.copy_buffer(self._device_ptr(), self.nbytes)
@@ -275,12 +301,12 @@ class DeviceArray(NDArrayOperatorsMixin):
     def reshape(self, *shape, **kw):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
-        return np.asarray(self).reshape(*shape, **kw)
+        return self._expose_host().reshape(*shape, **kw)   # a view of the host copy
 
-    def ravel(self, *a, **kw): return self if self.ndim == 1 and not a and not kw else np.asarray(self).ravel(*a, **kw)
-    def flatten(self, *a, **kw): return np.asarray(self).flatten(*a, **kw)
-    def tolist(self): return np.asarray(self).tolist()
-    def item(self, *a): return np.asarray(self).item(*a)
+    def ravel(self, *a, **kw): return self if self.ndim == 1 and not a and not kw else self._expose_host().ravel(*a, **kw)
+    def flatten(self, *a, **kw): return _h(self).flatten(*a, **kw)
+    def tolist(self): return _h(self).tolist()
+    def item(self, *a): return _h(self).item(*a)
 
     def sort(self, axis=-1, kind=None, order=None):
         """In-place like ndarray.sort."""
@@ -291,35 +317,54 @@ class DeviceArray(NDArrayOperatorsMixin):
         self._host = None
 
     def __getitem__(self, key):
-        return np.asarray(self)[key]
+        host = self._host_view()
+        out = host[key]
+        if isinstance(out, np.ndarray) and out.size and np.shares_memory(out, host):
+            return self._expose_host()[key]     # a writable VIEW of the host copy leaves the proxy
+        return out
 
     def __setitem__(self, key, value):
         self._before_mutation()
-        host = np.asarray(self)
+        host = _h(self)
         if not host.flags.writeable:
             host = host.copy()
-        host[key] = np.asarray(value) if isinstance(value, DeviceArray) else value
+        host[key] = _h(value) if isinstance(value, DeviceArray) else value
         self._host = host
         if self._ptr is not None:  # device copy is stale now
             self._backend.free(self._ptr)
             self._ptr = None
         self._deferred = None
 
-    def __iter__(self): return iter(np.asarray(self))
-    def __repr__(self): return repr(np.asarray(self))
-    def __str__(self): return str(np.asarray(self))
-    def __format__(self, spec): return format(np.asarray(self), spec)
-    def __float__(self): return float(np.asarray(self))
-    def __int__(self): return int(np.asarray(self))
-    def __bool__(self): return bool(np.asarray(self))
-    def __index__(self): return operator.index(np.asarray(self))
-    def __contains__(self, item): return item in np.asarray(self)
+    def __iter__(self): return iter(_h(self) if self.ndim <= 1 else self._expose_host())   # rows are views
+    def __repr__(self): return repr(_h(self))
+    def __str__(self): return str(_h(self))
+    def __format__(self, spec): return format(_h(self), spec)
+    def __float__(self): return float(_h(self))
+    def __int__(self): return int(_h(self))
+    def __bool__(self): return bool(_h(self))
+    def __index__(self): return operator.index(_h(self))
+    def __contains__(self, item): return item in _h(self)
 
     def __getattr__(self, name):
         # anything else an ndarray has (std, var, round, clip, ...): numpy on the host copy
         if name.startswith("_"):
             raise AttributeError(name)
-        return getattr(np.asarray(self), name)
+        if name in _PURE_NDARRAY_ATTRS:
+            return getattr(self._host_view(), name)
+        # unknown ndarray attribute: it may mutate (fill, put, partition, resize, ...) or return a
+        # view (squeeze, transpose, view, ...): the host copy becomes the single source of truth
+        return getattr(self._expose_host(), name)
+
+
+# ndarray attributes that neither mutate the array nor return a view of it
+_PURE_NDARRAY_ATTRS = frozenset({
+    "round", "clip", "any", "all", "prod", "nonzero", "searchsorted", "tobytes", "tofile", "dump", "dumps", "conj",
+    "conjugate", "cumprod", "choose", "compress", "repeat", "take", "trace", "ptp", "strides", "flags"})
+
+
+def _h(x):
+    """Host ndarray of `x` for internal read-only use (never invalidates a device copy)."""
+    return x._host_view() if isinstance(x, DeviceArray) else np.asarray(x)
 
 
 _UNARY_NP = {L.EW_SQUARE: np.square, L.EW_ABS: np.absolute, L.EW_NEG: np.negative, L.EW_SQRT: np.sqrt,
@@ -332,7 +377,7 @@ _BINARY_NP = {L.EW_ADD: np.add, L.EW_SUB: np.subtract, L.EW_MUL: np.multiply, L.
 
 def _to_host(obj):
     if isinstance(obj, DeviceArray):
-        return np.asarray(obj)
+        return obj._host_view()
     if isinstance(obj, (list, tuple)):
         return type(obj)(_to_host(o) for o in obj)
     if isinstance(obj, dict):
@@ -447,7 +492,7 @@ def _method_reduce(np_func, red_op, x, axis, dtype, out, kw):
     kw = {k: v for k, v in kw.items() if v is not np._NoValue}
     if dtype is not None:
         kw["dtype"] = dtype
-    return np_func(np.asarray(x), axis=axis, out=out, **kw)
+    return np_func(_h(x), axis=axis, out=out, **kw)
 
 
 def _np_sum(a, axis=None, dtype=None, out=None, **kw): return _method_reduce(np.sum, L.RED_SUM, _need_dev(a), axis, dtype, out, kw)

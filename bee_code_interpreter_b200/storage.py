@@ -61,14 +61,16 @@ class HashService:
             raise box[1]
         return box[0]
 
-    def hash_file(self, path: str) -> bytes:
+    def hash_fd(self, fd: int) -> bytes:
+        """SHA-256 of an open regular file (the descriptor stays open and is read from offset 0)."""
         stream = self.new_stream()
-        with open(path, "rb") as f:
-            while True:
-                chunk = f.read(8 << 20)
-                if not chunk:
-                    break
-                self.update(stream, chunk)
+        off = 0
+        while True:
+            chunk = os.pread(fd, 8 << 20, off)
+            if not chunk:
+                break
+            off += len(chunk)
+            self.update(stream, chunk)
         return self.final(stream)
 
     def close(self):
@@ -155,8 +157,8 @@ class RemoteHashService:
             stream.state = self._backend().sha256_update(None, b"")
         return self._backend().sha256_final(stream.state)
 
-    def hash_file(self, path: str) -> bytes:
-        return self._backend().sha256_file(path)
+    def hash_fd(self, fd: int) -> bytes:
+        return self._backend().sha256_fd(fd)     # the descriptor crosses the socket (SCM_RIGHTS), never a path
 
     def close(self):
         pass
@@ -231,16 +233,44 @@ class ContentAddressedStorage:
     async def put_file(self, path: str) -> str:
         """Stores an existing file (an executor output) under its SHA-256: hashed where it
         lies, then moved into the store (copy across filesystems).  Not in the reference's
-        Storage; the streaming `writer()` above is the protocol-compatible path."""
-        import shutil
+        Storage; the streaming `writer()` above is the protocol-compatible path.
 
-        digest = (await asyncio.to_thread(self.hasher.hash_file, str(path))).hex()
-        await self.storage_path.mkdir(parents=True, exist_ok=True)
-        target = self.storage_path / digest
-        if not await target.exists():
-            tmp = self.storage_path / (".tmp-" + secrets.token_hex(16))
-            await asyncio.to_thread(shutil.move, str(path), str(tmp))
-            await tmp.rename(target)
+        Only regular files get in: the source is opened with O_NOFOLLOW and the bytes that were
+        hashed are the bytes of that descriptor, so a symlink a script planted can neither enter
+        the store nor redirect the id to another file.  Dedupe is a hard link with O_EXCL semantics
+        (`os.link` fails if the id exists), so two writers of the same content cannot race."""
+        import shutil
+        import stat as stat_mod
+
+        fd = await asyncio.to_thread(os.open, str(path), os.O_RDONLY | os.O_NOFOLLOW | os.O_CLOEXEC)
+        try:
+            st = os.fstat(fd)
+            if not stat_mod.S_ISREG(st.st_mode):
+                raise ValueError(f"{path!r} is not a regular file")
+            digest = (await asyncio.to_thread(self.hasher.hash_fd, fd)).hex()
+            await self.storage_path.mkdir(parents=True, exist_ok=True)
+            target = self.storage_path / digest
+            if not await target.exists():
+                tmp = str(self.storage_path / (".tmp-" + secrets.token_hex(16)))
+
+                def place():
+                    try:
+                        os.rename(str(path), tmp)                       # same filesystem: the inode we hashed
+                        if os.stat(tmp, follow_symlinks=False).st_ino != st.st_ino:
+                            raise OSError("source changed under the store")
+                    except OSError:
+                        with open(tmp, "wb") as out, os.fdopen(os.dup(fd), "rb") as src:   # across filesystems: copy the hashed descriptor
+                            shutil.copyfileobj(src, out, 8 << 20)
+                    try:
+                        os.link(tmp, str(target))                       # EEXIST = same content already stored
+                    except FileExistsError:
+                        pass
+                    finally:
+                        os.unlink(tmp)
+
+                await asyncio.to_thread(place)
+        finally:
+            os.close(fd)
         return digest
 
     @asynccontextmanager

@@ -129,6 +129,15 @@ int bci_h2d(void* dst_dev, const void* src_host, size_t bytes);
 int bci_d2h(void* dst_host, const void* src_dev, size_t bytes);
 int bci_d2d(void* dst_dev, const void* src_dev, size_t bytes);
 int bci_memset(void* dst_dev, int byte, size_t bytes);
+/* Pinned transfer path between an open file and device memory (the request's `files` map going
+ * in, kubernetes_code_executor.py:100-113; output files coming out, :126-142): the bytes pass
+ * through page-locked bounce buffers on a dedicated copy stream — pread/pwrite of chunk k+1
+ * overlaps the DMA of chunk k — and the library lock is NOT held while data moves, so uploads
+ * do not stall other requests' launches.  The descriptor is only pread/pwritten (never mapped:
+ * a file truncated underneath cannot raise SIGBUS); short files fail with BCI_ERR_INVALID.
+ * Both calls are ordered after everything already enqueued and return when the copy is done. */
+int bci_h2d_fd(void* dst_dev, int fd, uint64_t file_offset, size_t bytes);
+int bci_d2h_fd(int fd, uint64_t file_offset, const void* src_dev, size_t bytes);
 int bci_sync(void);
 
 /* Timing on the op stream with CUDA events (what bench.py reports). */
@@ -186,6 +195,60 @@ int bci_rand_normal_f64(int B, void* const* out, const size_t* n, const uint64_t
  * state after drawing n[i] doubles, ready for numpy's set_state().  out[i]: n[i] float64. */
 #define BCI_MT19937_STATE_WORDS 625
 int bci_rand_mt19937_f64(int B, void* const* out, const size_t* n, uint32_t* states);
+
+/* ---- K8d numpy.random.Generator(PCG64) streams, bit-exact with numpy: the generators BASELINE
+ * configs C2/C3/C5 draw their inputs from (`numpy.random.default_rng(seed)`) and
+ * C4's payload (`.bytes(n)`).  gen[i] is the bit generator's state as numpy reports it
+ * (`bit_generator.state["state"]`: 128-bit `state` and `inc`); out[i] receives n[i] elements that
+ * numpy would have produced starting from that state.  The caller advances the host generator
+ * (PCG64.advance) by the draws consumed: n for F64, ceil(n/2) for the 32-bit kinds.
+ *   BCI_PCG_F64            Generator.random(n)                  (next64 >> 11) * 2^-53
+ *   BCI_PCG_F32            Generator.random(n, dtype=float32)   (next32 >> 8)  * 2^-24
+ *   BCI_PCG_U32            the next32 stream itself             (Generator.bytes, full-range uint32)
+ *   BCI_PCG_BOUNDED32_I64  Generator.integers(low, low+range, n)          2 <= range < 2^32, int64 out
+ *   BCI_PCG_BOUNDED32_I32  Generator.integers(..., dtype=int32)           int32 out
+ * Bounded kinds use numpy's Lemire multiply-shift; a draw numpy would REJECT shifts the rest of
+ * its stream, which a parallel generator cannot follow: rejected[i] (host, B words, required for
+ * bounded kinds) counts them and the caller falls back to numpy when it is not 0 (it is always
+ * 0 for power-of-two ranges).  Asynchronous unless `rejected` is filled. */
+#define BCI_PCG_F64 0
+#define BCI_PCG_F32 1
+#define BCI_PCG_U32 2
+#define BCI_PCG_BOUNDED32_I64 3
+#define BCI_PCG_BOUNDED32_I32 4
+typedef struct bci_pcg64_gen {
+  uint64_t state_lo, state_hi; /* bit_generator.state["state"]["state"] */
+  uint64_t inc_lo, inc_hi;     /* bit_generator.state["state"]["inc"]   */
+  int64_t low;                 /* bounded kinds: lowest value returned  */
+  uint64_t range;              /* bounded kinds: high - low             */
+} bci_pcg64_gen;
+int bci_rand_pcg64(int kind, int B, void* const* out, const size_t* n, const bci_pcg64_gen* gen,
+                   uint32_t* rejected);
+
+/* ---- K1+K2+K8 fused: reduce_op(pre(rand(n))) with the uniform stream of bci_rand_f64(seed)
+ * generated in registers — `numpy.sum(numpy.square(numpy.random.rand(n)))`, the whole body of
+ * examples/benchmark-numpy.py:20-21, without the n*8-byte array ever reaching HBM.  Same values
+ * and same summation order as bci_rand_f64 followed by bci_reduce (bit-identical result).
+ * host_out = B slots of 8 bytes (float64). */
+int bci_reduce_rand_f64(int op, int pre, int B, const size_t* n, const uint64_t* seed, void* host_out);
+
+/* ---- array creation (numpy.zeros/ones/full, numpy.arange, numpy.linspace), SURVEY.md §8a K1:
+ * arrays born on the device never cross PCIe.
+ *   BCI_FILL_CONST     out[j] = a
+ *   BCI_FILL_ARANGE    out[j] = a + j*b   rounded like numpy's @TYPE@_fill (product, then sum);
+ *                      a = first element, b = second - first, both already in the array dtype;
+ *                      out[1] = c if `c` is given (numpy stores start+step itself)
+ *   BCI_FILL_LINSPACE  float64 only: out[j] = j*b + a, out[n-1] = c if `c` is given
+ *                      (numpy/_core/function_base.py linspace: arange(num)*step + start, endpoint fix-up) */
+#define BCI_FILL_CONST 0
+#define BCI_FILL_ARANGE 1
+#define BCI_FILL_LINSPACE 2
+int bci_fill(int kind, int dtype, int B, void* const* out, const size_t* n, const bci_scalar* a,
+             const bci_scalar* b, const bci_scalar* c);
+
+/* ---- numpy.ndarray.astype between the device dtypes (value-preserving or round-to-nearest
+ * casts: f32<->f64, i32<->i64, int->float; float->int is left to numpy). */
+int bci_cast(int src_dtype, int dst_dtype, int B, const void* const* in, void* const* out, const size_t* n);
 
 /* ---- K3 numpy.matmul for 2-D float32, C[i] = A[i] (MxK) @ Bm[i] (KxN), row-major.
  * 3xTF32 split on tcgen05 with fp32 accumulation in TMEM (error ~1e-7 normwise). */

@@ -100,6 +100,21 @@ def d2d(dst, src, nbytes):
     _mem[dst][:nbytes] = _mem[src][:nbytes]
 
 
+def h2d_fd(dst, fd, offset, nbytes):
+    import os
+
+    data = os.pread(fd, nbytes, offset)
+    if len(data) < nbytes:
+        raise L.BciError(L.ERR_INVALID, "file ends short")
+    _mem[dst][:nbytes] = np.frombuffer(data, dtype=np.uint8)
+
+
+def d2h_fd(fd, offset, src, nbytes):
+    import os
+
+    os.pwrite(fd, _mem[src][:nbytes].tobytes(), offset)
+
+
 def upload(arr):
     arr = np.ascontiguousarray(arr)
     p = alloc(arr.nbytes)
@@ -181,6 +196,67 @@ def rand_f64(out_ptrs, ns, seeds):
     calls.append(("rand", len(out_ptrs), None))
     for p, n, s in zip(out_ptrs, ns, seeds):
         _view(p, n, np.float64)[:] = O.rand_f64(n, s)
+
+
+PCG_OUT_DTYPE = {L.PCG_F64: np.dtype(np.float64), L.PCG_F32: np.dtype(np.float32), L.PCG_U32: np.dtype(np.uint32),
+                 L.PCG_BOUNDED32_I64: np.dtype(np.int64), L.PCG_BOUNDED32_I32: np.dtype(np.int32)}
+
+
+def rand_pcg64(kind, out_ptrs, ns, gens):
+    """numpy's own PCG64 Generator is the oracle: state in, n draws out."""
+    calls.append(("rand_pcg", len(out_ptrs), kind))
+    rej = np.zeros(len(out_ptrs), dtype=np.uint32)
+    for i, (p, n, g) in enumerate(zip(out_ptrs, ns, gens)):
+        bg = np.random.PCG64()
+        bg.state = {"bit_generator": "PCG64", "state": {"state": int(g[0]), "inc": int(g[1])}, "has_uint32": 0, "uinteger": 0}
+        gen = np.random.Generator(bg)
+        if kind == L.PCG_F64:
+            out = gen.random(n)
+        elif kind == L.PCG_F32:
+            out = gen.random(n, dtype=np.float32)
+        elif kind == L.PCG_U32:
+            out = gen.integers(0, 1 << 32, n, dtype=np.uint32)
+        else:
+            dt = np.int64 if kind == L.PCG_BOUNDED32_I64 else np.int32
+            low, span = int(g[2]), int(g[3])
+            out = gen.integers(low, low + span, n, dtype=dt)
+            # the real kernel cannot follow rejections: report them like it does
+            consumed = (bg.state["state"]["state"], bg.state["has_uint32"])
+            ref = np.random.PCG64()
+            ref.state = {"bit_generator": "PCG64", "state": {"state": int(g[0]), "inc": int(g[1])}, "has_uint32": 0, "uinteger": 0}
+            ref.advance((n + 1) // 2)
+            rej[i] = 0 if consumed[0] == ref.state["state"]["state"] else 1
+        _view(p, n, PCG_OUT_DTYPE[kind])[:] = out
+    return rej
+
+
+def reduce_rand_f64(op, ns, seeds, pre=L.PRE_NONE):
+    calls.append(("reduce_rand", len(ns), (op, pre)))
+    return np.array([RED[op](PRE[pre](O.rand_f64(n, s))) for n, s in zip(ns, seeds)], dtype=np.float64)
+
+
+def fill(kind, dtype, out_ptrs, ns, a, b=None, c=None):
+    calls.append(("fill", len(out_ptrs), kind))
+    dtype = np.dtype(dtype)
+    for i, (p, n) in enumerate(zip(out_ptrs, ns)):
+        v = _view(p, n, dtype)
+        idx = np.arange(n).astype(dtype)
+        if kind == L.FILL_CONST:
+            v[:] = dtype.type(a[i])
+        elif kind == L.FILL_ARANGE:
+            v[:] = dtype.type(a[i]) + idx * dtype.type(b[i])
+            if c is not None and n > 1:
+                v[1] = dtype.type(c[i])
+        else:
+            v[:] = idx * dtype.type(b[i]) + dtype.type(a[i])
+            if c is not None and n:
+                v[-1] = dtype.type(c[i])
+
+
+def cast(src_dtype, dst_dtype, in_ptrs, out_ptrs, ns):
+    calls.append(("cast", len(in_ptrs), (np.dtype(src_dtype).name, np.dtype(dst_dtype).name)))
+    for p, o, n in zip(in_ptrs, out_ptrs, ns):
+        _view(o, n, dst_dtype)[:] = _view(p, n, src_dtype).astype(dst_dtype)
 
 
 def rand_normal_f64(out_ptrs, ns, seeds, locs, scales):

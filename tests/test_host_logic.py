@@ -449,3 +449,27 @@ def test_changed_files_do_not_depend_on_the_coarse_clock(tmp_path):
     os.utime(ws / "input.txt")                   # touched: ctime / mtime move
     assert "input.txt" in E._changed_files(ws, start, before)
     assert E._changed_files(ws, start, E._snapshot(ws)) == []
+
+
+def test_ufunc_reduce_of_a_2d_array_keeps_numpys_axis_default(be):
+    """ufunc.reduce defaults to axis=0: only 1-D arrays (or axis=None) are full reductions."""
+    h = np.arange(12, dtype=np.float64).reshape(3, 4)
+    x = P.DeviceArray.from_host(be, h.copy())
+    assert np.array_equal(np.add.reduce(x), np.add.reduce(h))
+    assert np.array_equal(np.maximum.reduce(x, axis=0), np.maximum.reduce(h, axis=0))
+    assert np.add.reduce(x, axis=None) == h.sum()
+    v = P.DeviceArray.from_host(be, np.arange(5, dtype=np.float64))
+    fake_device.calls.clear()
+    assert np.add.reduce(v) == 10.0 and names(fake_device.calls) == ["reduce"]
+
+
+def test_writes_through_an_exposed_host_copy_reach_later_device_ops(be):
+    """A view / np.asarray / mutating ndarray method hands out the host cache: it becomes the single
+    source of truth, later device ops re-upload it (stale device copy)."""
+    mk = lambda: P.DeviceArray.from_host(be, np.arange(8, dtype=np.float64))  # noqa: E731
+    x = mk(); v = x[:4]; v[:] = 100; assert x.sum() == 422.0
+    x = mk(); x.fill(0.5); assert x.sum() == 4.0
+    x = mk(); a = np.asarray(x); a[0] = 50; assert x.max() == 50.0 and np.sum(np.square(x)) == float((a * a).sum())
+    x = mk(); assert x[3] == 3.0 and x[[1, 2]].tolist() == [1.0, 2.0] and x._ptr is not None    # copies keep the device buffer
+    x = mk(); np.cumsum(np.arange(8.0), out=x); assert x.sum() == float(np.cumsum(np.arange(8.0)).sum())
+    x = mk(); y = np.square(x); x[0] = 7.0; assert np.asarray(y)[0] == 0.0                       # deferred reader saw the old value
