@@ -19,7 +19,7 @@ class LocalBackend:
     def alloc(self, nbytes): return self.dev.alloc(nbytes)
     def free(self, ptr): self.dev.free(ptr)
     def upload(self, arr): return self.dev.upload(arr)
-    def download(self, ptr, n, dtype): return self.dev.download(ptr, n, dtype)
+    def download(self, ptr, n, dtype, offset=0): return self.dev.download(ptr, n, dtype, offset)
 
     def _new(self, nbytes, fill):
         out = self.dev.alloc(nbytes)
@@ -64,17 +64,21 @@ class LocalBackend:
         """Array -> file behind `header`, digest of header||array computed on the device."""
         import os
 
-        msg = self.dev.alloc(len(header) + nbytes)
-        try:
-            if header:
-                self.dev.h2d(msg, np.frombuffer(header, dtype=np.uint8))
-                self.dev.sync()
-            self.dev.d2d(msg + len(header), ptr, nbytes)
-            digest = self.dev.sha256_device([msg], [len(header) + nbytes])[0]
-            self.dev.d2h_fd(fd, 0, msg, len(header) + nbytes)
-            os.ftruncate(fd, len(header) + nbytes)
-        finally:
-            self.dev.free(msg)
+        hdr = np.frombuffer(header, dtype=np.uint8)
+        if not len(hdr):
+            digest = self.dev.sha256_device([ptr], [nbytes])[0]
+            self.dev.d2h_fd(fd, 0, ptr, nbytes)
+        else:   # one contiguous message on the device: header bytes, then the array
+            host = np.empty(len(hdr) + nbytes, dtype=np.uint8)
+            host[: len(hdr)] = hdr
+            self.dev.d2h(host[len(hdr):], ptr)
+            msg = self.dev.upload(host)
+            try:
+                digest = self.dev.sha256_device([msg], [len(host)])[0]
+                self.dev.d2h_fd(fd, 0, msg, len(host))
+            finally:
+                self.dev.free(msg)
+        os.ftruncate(fd, len(hdr) + nbytes)
         return digest
 
     def rand_normal(self, n, seed, loc, scale):

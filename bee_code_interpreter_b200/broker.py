@@ -358,24 +358,30 @@ class GpuBroker:
                     dev.sync()
             return p, b""
         if op == W.DOWNLOAD:
-            need(p0, n)
+            skip = ints[1]
+            if skip < 0:
+                raise L.BciError(L.ERR_INVALID, "negative offset")
+            need(p0, skip + n)
             if flags & W.F_FD:
-                dev.d2h_fd(fd, ints[0], p0, n)
+                if skip:        # (handles of an injected device module are opaque: go through the host)
+                    os.pwrite(fd, dev.download(p0, n, np.uint8, skip).tobytes(), ints[0])
+                else:
+                    dev.d2h_fd(fd, ints[0], p0, n)
                 return 0, b""
-            return 0, dev.download(p0, n, np.uint8).tobytes()
+            return 0, dev.download(p0, n, np.uint8, skip).tobytes()
         if op == W.EXPORT:
             if fd is None:
                 raise L.BciError(L.ERR_INVALID, "export needs a descriptor")
             need(p0, n)
-            msg = new(len(payload) + n)
+            # (the native broker assembles header||array on the device; handles of an injected device
+            # module are opaque, so this stand-in builds the message on the host)
+            host = np.concatenate([np.frombuffer(payload, dtype=np.uint8), dev.download(p0, n, np.uint8)])
+            msg = dev.upload(host)
             try:
-                if payload:
-                    dev.h2d(msg, np.frombuffer(payload, dtype=np.uint8))
-                dev.d2d(msg + len(payload), p0, n)
-                digest = self.submit((W.SHA256_DEV,), (msg, len(payload) + n))
-                dev.d2h_fd(fd, ints[0], msg, len(payload) + n)
+                digest = self.submit((W.SHA256_DEV,), (msg, len(host)))
+                dev.d2h_fd(fd, ints[0], msg, len(host))
                 if ints[0] == 0:
-                    os.ftruncate(fd, len(payload) + n)
+                    os.ftruncate(fd, len(host))
             finally:
                 dev.free(msg)
             return 0, digest

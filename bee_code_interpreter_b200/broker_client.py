@@ -145,14 +145,16 @@ class RemoteBackend:
         """Device buffer filled straight from an open file (an input of the `files` map): no host copy here."""
         return self._call(W.UPLOAD, fd=fd, n=int(nbytes), i0=int(offset))[0]
 
-    def download(self, ptr, n, dtype):
+    def download(self, ptr, n, dtype, offset=0):
+        """`n` elements starting `offset` elements into the buffer."""
         dtype = np.dtype(dtype)
         nbytes = int(n) * dtype.itemsize
+        skip = int(offset) * dtype.itemsize
         if nbytes <= W.INLINE_MAX:
-            return np.frombuffer(self._call(W.DOWNLOAD, p0=ptr, n=nbytes)[1], dtype=dtype).copy()
+            return np.frombuffer(self._call(W.DOWNLOAD, p0=ptr, n=nbytes, i1=skip)[1], dtype=dtype).copy()
         fd = _anon_file()
         try:
-            self._call(W.DOWNLOAD, fd=fd, p0=ptr, n=nbytes)
+            self._call(W.DOWNLOAD, fd=fd, p0=ptr, n=nbytes, i1=skip)
             out = np.empty(int(n), dtype=dtype)
             view = memoryview(out).cast("B")
             done = 0

@@ -434,15 +434,20 @@ void serve(int fd) {
       case BRK_DOWNLOAD: {
         FdGuard dst;
         if ((rq.flags & BRK_F_FD) && !take_fd(dst)) { ok = reply_err(fd, BCI_ERR_INVALID, "broker: request announces a descriptor but none arrived"); break; }
-        if (!owns(rq.p0, (size_t)rq.n)) { ok = reply_err(fd, BCI_ERR_INVALID, "buffer does not belong to this request"); break; }
+        // i1 = byte offset INTO the buffer: `x[i]`, `x[a:b]` of a device array fetch only what they print
+        size_t end = 0;
+        if (rq.i1 < 0 || __builtin_add_overflow((size_t)rq.i1, (size_t)rq.n, &end) || !owns(rq.p0, end)) {
+          ok = reply_err(fd, BCI_ERR_INVALID, "buffer does not belong to this request"); break;
+        }
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(rq.p0) + rq.i1;
         if (rq.flags & BRK_F_FD) {
-          int rc = rq.i0 < 0 ? BCI_ERR_INVALID : bci_d2h_fd(dst.fd, (uint64_t)rq.i0, reinterpret_cast<void*>(rq.p0), (size_t)rq.n);
+          int rc = rq.i0 < 0 ? BCI_ERR_INVALID : bci_d2h_fd(dst.fd, (uint64_t)rq.i0, src, (size_t)rq.n);
           ok = rc == BCI_OK ? reply(fd, BCI_OK, 0, nullptr, 0) : reply_err(fd, rc, bci_last_error());
         } else if (rq.n > (64u << 20)) {
           ok = reply_err(fd, BCI_ERR_INVALID, "broker: inline downloads stop at 64 MiB, pass a descriptor");
         } else {
           std::vector<uint8_t> host((size_t)rq.n);
-          int rc = rq.n ? bci_d2h(host.data(), reinterpret_cast<void*>(rq.p0), (size_t)rq.n) : BCI_OK;
+          int rc = rq.n ? bci_d2h(host.data(), src, (size_t)rq.n) : BCI_OK;
           ok = rc == BCI_OK ? reply(fd, BCI_OK, 0, host.data(), host.size()) : reply_err(fd, rc, bci_last_error());
         }
         break;

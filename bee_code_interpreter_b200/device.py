@@ -173,10 +173,11 @@ def upload(arr: np.ndarray) -> int:
     return p
 
 
-def download(ptr: int, n: int, dtype) -> np.ndarray:
+def download(ptr: int, n: int, dtype, offset: int = 0) -> np.ndarray:
+    """`n` elements of `dtype`, starting `offset` elements into the buffer."""
     out = np.empty(int(n), dtype=dtype)
     if out.nbytes:
-        d2h(out, ptr)
+        d2h(out, ptr + int(offset) * out.dtype.itemsize)
     return out
 
 

@@ -85,6 +85,7 @@ def _backend():
 def _build_view():
     import numpy as real_np
 
+    from . import _lib as L
     from . import numpy_proxy as P
 
     real_random = real_np.random
@@ -154,7 +155,84 @@ def _build_view():
         shape = (size,) if isinstance(size, (int, real_np.integer)) else tuple(size)
         return _device_normal(shape, loc, scale, lambda: real_random.normal(loc, scale, size))
 
-    random_view = _ModuleView(real_random, {"rand": rand, "random": random_sample, "random_sample": random_sample,
+    # ---- numpy.random.Generator over PCG64 (default_rng): the generator BASELINE configs C2/C3/C5 draw from
+    f64, f32, i64, i32 = (real_np.dtype(t) for t in (real_np.float64, real_np.float32, real_np.int64, real_np.int32))
+
+    def _shape_of(size):
+        if size is None:
+            return None
+        if isinstance(size, (int, real_np.integer)):
+            return (int(size),)
+        try:
+            shape = tuple(int(v) for v in size)
+        except TypeError:
+            return None
+        return shape if all(v >= 0 for v in shape) else None
+
+    def _plain_int(v):
+        return isinstance(v, (int, real_np.integer)) and not isinstance(v, (bool, real_np.bool_))
+
+    class DeviceGenerator(real_random.Generator):
+        """numpy.random.Generator whose large draws are produced on the device, bit for bit numpy's
+        stream (csrc/bci_rand_pcg.cu); everything else — and every case the kernel does not take — is
+        the inherited numpy method on the same bit generator."""
+
+        def _device(self, shape, kind, low=0, span=0):
+            if shape is None or _size_of(shape) < _state["min_rand"]:
+                return None
+            try:
+                return P.device_pcg(_backend(), self, shape, kind, low, span)
+            except Exception as e:
+                if os.environ.get("BCI_DEBUG_FALLBACK"):
+                    print(f"[bci] device Generator draw fell back to numpy: {e!r}", file=sys.stderr)
+                return None
+
+        def random(self, size=None, dtype=real_np.float64, out=None):
+            if out is None:
+                try:
+                    dt = real_np.dtype(dtype)
+                except TypeError:
+                    dt = None
+                kind = L.PCG_F64 if dt == f64 else L.PCG_F32 if dt == f32 else None
+                if kind is not None:
+                    got = self._device(_shape_of(size), kind)
+                    if got is not None:
+                        return got
+            return super().random(size, dtype, out)
+
+        def integers(self, low, high=None, size=None, dtype=real_np.int64, endpoint=False):
+            try:
+                dt = real_np.dtype(dtype)
+            except TypeError:
+                dt = None
+            if dt in (i64, i32) and _plain_int(low) and (high is None or _plain_int(high)):
+                lo, hi = (0, int(low)) if high is None else (int(low), int(high))
+                if endpoint:
+                    hi += 1
+                info = real_np.iinfo(dt)
+                # numpy's 32-bit Lemire path: inclusive range 1 .. 2^32 - 2 (it validates the bounds itself otherwise)
+                if info.min <= lo and hi - 1 <= info.max and 2 <= hi - lo <= 0xFFFFFFFF:
+                    got = self._device(_shape_of(size), L.PCG_BOUNDED32_I64 if dt == i64 else L.PCG_BOUNDED32_I32, lo, hi - lo)
+                    if got is not None:
+                        return got
+            return super().integers(low, high, size, dtype, endpoint)
+
+        def uniform(self, low=0.0, high=1.0, size=None):
+            plain = all(isinstance(v, (int, float)) and not isinstance(v, bool) for v in (low, high))
+            if plain and real_np.isfinite(float(high) - float(low)):
+                got = self._device(_shape_of(size), L.PCG_F64)
+                if got is not None:
+                    # random_uniform(): off + rng * next_double, product and sum each rounded once
+                    return float(low) + (float(high) - float(low)) * got
+            return super().uniform(low, high, size)
+
+    def default_rng(seed=None):
+        if isinstance(seed, real_random.Generator) and not isinstance(seed, DeviceGenerator):
+            return DeviceGenerator(seed.bit_generator)
+        g = real_random.default_rng(seed)
+        return g if isinstance(g, DeviceGenerator) else DeviceGenerator(g.bit_generator)
+
+    random_view = _ModuleView(real_random, {"default_rng": default_rng, "Generator": DeviceGenerator, "rand": rand, "random": random_sample, "random_sample": random_sample,
                                             "ranf": random_sample, "sample": random_sample, "seed": seed,
                                             "randn": randn, "standard_normal": standard_normal, "normal": normal})
 
@@ -172,8 +250,74 @@ def _build_view():
         wrapper.__doc__ = real_fn.__doc__
         return wrapper
 
+    # ---- arrays born on the device: creation functions and numpy.load above the offload threshold
+    def _creation(real_fn, device_fn):
+        def wrapper(*args, **kwargs):
+            try:
+                got = device_fn(*args, **kwargs)
+                if got is not None:
+                    return got
+            except Exception as e:
+                if os.environ.get("BCI_DEBUG_FALLBACK"):
+                    print(f"[bci] {real_fn.__name__} stayed on the host: {e!r}", file=sys.stderr)
+            return real_fn(*args, **kwargs)
+        wrapper.__name__ = real_fn.__name__
+        wrapper.__doc__ = real_fn.__doc__
+        return wrapper
+
+    def _big_shape(shape):
+        shp = _shape_of(shape)
+        return shp if shp is not None and _size_of(shp) >= P.OFFLOAD_MIN_ELEMS else None
+
+    def _full_like(value):
+        def fn(shape, dtype=float, order="C", *, device=None, like=None):
+            shp = _big_shape(shape)
+            if shp is None or order not in ("C", "K", "A") or device is not None or like is not None:
+                return None
+            return P.device_full(_backend(), shp, real_np.dtype(dtype), value)
+        return fn
+
+    def _full(shape, fill_value, dtype=None, order="C", *, device=None, like=None):
+        shp = _big_shape(shape)
+        if shp is None or order not in ("C", "K", "A") or device is not None or like is not None or \
+                not isinstance(fill_value, (int, float)) or isinstance(fill_value, bool):
+            return None
+        dt = real_np.dtype(dtype) if dtype is not None else real_np.asarray(fill_value).dtype
+        return P.device_full(_backend(), shp, dt, fill_value)
+
+    def _arange(*args, dtype=None, device=None, like=None):
+        if device is not None or like is not None or not 1 <= len(args) <= 3 or \
+                not all(isinstance(a, (int, float)) and not isinstance(a, bool) for a in args):
+            return None
+        start, stop, step = (0, args[0], 1) if len(args) == 1 else (args[0], args[1], 1) if len(args) == 2 else args
+        if step == 0:
+            return None
+        dt = real_np.dtype(dtype) if dtype is not None else (
+            real_np.dtype(real_np.int64) if all(isinstance(a, int) for a in (start, stop, step)) else f64)
+        return P.device_arange(_backend(), start, stop, step, dt)
+
+    def _linspace(start, stop, num=50, endpoint=True, retstep=False, dtype=None, axis=0, *, device=None):
+        if retstep or dtype not in (None, float, real_np.float64) or axis != 0 or device is not None or \
+                not all(isinstance(a, (int, float)) and not isinstance(a, bool) for a in (start, stop)) or \
+                not isinstance(num, int) or num < 2:
+            return None
+        return P.device_linspace(_backend(), start, stop, num, bool(endpoint))
+
+    def _load(file, mmap_mode=None, allow_pickle=False, fix_imports=True, encoding="ASCII", *, max_header_size=10000):
+        if mmap_mode is not None or not (isinstance(file, str) or hasattr(file, "__fspath__")) or \
+                not os.fspath(file).endswith(".npy"):
+            return None
+        return P.device_load(_backend(), os.fspath(file))
+
     overrides = {
         "random": random_view,
+        "zeros": _creation(real_np.zeros, _full_like(0)),
+        "ones": _creation(real_np.ones, _full_like(1)),
+        "empty": _creation(real_np.empty, _full_like(0)),
+        "full": _creation(real_np.full, _full),
+        "arange": _creation(real_np.arange, _arange),
+        "linspace": _creation(real_np.linspace, _linspace),
+        "load": _creation(real_np.load, _load),
         "sort": _offloading(P.sort, real_np.sort, 1),
         "argsort": _offloading(P.argsort, real_np.argsort, 1),
         "cumsum": _offloading(P.cumsum, real_np.cumsum, 1),

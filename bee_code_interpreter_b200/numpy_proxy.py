@@ -71,7 +71,7 @@ class DeviceArray(NDArrayOperatorsMixin):
         self._shape = tuple(int(s) for s in shape)
         self._dtype = np.dtype(dtype)
         self._host = None                    # cached host copy
-        self._deferred = deferred            # ("unary", op, a) | ("binary", op, a, b_or_None, scalar)
+        self._deferred = deferred            # ("unary", op, a) | ("binary", op, a, b_or_None, scalar) | ("rand", seed)
         self._dependents = {}                # id -> weakref of deferred arrays that read this one
         if deferred is not None:
             for src in deferred[2:4]:
@@ -129,7 +129,9 @@ class DeviceArray(NDArrayOperatorsMixin):
     def _materialise_deferred(self):
         d = self._deferred
         n = self.size
-        if d[0] == "unary":
+        if d[0] == "rand":        # numpy.random.rand(n) nobody has read yet: now somebody does
+            out = self._backend.rand(n, d[1])
+        elif d[0] == "unary":
             _, op, a = d
             out = self._backend.ewise_new(op, self._dtype, a._device_ptr(), None, None, n)
         else:
@@ -177,6 +179,8 @@ class DeviceArray(NDArrayOperatorsMixin):
         d = self._deferred
         if d is None:
             raise L.BciError(L.ERR_CUDA, "device array lost: neither a host copy nor a producer to re-run")
+        if d[0] == "rand":       # the unseeded legacy generator: any fresh stream is a valid answer
+            return np.random.random_sample(self._shape)
         if d[0] == "unary":
             return _UNARY_NP[d[1]](_h(d[2]))
         _, op, a, b, scalar = d
@@ -291,12 +295,29 @@ class DeviceArray(NDArrayOperatorsMixin):
     def astype(self, dtype, *a, **kw):
         if np.dtype(dtype) == self._dtype and not a and not kw:
             return self.copy()
+        dst = np.dtype(dtype)
+        if not a and not kw and dst in SUPPORTED and (self._dtype.kind == "i" or dst.kind == "f"):
+            try:     # value-preserving / round-to-nearest casts run on the device (float -> int is numpy's)
+                out = self._backend.cast_new(self._dtype, dst, self._device_ptr(), self.size)
+                return DeviceArray(self._backend, out, self._shape, dst)
+            except (L.BciError, AttributeError):
+                pass
         out = _h(self).astype(dtype, *a, **kw)
         return out.copy() if out is self._host else out   # astype(copy=False) must not leak the cache
 
     def copy(self, order="C"):
         out = self._backend.copy_buffer(self._device_ptr(), self.nbytes)
         return DeviceArray(self._backend, out, self._shape, self._dtype)
+
+    def tofile(self, fid, sep="", format="%s"):
+        """ndarray.tofile: raw bytes straight from HBM into the file (pinned path in the broker)."""
+        if sep == "" and isinstance(fid, (str, bytes)) or hasattr(fid, "__fspath__"):
+            try:
+                _export(self, fid, b"")
+                return
+            except (L.BciError, AttributeError, OSError):
+                pass
+        _h(self).tofile(fid, sep, format)
 
     def reshape(self, *shape, **kw):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
@@ -317,6 +338,16 @@ class DeviceArray(NDArrayOperatorsMixin):
         self._host = None
 
     def __getitem__(self, key):
+        if self._host is None and self.ndim == 1 and self.size:
+            # x[i] of an array that lives only in HBM: fetch that element, not the array (`print(s[0], s[-1])`
+            # after a sort of 10^7 rows moves 8 bytes, not 40 MB).  A scalar is a copy in numpy too; slices
+            # are VIEWS there (writes go through), so they take the host-copy path below.
+            n = self._shape[0]
+            try:
+                if isinstance(key, (int, np.integer)) and not isinstance(key, (bool, np.bool_)) and -n <= key < n:
+                    return self._backend.download(self._device_ptr(), 1, self._dtype, int(key) % n)[0]
+            except (L.BciError, TypeError):
+                pass
         host = self._host_view()
         out = host[key]
         if isinstance(out, np.ndarray) and out.size and np.shares_memory(out, host):
@@ -447,6 +478,12 @@ def _reduce(red_op, x):
         raise _Fallback("empty")
     d = x._deferred
     if d is not None:
+        # numpy.random.rand(n) that was never read: generate it in registers inside the reduction
+        if d[0] == "rand":
+            return _result_scalar(be.reduce_rand(red_op, n, d[1]))
+        if d[0] == "unary" and d[1] in PRE_OF and d[2]._deferred is not None and d[2]._deferred[0] == "rand" \
+                and d[2]._ptr is None:
+            return _result_scalar(be.reduce_rand(red_op, n, d[2]._deferred[1], pre=PRE_OF[d[1]]))
         # fold the single-use producer into the reduction's load
         if d[0] == "unary" and d[1] in PRE_OF:
             pre, inner = PRE_OF[d[1]], d[2]
@@ -595,7 +632,42 @@ def _std(a, axis=None, dtype=None, out=None, ddof=0, **kw):
     return np.sqrt(_var(a, axis=axis, dtype=dtype, out=out, ddof=ddof, **kw))
 
 
+def _export(a: DeviceArray, path, header: bytes) -> None:
+    """`a`'s bytes -> the file `path` behind `header`; the broker hashes header||array on the device while the
+    bytes leave through the pinned path, so the object store knows the file's id without reading it back."""
+    import os
+
+    fd = os.open(os.fspath(path), os.O_RDWR | os.O_CREAT | os.O_TRUNC | getattr(os, "O_CLOEXEC", 0), 0o666)
+    try:
+        a._backend.export(a._device_ptr(), a.nbytes, fd, header)
+    finally:
+        os.close(fd)
+
+
+def _np_save(file, arr, allow_pickle=True, fix_imports=np._NoValue):
+    """numpy.save of a device array to a path: the .npy header is built here, the data never visits this process."""
+    import io
+    import os
+
+    arr = _need_dev(arr)
+    if not (isinstance(file, (str, bytes)) or hasattr(file, "__fspath__")):
+        raise _Fallback("file object")
+    path = os.fspath(file)
+    if isinstance(path, bytes):
+        path = os.fsdecode(path)
+    if not path.endswith(".npy"):
+        path += ".npy"
+    head = io.BytesIO()
+    np.lib.format.write_array_header_1_0(head, {"descr": np.lib.format.dtype_to_descr(arr.dtype), "fortran_order": False,
+                                                "shape": arr.shape})
+    try:
+        _export(arr, path, head.getvalue())
+    except (AttributeError, OSError) as e:
+        raise _Fallback(str(e)) from None
+
+
 _FUNCTIONS = {
+    np.save: _np_save,
     np.sum: _np_sum, np.mean: _np_mean, np.max: _np_max, np.min: _np_min, np.amax: _np_max, np.amin: _np_min,
     np.argmax: argmax, np.argmin: argmin, np.cumsum: cumsum, np.sort: sort, np.argsort: argsort,
     np.matmul: matmul, np.dot: _dot, np.var: _var, np.std: _std,
@@ -607,11 +679,15 @@ OFFLOAD_MIN_ELEMS = 1 << 18   # host arrays smaller than this stay with numpy
 
 
 def device_rand(backend, shape, seed: int) -> DeviceArray:
-    """numpy.random.rand / random_sample for an unseeded legacy generator."""
-    n = 1
-    for s in shape:
-        n *= int(s)
-    return DeviceArray(backend, backend.rand(n, seed), shape, np.float64)
+    """numpy.random.rand / random_sample for an unseeded legacy generator.  Nothing is generated yet:
+    a reduction over the result (`numpy.sum(numpy.square(x))`, examples/benchmark-numpy.py:21) draws
+    the stream in registers; any other use materialises it (same seed, same values)."""
+    if not hasattr(backend, "reduce_rand"):
+        n = 1
+        for s in shape:
+            n *= int(s)
+        return DeviceArray(backend, backend.rand(n, seed), shape, np.float64)
+    return DeviceArray(backend, None, shape, np.float64, deferred=("rand", int(seed) & 0xFFFFFFFFFFFFFFFF))
 
 
 def device_normal(backend, shape, seed: int, loc: float = 0.0, scale: float = 1.0) -> DeviceArray:
@@ -647,3 +723,113 @@ def offload(backend, arr):
             and arr.flags["C_CONTIGUOUS"]):
         return DeviceArray.from_host(backend, arr)
     raise _Fallback("host array")
+
+
+# ---- numpy.random.Generator(PCG64) on the device -----------------------------------------------------------
+_M64 = (1 << 64) - 1
+_PCG_MULT = (2549297995355413924 << 64) | 4865540595714422341
+
+
+def _pcg_output(state: int) -> int:
+    """XSL-RR output of a 128-bit PCG64 state (numpy/random/src/pcg64/pcg64.h)."""
+    hi, lo = state >> 64, state & _M64
+    x, rot = hi ^ lo, state >> 122
+    return ((x >> rot) | (x << ((64 - rot) & 63))) & _M64
+
+
+def device_pcg(backend, generator, shape, kind: int, low: int = 0, span: int = 0) -> DeviceArray:
+    """`n` values of `generator` (a numpy Generator over PCG64) produced on the device, bit for bit what
+    numpy would return; the host generator is advanced past them, so draws before and after stay on
+    numpy's stream.  Raises _Fallback (host generator untouched) when the stream cannot be followed."""
+    bg = generator.bit_generator
+    st = bg.state
+    if st.get("bit_generator") != "PCG64":
+        raise _Fallback("bit generator")
+    n = 1
+    for s in shape:
+        n *= int(s)
+    wide = kind == L.PCG_F64
+    if not wide and st["has_uint32"]:
+        raise _Fallback("a buffered 32-bit word is pending")       # rare: an odd number of 32-bit draws came before
+    state, inc = int(st["state"]["state"]), int(st["state"]["inc"])
+    ptr, rejected = backend.rand_pcg(kind, n, state, inc, low, span)
+    if rejected:
+        backend.free(ptr)
+        raise _Fallback("Lemire rejection in the stream")
+    draws = n if wide else (n + 1) // 2
+    bg.advance(draws)           # also clears numpy's buffered 32-bit word: put back what numpy would hold
+    after = bg.state
+    if wide:                    # 64-bit draws never touch the buffered word
+        after["has_uint32"], after["uinteger"] = st["has_uint32"], st["uinteger"]
+    else:                       # the high half of the last draw: pending when n is odd, spent (but still stored) otherwise
+        after["has_uint32"] = n & 1
+        after["uinteger"] = _pcg_output(int(after["state"]["state"])) >> 32 if n else st["uinteger"]
+    bg.state = after
+    dtype = {L.PCG_F64: np.float64, L.PCG_F32: np.float32, L.PCG_U32: np.uint32, L.PCG_BOUNDED32_I64: np.int64,
+             L.PCG_BOUNDED32_I32: np.int32}[kind]
+    return DeviceArray(backend, ptr, shape, dtype)
+
+
+# ---- array creation ---------------------------------------------------------------------------------------
+def device_full(backend, shape, dtype, value) -> DeviceArray:
+    dtype = np.dtype(dtype)
+    if dtype not in SUPPORTED:
+        raise _Fallback("dtype")
+    n = 1
+    for s in shape:
+        n *= int(s)
+    v = dtype.type(value)            # numpy casts the fill value to the array dtype
+    return DeviceArray(backend, backend.fill_new(L.FILL_CONST, dtype, n, v.item()), shape, dtype)
+
+
+def device_arange(backend, start, stop, step, dtype) -> DeviceArray:
+    """numpy.arange for python scalars: length = ceil((stop - start) / step); element i = start + i*delta with
+    delta = dtype(start + step) - dtype(start), like numpy's @TYPE@_fill."""
+    import math
+
+    dtype = np.dtype(dtype)
+    if dtype not in SUPPORTED:
+        raise _Fallback("dtype")
+    n = int(math.ceil((stop - start) / step))
+    if n < OFFLOAD_MIN_ELEMS:
+        raise _Fallback("small")
+    first, second = dtype.type(start), dtype.type(start + step)
+    with np.errstate(all="ignore"):
+        delta = dtype.type(second - first)
+    return DeviceArray(backend, backend.fill_new(L.FILL_ARANGE, dtype, n, first.item(), delta.item(), second.item()), (n,), dtype)
+
+
+def device_linspace(backend, start: float, stop: float, num: int, endpoint: bool) -> DeviceArray:
+    """numpy.linspace (float64, scalars): y = arange(num) * step + start, y[-1] = stop when endpoint."""
+    div = (num - 1) if endpoint else num
+    delta = float(stop) - float(start)
+    step = delta / div
+    if step == 0 or num < OFFLOAD_MIN_ELEMS:
+        raise _Fallback("degenerate step")
+    ptr = backend.fill_new(L.FILL_LINSPACE, np.float64, num, float(start), step, float(stop) if endpoint else None)
+    return DeviceArray(backend, ptr, (num,), np.float64)
+
+
+def device_load(backend, path) -> DeviceArray:
+    """numpy.load of a plain .npy file: the header is parsed here, the data goes file -> pinned buffer -> HBM
+    inside the broker (the descriptor is passed, this process never reads the array)."""
+    import os
+
+    with open(path, "rb") as f:
+        version = np.lib.format.read_magic(f)
+        if version == (1, 0):
+            shape, fortran, dtype = np.lib.format.read_array_header_1_0(f)
+        elif version == (2, 0):
+            shape, fortran, dtype = np.lib.format.read_array_header_2_0(f)
+        else:
+            raise _Fallback("npy version")
+        offset = f.tell()
+        n = 1
+        for s in shape:
+            n *= int(s)
+        if fortran and len(shape) > 1 or dtype not in SUPPORTED or n < OFFLOAD_MIN_ELEMS:
+            raise _Fallback("layout")
+        if os.fstat(f.fileno()).st_size - offset < n * dtype.itemsize:
+            raise _Fallback("truncated file")
+        ptr = backend.upload_fd(f.fileno(), offset, n * dtype.itemsize)
+    return DeviceArray(backend, ptr, shape, dtype)

@@ -32,12 +32,21 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 PER_GPU_BATCH = 1024
+DRY = bool(os.environ.get("BCI_BENCH_DRY"))
 METRIC = "requests/sec on benchmark-numpy.py at batch=1024 per GPU"
 
 
 def env_int(name: str, default: int) -> int:
     v = os.environ.get(name)
     return int(v) if v not in (None, "") else default
+
+
+def measured_bf16() -> float:
+    p = ROOT / "MEASURED_PEAKS.json"
+    try:
+        return float(json.loads(p.read_text())["bf16_tflops"])
+    except Exception:
+        return 1590.0        # the profiling recipe's fallback (burst)
 
 
 def measured_peaks() -> tuple[float, str]:
@@ -101,56 +110,64 @@ class ClockSampler:
 
 # ---- the GPU arm ---------------------------------------------------------------------------
 def c1_step(dev, L, n: int, requests: int, wave: int, seed0: int, timing: dict | None):
-    """One step on this rank: `requests` benchmark-numpy bodies, `wave` at a time.
-    Per wave: alloc -> ONE rand launch -> ONE fused sum(square) launch -> 8 B/request D2H."""
-    import numpy as np
-
-    # Software-pipelined by one wave: the rand launch of wave i+1 is queued BEFORE the host blocks
-    # on wave i's results, so the frees / allocations / descriptor uploads between two waves
-    # (~1 ms of driver calls per 64 requests) happen while the GPU is busy.  Two waves are resident.
-    def launch_rand(w0):
+    """One step on this rank: `requests` benchmark-numpy bodies, `wave` per launch.
+    Per wave ONE kernel: rand(n) is generated in registers inside the fused sum(square(.)) reduction
+    (bci_reduce_rand_f64) — no array is allocated, nothing but 8 B/request of results touches HBM."""
+    results = []
+    for w0 in range(0, requests, wave):
         b = min(wave, requests - w0)
-        ptrs = [dev.alloc(n * 8) for _ in range(b)]
         if timing is not None:
             dev.event_record(0)
-        dev.rand_f64(ptrs, [n] * b, [seed0 + w0 + j for j in range(b)])
+        res = dev.reduce_rand_f64(L.RED_SUM, [n] * b, [seed0 + w0 + j for j in range(b)], pre=L.PRE_SQUARE)
         if timing is not None:
             dev.event_record(1)
-        return ptrs
-
-    results = []
-    starts = list(range(0, requests, wave))
-    cur = launch_rand(starts[0])
-    for k, w0 in enumerate(starts):
-        rand_ms = dev.event_elapsed(0, 1) if timing is not None and k == 0 else None
-        nxt = launch_rand(starts[k + 1]) if k + 1 < len(starts) else None
-        if timing is not None:
-            dev.event_record(2)
-        res = dev.reduce(L.RED_SUM, np.float64, cur, [n] * len(cur), pre=L.PRE_SQUARE)
-        if timing is not None:
-            dev.event_record(3)
-            # events 0/1 now bracket the NEXT wave's rand launch (read after the reduce has waited)
-            timing["sumsq_ms"].append(dev.event_elapsed(2, 3))
-            timing["wave_b"].append(len(cur))
-            if rand_ms is not None:
-                timing["rand_ms"].append(rand_ms)
-            if nxt is not None:
-                timing["rand_ms"].append(dev.event_elapsed(0, 1))
-        for p in cur:
-            dev.free(p)
+            timing["fused_ms"].append(dev.event_elapsed(0, 1))
+            timing["wave_b"].append(b)
         results.extend(res.tolist())
-        cur = nxt
     return results
+
+
+def c1_unfused_probe(dev, L, n: int, b: int, reps: int = 3) -> dict:
+    """The two HBM-bound kernels the fused launch replaced, timed alone on a wave of `b` requests (outside
+    the timed step): rand_f64_kernel writes 8n bytes per request, reduce_kernel<double,SUM,PRE_SQUARE> reads them."""
+    import numpy as np
+
+    ptrs = [dev.alloc(n * 8) for _ in range(b)]
+    out = {}
+    try:
+        rand_ms, red_ms = [], []
+        for r in range(reps + 1):
+            dev.event_record(4)
+            dev.rand_f64(ptrs, [n] * b, [1234 + r * b + j for j in range(b)])
+            dev.event_record(5)
+            dev.reduce(L.RED_SUM, np.float64, ptrs, [n] * b, pre=L.PRE_SQUARE)
+            dev.event_record(6)
+            if r:   # first round warms up
+                rand_ms.append(dev.event_elapsed(4, 5))
+                red_ms.append(dev.event_elapsed(5, 6))
+        by = 8.0 * n * b
+        out = {"rand_f64_kernel": {"avg_launch_ms": sum(rand_ms) / len(rand_ms), "achieved": by / (sum(rand_ms) / len(rand_ms) / 1e3) / 1e9},
+               "reduce_kernel<double,SUM,PRE_SQUARE>": {"avg_launch_ms": sum(red_ms) / len(red_ms),
+                                                        "achieved": by / (sum(red_ms) / len(red_ms) / 1e3) / 1e9}}
+    finally:
+        for p in ptrs:
+            dev.free(p)
+    return out
 
 
 def run_ours(args) -> dict | None:
     import numpy as np
     from bee_code_interpreter_b200 import _lib as L
-    from bee_code_interpreter_b200 import device as dev
     from bee_code_interpreter_b200 import workloads as W
+    if DRY:      # control-flow check on the CPU test double (tests/test_bench_contract.py): numbers are meaningless
+        sys.path.insert(0, str(ROOT / "tests"))
+        import fake_device as dev
+    else:
+        from bee_code_interpreter_b200 import device as dev
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     dist = None
+    torch = None
     if world > 1:
         import torch
         import torch.distributed as dist_mod
@@ -161,8 +178,7 @@ def run_ours(args) -> dict | None:
     dev.init(local)
     n = args.n
     requests = args.requests
-    free_b, _total = dev.mem_info()
-    wave = max(1, min(args.wave, int(free_b * 0.8) // (2 * n * 8), requests))   # two waves are resident
+    wave = max(1, min(args.wave, requests))
 
     def barrier():
         dev.sync()
@@ -175,7 +191,7 @@ def run_ours(args) -> dict | None:
     seed_base = 0x5EED0000 + rank * 10_000_019
     for s in range(args.warmup):
         c1_step(dev, L, n, requests, wave, seed_base + s * requests, None)
-    timing = {"rand_ms": [], "sumsq_ms": [], "wave_b": []}
+    timing = {"fused_ms": [], "wave_b": []}
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -207,8 +223,69 @@ def run_ours(args) -> dict | None:
         step_ms = float(t.item())
     value = requests * world / (step_ms / 1e3)
 
+    unfused, unfused_b = None, 0
+    if rank == 0:
+        try:
+            free_b, _t = dev.mem_info()
+            unfused_b = max(1, min(64, int(free_b * 0.5) // (n * 8)))
+            unfused = c1_unfused_probe(dev, L, n, unfused_b)
+        except Exception as e:  # a probe must never cost the bench line
+            print("bench.py: unfused probe failed: %r" % (e,), file=sys.stderr)
+    # strong scaling datum (north star: "batch 1024 on 8 x B200"): the SAME global batch of 1024 split over the ranks
+    strong = None
+    if world > 1:
+        share = max(1, PER_GPU_BATCH // world)
+        c1_step(dev, L, n, share, min(wave, share), seed_base + 7_000_000, None)
+        barrier()
+        dev.timer_begin()
+        for s_ in range(args.steps):
+            c1_step(dev, L, n, share, min(wave, share), seed_base + 8_000_000 + s_ * share, None)
+        s_ms = dev.timer_end() / args.steps
+        t = torch.tensor([s_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"global_batch": share * world, "per_gpu_batch": share, "ms_per_step": float(t.item()),
+                  "value": share * world / (float(t.item()) / 1e3), "unit": "requests/s", "scaling": "strong"}
+
+    # hardware evidence of the split-operand collectives: only when >= 2 GPUs are here
+    split_parity = None
+    if world > 1 and not args.no_split_check:
+        try:
+            from bee_code_interpreter_b200 import split_check
+
+            split_parity = split_check.run(dist, dev, rank, world)
+            if split_parity is not None:
+                split_parity["ok"] = all(v for k, v in split_parity.items() if k.endswith("_ok"))
+        except Exception as e:
+            split_parity = {"ok": False, "error": repr(e)}
+
+    # the other BASELINE configs, device resident (bench_configs.py)
+    import bench_configs as BC
+
+    which = [c for c in args.configs.split(",") if c in BC.DEVICE_ARMS]
+    peaks_all = {"hbm_gbs": measured_peaks()[0], "bf16_tflops": measured_bf16()}
+    cfg = BC.run_device_arms(dev, L, rank, world, dist, peaks_all, which, lambda m: print(m, file=sys.stderr)) if which else {}
+
     dev.shutdown()   # hand the GPU memory back before the service processes start
-    e2e = measure_e2e(args, dist, rank, world, local, n)
+    e2e = {"value": None, "unit": "requests/s", "error": "skipped (--e2e-requests 0)"}
+    if args.e2e_requests > 0:
+        harness = None
+        try:
+            harness = E2EHarness(args, world, local)
+            inflight = args.e2e_inflight if args.e2e_inflight > 0 else (16 if world <= 2 else 8)
+            e2e = harness.run("c1", args.e2e_requests, dist, rank, n, inflight)
+            e2e["parity_6sigma"] = e2e["parity"]
+            for name in which:
+                try:
+                    got = harness.run(name, BC.E2E_SAMPLE[name], dist, rank, n, BC_INFLIGHT[name] if world <= 2 else max(8, BC_INFLIGHT[name] // 2))
+                except Exception as e:
+                    got = {"value": None, "error": repr(e)}
+                if isinstance(cfg.get(name), dict):
+                    cfg[name]["e2e"] = got
+        except Exception as e:  # executor layer not usable: no end-to-end number
+            e2e = {"value": None, "unit": "requests/s", "error": repr(e)}
+        finally:
+            if harness is not None:
+                harness.close()
 
     if dist is not None:
         dist.barrier()
@@ -218,27 +295,34 @@ def run_ours(args) -> dict | None:
 
     peak, peak_kind = measured_peaks()
     tot_b = sum(timing["wave_b"])
-    rand_s = sum(timing["rand_ms"]) / 1e3
-    sumsq_s = sum(timing["sumsq_ms"]) / 1e3
-    k_rand = {"kernel": "rand_f64_kernel", "algorithmic_bytes_per_launch": 8 * n * wave,
-              "avg_launch_ms": 1e3 * rand_s / max(1, len(timing["rand_ms"])),
-              "achieved": 8 * n * tot_b / rand_s / 1e9 if rand_s else None}
-    k_sumsq = {"kernel": "reduce_kernel<double,SUM,PRE_SQUARE>", "algorithmic_bytes_per_launch": 8 * n * wave,
-               "avg_launch_ms": 1e3 * sumsq_s / max(1, len(timing["sumsq_ms"])),
-               "achieved": 8 * n * tot_b / sumsq_s / 1e9 if sumsq_s else None,
-               "note": "fused square+sum: the unfused numpy sequence moves 3x these bytes (24n)"}
-    dom = k_rand if rand_s >= sumsq_s else k_sumsq
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak,
-                "unit": "GB/s", "frac": (dom["achieved"] / peak) if dom["achieved"] else None,
-                # dram__bytes_read+write of one `ncu --set full` capture (profiles/r1a_ncu_full_c1.csv:
-                # 12.74 GB for a 12.8 GB launch of rand_f64_kernel, 12.81 GB for the reduce), scaled
-                # to this launch size: traffic == algorithmic bytes, nothing is re-read
-                "traffic": dom["algorithmic_bytes_per_launch"] * (0.9953 if dom is k_rand else 1.0004),
-                "traffic_source": "ncu capture of a 16-request launch, scaled to the %d-request launch" % wave,
-                "bound_note": "rand_f64_kernel is limited by the fmaheavy pipe (IMAD.WIDE of Philox4x32-10, "
-                              "82 % busy in ncu) before HBM; the fused reduce runs at 1.1x the measured copy peak",
-                "peak_kind": peak_kind, "kernels": [k_rand, k_sumsq],
-                "share_of_step": {"rand": rand_s / (dev_ms / 1e3), "sumsq": sumsq_s / (dev_ms / 1e3)}}
+    fused_s = sum(timing["fused_ms"]) / 1e3
+    sm_mhz = (clocks.get("sm_mhz") or 1965.0)
+    # instruction roofline of the fused kernel: Philox4x32-10 = 20 IMAD.WIDE per counter = 10 per float64;
+    # the fma pipe issues one warp instruction per SMSP every 2 cycles -> 148 SMs x 4 SMSPs x 16 lanes per clock
+    imad_rate = 10.0 * n * tot_b / fused_s if fused_s else None
+    imad_peak = 148 * 4 * 16 * sm_mhz * 1e6
+    algo = float(W.C1_ALGO_BYTES) * n / W.C1_N      # numpy's unfused traffic per request (32 n bytes)
+    k_fused = {"kernel": "reduce_rand_kernel<SUM,PRE_SQUARE>", "requests_per_launch": wave,
+               "algorithmic_bytes_per_launch": algo * wave, "moved_bytes_per_launch": 8 * wave,
+               "avg_launch_ms": 1e3 * fused_s / max(1, len(timing["fused_ms"])),
+               "achieved": algo * tot_b / fused_s / 1e9 if fused_s else None}
+    roofline = {"bound": "hbm", "kernel": k_fused["kernel"], "achieved": k_fused["achieved"], "peak": peak,
+                "unit": "GB/s", "frac": (k_fused["achieved"] / peak) if k_fused["achieved"] else None,
+                "traffic": None,
+                "traffic_note": "the kernel reads no array and writes 8 B per request + one partial per CTA: rand(n), its square "
+                                "and the sum live in registers.  `achieved` counts numpy's UNFUSED algorithmic bytes (32 n per "
+                                "request, SURVEY.md a9), which is why frac > 1; bytes actually moved are ~0",
+                "bound_note": "not HBM: the fma pipe (IMAD.WIDE of Philox4x32-10, 10 per float64) — see `issue`",
+                "issue": {"unit": "IMAD.WIDE lane-ops/s", "achieved": imad_rate, "peak": imad_peak,
+                          "frac": (imad_rate / imad_peak) if imad_rate else None,
+                          "peak_how": "148 SMs x 4 SMSPs x 16 lanes/clk (fma pipe, one warp instruction per 2 cycles) x median SM clock under load"},
+                "peak_kind": peak_kind, "kernels": [k_fused],
+                "share_of_step": {"fused": fused_s / (dev_ms / 1e3)}}
+    if unfused:
+        for name, k in unfused.items():
+            k.update({"kernel": name, "frac": k["achieved"] / peak, "algorithmic_bytes_per_launch": 8 * n * unfused_b,
+                      "note": "timed alone outside the step (the pair the fused launch replaced)"})
+            roofline["kernels"].append(k)
     out = {
         "metric": METRIC, "value": value, "unit": "requests/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -246,128 +330,200 @@ def run_ours(args) -> dict | None:
         "config": {"workload": "benchmark-numpy.py x %d requests/GPU (rand(%d) f64 -> square -> sum)" % (requests, n),
                    "global_batch": requests * world, "per_gpu_batch": requests, "array_elems": n,
                    "wave": wave, "parallelism": "requests round-robin, dp%d, no collective" % world,
-                   "cache": "inputs larger than L2 (each wave touches %.1f GB)" % (wave * n * 8 / 1e9),
-                   "fusion": "square+sum fused; rand materialised in HBM"},
+                   "cache": "no HBM inputs: the operand is generated in registers (compute-bound step); "
+                            "the HBM-bound kernels it replaced are timed on 51 GB waves (>> L2) in roofline.kernels",
+                   "fusion": "rand + square + sum in ONE kernel per wave (bci_reduce_rand_f64)"},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
         "wall_ms_per_step": 1e3 * wall_s / args.steps, "parity": {"statistical_6sigma": parity_ok},
     }
+    if strong is not None:
+        out["strong_scaling"] = strong
+    if split_parity is not None:
+        out["split_operand_parity"] = split_parity
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(n, budget_s=args.cpu_budget)
+    for name in which:
+        c = cfg.get(name)
+        if not isinstance(c, dict):
+            continue
+        c["workload"] = BC.DESCRIPTIONS[name]
+        c["n_gpus"] = world
+        if world == 1 and not args.no_cpu_baseline and "error" not in c:
+            try:
+                c["cpu_baseline"] = BC.cpu_baseline(name, budget_s=args.cfg_cpu_budget)
+            except Exception as e:
+                c["cpu_baseline"] = {"error": repr(e)}
+    if cfg:
+        out["configs"] = cfg
     return out
 
 
-def measure_e2e(args, dist, rank, world, local, n):
-    """The same requests through the public executor API — LocalGpuExecutor.execute(source_code,
-    files, env): source text in, stdout text out — from `--e2e-workers` service processes per
-    GPU (the way several uvicorn workers would front one GPU), all sharing this rank's broker
-    process.  Timed from the first worker's start to the last worker's end."""
-    if args.e2e_requests <= 0:
-        return {"value": None, "unit": "requests/s", "error": "skipped (--e2e-requests 0)"}
-    try:
+BC_INFLIGHT = {"c2": 16, "c3": 16, "c4": 48, "c5": 16}      # admitted requests per GPU in the e2e arm of each config
+MIN_JOBS = {"c1": 1, "c2": 6, "c3": 5, "c4": 1, "c5": 5}     # broker jobs one request of each workload must cause
+
+
+class E2EHarness:
+    """The public-API arm: `--e2e-workers` service processes per GPU (the way several uvicorn workers would front
+    one GPU), each with its own LocalGpuExecutor (zygotes, object store), all sharing this rank's broker process.
+    Workers are started once and then run one workload after the other on command."""
+
+    def __init__(self, args, world: int, local: int):
         from bee_code_interpreter_b200.broker import BrokerProcess
-        from bee_code_interpreter_b200 import workloads as W
-    except Exception as e:  # executor layer not importable: no end-to-end number
-        return {"value": None, "unit": "requests/s", "error": repr(e)}
-    # the host's fork/exit capacity (~4k processes/s on this 128-core box, tools/spawn_scale.py) is
-    # shared by all ranks: fewer service processes per GPU when several GPUs are driven at once
-    # (measured: 4 service processes in total give ~3.0-3.2 k req/s whether they feed 1 GPU or 2,
-    # 8 give ~9 k, 16 give ~8.3 k — so 8 in total up to 4 GPUs, 2 per GPU beyond)
-    workers = max(1, args.e2e_workers if args.e2e_workers > 0 else (4 if world <= 2 else 2))
-    per_worker = [args.e2e_requests // workers + (1 if i < args.e2e_requests % workers else 0) for i in range(workers)]
-    # forking processes box-wide: the kernel's fork path peaks at 16-32 of them and degrades beyond
-    # (profiles/r1_fork_scale.md), so the warm interpreters per service process shrink with world size
-    zygotes = args.e2e_zygotes if args.e2e_zygotes > 0 else max(1, min(4, 32 // (world * workers)))
-    # admission: the fork / set-up phase of a request stretches from ~3 ms to ~25 ms when 128 script
-    # processes are alive at once, so throughput FALLS with the number admitted (tools/e2e_trace.py,
-    # 4 service processes on one GPU: 16 in flight 3.42 k req/s, 32: 3.22 k, 64: 2.88 k, 128: 2.35 k);
-    # 16 per GPU keeps the GPU fed (two dispatch groups) without crowding the host
-    # and box-wide: 4 GPUs, 64 admitted in total 6.4 k req/s, 32 in total 7.4 k -> 8 per GPU beyond 2 GPUs
-    inflight = args.e2e_inflight if args.e2e_inflight > 0 else max(2, (16 if world <= 2 else 8) // workers)
-    broker = BrokerProcess(device=local)
-    procs = []
-    try:
-        for i in range(workers):
-            cmd = [sys.executable, str(ROOT / "bench.py"), "--e2e-worker", "--broker-socket", broker.socket_path,
-                   "--n", str(n), "--e2e-requests", str(per_worker[i]), "--e2e-inflight", str(inflight),
-                   "--e2e-zygotes", str(zygotes)]
-            procs.append(subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True))
-        for p in procs:
-            line = p.stdout.readline()
-            if line.strip() != "ready":
-                raise RuntimeError("e2e worker failed to start: %r" % line)
-        if dist is not None:
-            dist.barrier()
-        for p in procs:
-            p.stdin.write("go\n")
-            p.stdin.flush()
-        outs = [json.loads(p.stdout.readline()) for p in procs]
-        for p in procs:
-            p.wait(timeout=30)
+
+        self.args, self.world = args, world
+        # the host's fork/exit capacity (~4k processes/s on this 128-core box, tools/spawn_scale.py) is
+        # shared by all ranks: fewer service processes per GPU when several GPUs are driven at once
+        # (measured: 4 service processes in total give ~3.0-3.2 k req/s whether they feed 1 GPU or 2,
+        # 8 give ~9 k, 16 give ~8.3 k — so 8 in total up to 4 GPUs, 2 per GPU beyond)
+        self.workers = max(1, args.e2e_workers if args.e2e_workers > 0 else (4 if world <= 2 else 2))
+        # forking processes box-wide: the kernel's fork path peaks at 16-32 of them and degrades beyond
+        # (profiles/r1_fork_scale.md), so the warm interpreters per service process shrink with world size
+        zygotes = args.e2e_zygotes if args.e2e_zygotes > 0 else max(1, min(4, 32 // (world * self.workers)))
+        self.broker = (BrokerProcess(fake_device="fake_device", extra_pythonpath=str(ROOT / "tests")) if DRY
+                       else BrokerProcess(device=local))
+        self.procs = []
+        try:
+            for _ in range(self.workers):
+                cmd = [sys.executable, str(ROOT / "bench.py"), "--e2e-worker", "--broker-socket", self.broker.socket_path,
+                       "--e2e-zygotes", str(zygotes)]
+                self.procs.append(subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True))
+            for p in self.procs:
+                line = p.stdout.readline()
+                if line.strip() != "ready":
+                    raise RuntimeError("e2e worker failed to start: %r" % line)
+        except Exception:
+            self.close()
+            raise
+
+    def _stats(self) -> dict:
         from bee_code_interpreter_b200.broker_client import RemoteBackend
 
-        broker_stats = RemoteBackend(broker.socket_path).ping()["stats"]
-    finally:
-        for p in procs:
-            if p.poll() is None:
-                p.kill()
-        broker.close()
-    dt = max(o["t_end"] for o in outs) - min(o["t_start"] for o in outs)
-    if dist is not None:
-        import torch
+        be = RemoteBackend(self.broker.socket_path)
+        try:
+            return be.ping()["stats"]
+        finally:
+            be.close()
 
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    lat = sorted(x for o in outs for x in o["latencies"])
-    src_bytes = len(W.benchmark_numpy_source(n).encode())
-    return {"value": args.e2e_requests * world / dt, "unit": "requests/s", "requests_per_gpu": args.e2e_requests,
-            "service_workers_per_gpu": workers, "inflight_per_worker": inflight,
-            "h2d_bytes_per_step": src_bytes * args.e2e_requests, "d2h_bytes_per_step": 8 * args.e2e_requests,
-            "p50_latency_s": lat[len(lat) // 2] if lat else None,
-            "parity_6sigma": all(o["parity"] for o in outs),
-            # every request must have reached the GPU (rand + fused reduce = 2 broker jobs): a
-            # script that silently fell back to host numpy would make this number meaningless
-            "broker_jobs": broker_stats["jobs"], "broker_launch_groups": broker_stats["batches"],
-            "all_requests_on_gpu": broker_stats["jobs"] >= 2 * sum(o["requests"] for o in outs),
-            "api": "LocalGpuExecutor.execute(source_code, files, env)"}
+    def _command(self, cmds):
+        for p, c in zip(self.procs, cmds):
+            p.stdin.write(json.dumps(c) + "\n")
+            p.stdin.flush()
+        outs = []
+        for p in self.procs:
+            line = p.stdout.readline()
+            if not line:
+                raise RuntimeError("e2e worker died")
+            outs.append(json.loads(line))
+        return outs
+
+    def run(self, workload: str, requests_per_gpu: int, dist, rank: int, n: int, inflight_per_gpu: int, check: int = 2) -> dict:
+        """`requests_per_gpu` requests of `workload` through execute() on this rank's GPU; request ids follow the
+        round-robin placement (id = rank + world * k).  Timed from the first worker's start to the last one's end,
+        max over ranks."""
+        w, world = self.workers, self.world
+        counts = [requests_per_gpu // w + (1 if i < requests_per_gpu % w else 0) for i in range(w)]
+        inflight = max(1, inflight_per_gpu // w)
+        base = {"workload": workload, "n": n, "inflight": inflight, "stride": world * w}
+        warm = [dict(base, count=min(c, max(8, 2 * inflight)), first=rank + world * i + world * w * 100_000, check=0) for i, c in enumerate(counts)]
+        self._command(warm)                                       # untimed: page cache, pool growth, zygote warm-up
+        before = self._stats()
+        if dist is not None:
+            dist.barrier()
+        outs = self._command([dict(base, count=c, first=rank + world * i, check=check) for i, c in enumerate(counts)])
+        after = self._stats()
+        dt = max(o["t_end"] for o in outs) - min(o["t_start"] for o in outs)
+        if dist is not None:
+            import torch
+
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        lat = sorted(x for o in outs for x in o["latencies"])
+        jobs = after["jobs"] - before["jobs"]
+        done = sum(o["requests"] for o in outs)
+        return {"value": requests_per_gpu * world / dt, "unit": "requests/s", "requests_per_gpu": requests_per_gpu,
+                "service_workers_per_gpu": w, "inflight_per_worker": inflight,
+                "h2d_bytes_per_step": sum(o["h2d_bytes"] for o in outs), "d2h_bytes_per_step": sum(o["d2h_bytes"] for o in outs),
+                "p50_latency_s": lat[len(lat) // 2] if lat else None,
+                "parity": all(o["parity"] for o in outs), "parity_checked": sum(o["checked"] for o in outs),
+                # every request must have reached the GPU: a script that silently fell back to host numpy
+                # would make this number meaningless
+                "broker_jobs": jobs, "broker_launch_groups": after["batches"] - before["batches"],
+                "all_requests_on_gpu": jobs >= MIN_JOBS[workload] * done,
+                "api": "LocalGpuExecutor.execute(source_code, files, env)"}
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.write(json.dumps({"op": "quit"}) + "\n")
+                p.stdin.flush()
+            except Exception:
+                pass
+        for p in self.procs:
+            try:
+                p.wait(timeout=10)
+            except Exception:
+                p.kill()
+        self.broker.close()
 
 
 def e2e_worker(args):
-    """One service process: its own executor (zygotes, object store) on the shared broker."""
+    """One service process: its own executor (zygotes, object store) on the shared broker; runs workloads on command."""
     import types
 
     import numpy as np
     from bee_code_interpreter_b200.executor import LocalGpuExecutor
     from bee_code_interpreter_b200 import workloads as W
+    import bench_configs as BC
 
-    n, requests = args.n, args.e2e_requests
-    src = W.benchmark_numpy_source(n)
     shared = types.SimpleNamespace(socket_path=args.broker_socket, close=lambda: None)
-    execu = LocalGpuExecutor(broker=shared, max_inflight=args.e2e_inflight, timeout=300, zygotes=args.e2e_zygotes or None)
-    lat = []
-
-    async def one():
-        t = time.perf_counter()
-        r = await execu.execute(src)
-        lat.append(time.perf_counter() - t)
-        return r
-
-    async def batch(k):
-        return await asyncio.gather(*(one() for _ in range(k)))
-
-    asyncio.run(batch(min(requests, max(64, 2 * args.e2e_inflight))))  # warm-up: zygotes, pool growth, page cache
-    lat.clear()
+    execu = LocalGpuExecutor(broker=shared, max_inflight=64, timeout=600, zygotes=args.e2e_zygotes or None,
+                             min_rand_elems=1000 if DRY else None)
     print("ready", flush=True)
-    sys.stdin.readline()
-    t0 = time.time()
-    res = asyncio.run(batch(requests))
-    t1 = time.time()
-    ok = all(r.exit_code == 0 and r.stdout.startswith("Result:") for r in res)
-    vals = np.array([float(r.stdout.split()[1]) for r in res]) / n if ok else np.array([])
-    sigma = np.sqrt(4.0 / 45.0 / n)
-    parity = bool(ok and np.all(np.abs(vals - 1.0 / 3.0) < 6 * sigma))
+    while True:
+        line = sys.stdin.readline()
+        if not line:
+            break
+        cmd = json.loads(line)
+        if cmd.get("op") == "quit":
+            break
+        name, n, count = cmd["workload"], cmd["n"], cmd["count"]
+        ids = [cmd["first"] + j * cmd["stride"] for j in range(count)]
+        srcs = [W.benchmark_numpy_source(n)] * count if name == "c1" else [BC.source_for(name, i) for i in ids]
+        lat: list[float] = []
+
+        async def batch():
+            sem = asyncio.Semaphore(cmd["inflight"])
+
+            async def one(src):
+                async with sem:
+                    t = time.perf_counter()
+                    r = await execu.execute(src)
+                    lat.append(time.perf_counter() - t)
+                    return r
+            return await asyncio.gather(*(one(s) for s in srcs))
+
+        t0 = time.time()
+        res = asyncio.run(batch())
+        t1 = time.time()
+        ok = all(r.exit_code == 0 for r in res)
+        checked = 0
+        if name == "c1":
+            good = ok and all(r.stdout.startswith("Result:") for r in res)
+            vals = np.array([float(r.stdout.split()[1]) for r in res]) / n if good else np.array([])
+            parity = bool(good and np.all(np.abs(vals - 1.0 / 3.0) < 6 * np.sqrt(4.0 / 45.0 / n)))
+            checked = len(res)
+        else:
+            parity = ok
+            for i, r in list(zip(ids, res))[: cmd.get("check", 0)]:
+                parity = parity and BC.check_result(name, i, r)
+                checked += 1
+        h2d = sum(len(s.encode()) for s in srcs) + (BC.C4_BYTES * count if name == "c4" else 0)
+        d2h = sum(len(r.stdout.encode()) for r in res) if name != "c1" else 8 * count
+        print(json.dumps({"t_start": t0, "t_end": t1, "requests": count, "parity": parity, "checked": checked, "latencies": lat,
+                          "h2d_bytes": h2d, "d2h_bytes": d2h,
+                          "first_error": next((r.stderr[-300:] for r in res if r.exit_code != 0), None)}), flush=True)
     execu.close()
-    print(json.dumps({"t_start": t0, "t_end": t1, "requests": requests, "parity": parity, "latencies": lat}), flush=True)
 
 
 # ---- the reference's CPU path ----------------------------------------------------------------
@@ -471,7 +627,7 @@ def main():
                     help="array elements per request (benchmark-numpy.py: 1e8); use the long form under torchrun, "
                          "whose own parser treats --n as an abbreviation")
     ap.add_argument("--requests", type=int, default=PER_GPU_BATCH, help="requests per GPU per step")
-    ap.add_argument("--wave", type=int, default=64, help="requests resident on the GPU at once")
+    ap.add_argument("--wave", type=int, default=256, help="requests per launch")
     ap.add_argument("--e2e-requests", type=int, default=-1,
                     help="requests per GPU in the e2e arm (-1 = min(steps, 4) batches of 1024: a single batch lasts ~0.3 s, "
                          "which is mostly ramp-up and tail)")
@@ -482,6 +638,9 @@ def main():
     ap.add_argument("--e2e-worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--broker-socket", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="c2,c3,c4,c5", help="other BASELINE configs to measure beside the headline ('' = none)")
+    ap.add_argument("--cfg-cpu-budget", type=float, default=10.0, help="seconds of CPU baseline per config")
+    ap.add_argument("--no-split-check", action="store_true", help="skip the split-operand NCCL self-check at N >= 2")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0)
     args = ap.parse_args()

@@ -49,7 +49,7 @@ int bci_broker_stats(uint64_t stats[4]);
 #define BRK_MATMUL 11       /* p0 = A, p1 = B, i0,i1,i2 = M,N,K   -> value = new buffer */
 #define BRK_COPY 12         /* p0, n = bytes                      -> value = new buffer */
 #define BRK_UPLOAD 13       /* n = bytes; payload = data | descriptor (flag FD), i0 = file offset -> value = new buffer */
-#define BRK_DOWNLOAD 14     /* p0, n = bytes; descriptor (flag FD), i0 = file offset, or none -> payload = data */
+#define BRK_DOWNLOAD 14     /* p0, i1 = byte offset into the buffer, n = bytes; descriptor (flag FD), i0 = file offset, or none -> payload = data */
 #define BRK_SHA256_DEV 15   /* p0, n = bytes                      -> payload = 32-byte digest */
 #define BRK_SHA256_FD 16    /* descriptor (flag FD) of a regular file -> payload = digest of its bytes */
 #define BRK_SHA256_BYTES 17 /* payload = data                     -> payload = digest */

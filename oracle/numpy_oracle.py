@@ -125,3 +125,58 @@ def sha256_c(data: bytes) -> bytes:
 
 def sha256_hashlib(data: bytes) -> bytes:
     return hashlib.sha256(data).digest()
+
+
+# ---- K8d numpy.random.Generator(PCG64): restatement of numpy/random/src/pcg64/pcg64.h, pinned in
+# tests/test_oracle.py against numpy's own `random_raw` and `advance` (the reference's arithmetic
+# for the inputs of BASELINE configs C2/C3/C5 is `numpy.random.default_rng(seed)`).
+PCG_MULT = (2549297995355413924 << 64) | 4865540595714422341
+_M128, _M64 = (1 << 128) - 1, (1 << 64) - 1
+
+
+def pcg64_output(state: int) -> int:
+    """pcg_output_xsl_rr_128_64: rotr64(hi ^ lo, state >> 122)."""
+    x, rot = ((state >> 64) ^ state) & _M64, state >> 122
+    return ((x >> rot) | (x << ((64 - rot) & 63))) & _M64
+
+
+def pcg64_raw(state: int, inc: int, n: int) -> list[int]:
+    """n successive next64 outputs: step, then output of the NEW state."""
+    out = []
+    for _ in range(n):
+        state = (state * PCG_MULT + inc) & _M128
+        out.append(pcg64_output(state))
+    return out
+
+
+def pcg64_jump(k: int) -> tuple[int, int]:
+    """(P, G) with s_{i+k} = P*s_i + inc*G: P = A^k, G = 1 + A + ... + A^(k-1) — the affine jump the device
+    kernel's tables hold (csrc/bci_rand_pcg.cu jump_of)."""
+    P, G, bp, bg = 1, 0, PCG_MULT, 1
+    while k:
+        if k & 1:
+            G = (bp * G + bg) & _M128
+            P = (bp * P) & _M128
+        bg = (bp * bg + bg) & _M128
+        bp = (bp * bp) & _M128
+        k >>= 1
+    return P, G
+
+
+def pcg64_random(state: int, inc: int, n: int, kind: str, low: int = 0, span: int = 0) -> np.ndarray:
+    """What numpy's Generator returns for n draws from (state, inc), per kind of the device kernel:
+    'f64' (next64 >> 11) * 2^-53; 'f32' (next32 >> 8) * 2^-24; 'u32' the next32 stream;
+    'bounded' low + ((next32 * span) >> 32) WITHOUT rejection (distributions.c buffered_bounded_lemire_uint32)."""
+    draws = n if kind == "f64" else (n + 1) // 2
+    raw = np.array(pcg64_raw(state, inc, draws), dtype=np.uint64)
+    if kind == "f64":
+        return (raw >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    words = np.empty(2 * draws, dtype=np.uint32)
+    words[0::2] = (raw & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    words[1::2] = (raw >> np.uint64(32)).astype(np.uint32)
+    words = words[:n]
+    if kind == "f32":
+        return (words >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    if kind == "u32":
+        return words
+    return (low + ((words.astype(np.uint64) * np.uint64(span)) >> np.uint64(32)).astype(np.int64))

@@ -68,6 +68,42 @@ def launch_count():
     return len(calls)
 
 
+# timing / lifecycle entry points bench.py uses (wall clock here)
+BciError, Unsupported = L.BciError, L.Unsupported
+_events: dict[int, float] = {}
+_t0 = [0.0]
+
+
+def event_record(slot):
+    import time
+
+    _events[slot] = time.perf_counter()
+
+
+def event_elapsed(a, b):
+    return max(1e-6, (_events[b] - _events[a]) * 1e3)
+
+
+def timer_begin():
+    import time
+
+    _t0[0] = time.perf_counter()
+
+
+def timer_end():
+    import time
+
+    return max(1e-6, (time.perf_counter() - _t0[0]) * 1e3)
+
+
+def flush_l2():
+    pass
+
+
+def shutdown():
+    _initialised[0] = False
+
+
 def alloc(nbytes):
     with _lock:
         p = _next[0]
@@ -123,8 +159,8 @@ def upload(arr):
     return p
 
 
-def download(ptr, n, dtype):
-    return _view(ptr, n, dtype).copy()
+def download(ptr, n, dtype, offset=0):
+    return _view(ptr, int(offset) + int(n), dtype)[int(offset):].copy()
 
 
 def ewise(op, dtype, in0, in1, scalars, out, ns):

@@ -40,3 +40,30 @@ def test_reference_arm_under_torchrun_only_rank0_prints(built):
                         "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     _check(r.stdout, 2)
+
+
+def test_our_arm_control_flow_on_the_cpu_test_double(built):
+    """bench.py's own arm with tests/fake_device.py standing in for the GPU binding (BCI_BENCH_DRY: tiny sizes,
+    numbers meaningless): one JSON line with the headline keys, `roofline`, `cpu_baseline`, `e2e` through execute(),
+    and the `configs` block — C2..C5 each with value, roofline, parity, e2e and cpu_baseline."""
+    import os
+
+    env = dict(os.environ, BCI_BENCH_DRY="1")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--warmup", "1", "--n", "20000", "--requests", "8",
+                        "--wave", "4", "--e2e-requests", "8", "--cpu-budget", "1", "--cfg-cpu-budget", "1"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert (KEYS - {"impl"}) | {"roofline", "clocks", "configs"} <= set(d)
+    assert d["value"] > 0 and d["gpu_launches"] >= 1 and d["e2e"]["value"] > 0 and d["e2e"]["all_requests_on_gpu"] and d["e2e"]["parity"]
+    assert d["roofline"]["kernel"].startswith("reduce_rand_kernel") and {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert set(d["configs"]) == {"c2", "c3", "c4", "c5"}
+    for name, c in d["configs"].items():
+        assert "error" not in c, (name, c)
+        assert c["value"] > 0 and c["parity"]["ok"], (name, c["parity"])
+        assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(c["roofline"])
+        assert c["e2e"]["value"] > 0 and c["e2e"]["parity"], (name, c["e2e"])
+        assert c["cpu_baseline"]["value"] > 0 and c["cpu_baseline"]["kind"] == "port"

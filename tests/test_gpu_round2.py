@@ -1,0 +1,160 @@
+"""Round-2 kernels through the C ABI against numpy (the reference's arithmetic): PCG64 Generator
+streams, reductions over a generated operand, creation / cast kernels, the pinned descriptor
+transfer path and device-side hashing of exported arrays."""
+import hashlib
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from bee_code_interpreter_b200 import _lib as L
+from oracle import numpy_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [0, 1, 7, 16, 16383, 16384, 16385, 32769, 1_000_003, (1 << 22) + 5]
+
+
+def _gen(seed):
+    st = np.random.PCG64(seed).state["state"]
+    return st["state"], st["inc"]
+
+
+def _ref(seed):
+    return np.random.default_rng(seed)
+
+
+@pytest.mark.parametrize("kind,dtype,draw", [
+    (L.PCG_F64, np.float64, lambda g, n: g.random(n)),
+    (L.PCG_F32, np.float32, lambda g, n: g.random(n, dtype=np.float32)),
+    (L.PCG_U32, np.uint32, lambda g, n: g.integers(0, 1 << 32, n, dtype=np.uint32)),
+])
+def test_pcg64_streams_are_numpys(dev, kind, dtype, draw):
+    """One ragged batch per kind: every request's output is bit for bit what numpy's Generator returns."""
+    seeds = [1000 + i for i in range(len(SIZES))]
+    ptrs = [dev.alloc(max(n, 1) * np.dtype(dtype).itemsize) for n in SIZES]
+    rej = dev.rand_pcg64(kind, ptrs, SIZES, [_gen(s) for s in seeds])
+    assert not rej.any()
+    for p, n, s in zip(ptrs, SIZES, seeds):
+        got = dev.download(p, n, dtype)
+        assert np.array_equal(got, draw(_ref(s), n)), (kind, n)
+        dev.free(p)
+
+
+@pytest.mark.parametrize("out_kind,dt", [(L.PCG_BOUNDED32_I64, np.int64), (L.PCG_BOUNDED32_I32, np.int32)])
+def test_pcg64_bounded_integers(dev, out_kind, dt):
+    """Lemire 32-bit path: exact for every range when no draw is rejected; rejections are COUNTED (the
+    caller then falls back to numpy) and the count matches how far numpy's generator really went."""
+    cases = [(0, 2**31, 10**6 + 1), (5, 2**20, 70001), (-7, 3, 16385), (0, 100, 2 * 10**6), (0, 2**31 + 12345, 5 * 10**5),
+             (10, 2**32 - 1, 33333)]
+    if dt == np.int32:
+        cases = [(lo, min(span, 2**31 - 1 - lo), n) for lo, span, n in cases]
+    for i, (low, span, n) in enumerate(cases):
+        seed = 5000 + i
+        p = dev.alloc(n * np.dtype(dt).itemsize)
+        state, inc = _gen(seed)
+        rej = int(dev.rand_pcg64(out_kind, [p], [n], [(state, inc, low, span)])[0])
+        got = dev.download(p, n, dt)
+        dev.free(p)
+        want = _ref(seed).integers(low, low + span, n, dtype=dt)
+        # numpy's stream equals the unrejected one up to its first rejection, which lies among the first n
+        # words: the kernel's count is zero exactly when the two outputs agree everywhere
+        assert (rej == 0) == np.array_equal(got, want), (low, span, rej)
+        assert got.min() >= low and got.max() < low + span
+        assert np.array_equal(got, O.pcg64_random(state, inc, n, "bounded", low, span).astype(dt))   # the unrejected stream itself
+
+
+def test_reduction_over_generated_operand_is_bit_identical(dev):
+    """bci_reduce_rand_f64 == bci_rand_f64 + bci_reduce for every op / pre-transform and ragged sizes."""
+    ns = [1, 5, 16383, 16384, 16385, 100_003, 3_000_017]
+    seeds = [77 + i for i in range(len(ns))]
+    ptrs = [dev.alloc(n * 8) for n in ns]
+    dev.rand_f64(ptrs, ns, seeds)
+    for op in (L.RED_SUM, L.RED_MEAN, L.RED_MAX, L.RED_MIN):
+        for pre in (L.PRE_NONE, L.PRE_SQUARE, L.PRE_ABS):
+            two = dev.reduce(op, np.float64, ptrs, ns, pre=pre)
+            one = dev.reduce_rand_f64(op, ns, seeds, pre=pre)
+            assert np.array_equal(two, one), (op, pre)
+    x = dev.download(ptrs[-1], ns[-1], np.float64)
+    assert abs(dev.reduce_rand_f64(L.RED_SUM, [ns[-1]], [seeds[-1]], pre=L.PRE_SQUARE)[0] - np.sum(np.square(x))) <= 1e-12 * np.sum(np.square(x))
+    for p in ptrs:
+        dev.free(p)
+
+
+def test_creation_kernels_match_numpy(dev):
+    for dt in (np.float32, np.float64, np.int32, np.int64):
+        for n in (0, 1, 4095, 4096, 4097, 100_003):
+            p = dev.alloc(max(n, 1) * np.dtype(dt).itemsize)
+            dev.fill(L.FILL_CONST, dt, [p], [n], [3])
+            assert np.array_equal(dev.download(p, n, dt), np.full(n, 3, dtype=dt))
+            dev.free(p)
+    for args, dt in [((0, 300_001, 1), np.int64), ((5, 900_000, 3), np.int32), ((0.5, 30000.25, 0.37), np.float64),
+                     ((0, 200_001, 1), np.float32), ((1.5, 70000.0, 0.1), np.float32), ((10.0, -50000.0, -0.7), np.float64),
+                     ((0, 2**25 + 7, 1), np.float32)]:
+        want = np.arange(*args, dtype=dt)
+        n = len(want)
+        first, second = np.dtype(dt).type(args[0]), np.dtype(dt).type(args[0] + args[2])
+        delta = np.dtype(dt).type(second - first)
+        p = dev.alloc(n * np.dtype(dt).itemsize)
+        dev.fill(L.FILL_ARANGE, dt, [p], [n], [first.item()], [delta.item()], [second.item()])
+        assert np.array_equal(dev.download(p, n, dt), want), (args, dt)
+        dev.free(p)
+    for start, stop, num, endpoint in [(0.0, 1.0, 100_001, True), (-3.3, 17.1, 65537, False), (1e-3, 1e9, 4099, True)]:
+        want = np.linspace(start, stop, num, endpoint=endpoint)
+        step = (stop - start) / ((num - 1) if endpoint else num)
+        p = dev.alloc(num * 8)
+        dev.fill(L.FILL_LINSPACE, np.float64, [p], [num], [start], [step], [stop] if endpoint else None)
+        assert np.array_equal(dev.download(p, num, np.float64), want), (start, stop, num)
+        dev.free(p)
+
+
+def test_casts_match_numpy_astype(dev):
+    rng = np.random.default_rng(3)
+    src = {np.float32: rng.standard_normal(100_003).astype(np.float32) * 1e3,
+           np.float64: rng.standard_normal(100_003) * 1e10,
+           np.int32: rng.integers(-2**31, 2**31, 100_003, dtype=np.int32),
+           np.int64: rng.integers(-2**62, 2**62, 100_003, dtype=np.int64)}
+    pairs = [(np.float32, np.float64), (np.float64, np.float32), (np.int32, np.int64), (np.int64, np.int32),
+             (np.int32, np.float32), (np.int32, np.float64), (np.int64, np.float32), (np.int64, np.float64)]
+    for s, d in pairs:
+        for n in (0, 5, 4096, 100_003):
+            x = src[s][:n]
+            p = dev.upload(x) if n else dev.alloc(1)
+            q = dev.alloc(max(n, 1) * np.dtype(d).itemsize)
+            dev.cast(s, d, [p], [q], [n])
+            with np.errstate(all="ignore"):
+                assert np.array_equal(dev.download(q, n, d), x.astype(d)), (s, d, n)
+            dev.free(p)
+            dev.free(q)
+    with pytest.raises(dev.Unsupported):
+        dev.cast(np.float64, np.int64, [dev.alloc(8)], [dev.alloc(8)], [1])
+
+
+def test_descriptor_transfers_round_trip(dev, tmp_path):
+    """bci_h2d_fd / bci_d2h_fd: sizes around the 8 MiB bounce chunk, non-zero file offsets, short files."""
+    rng = np.random.default_rng(11)
+    for nbytes, off in [(1, 0), (4097, 3), ((8 << 20) - 1, 0), (8 << 20, 128), ((8 << 20) + 1, 0), ((40 << 20) + 12345, 77)]:
+        data = rng.integers(0, 256, nbytes, dtype=np.uint8)
+        src = tmp_path / "in.bin"
+        with open(src, "wb") as f:
+            f.write(b"\xee" * off)
+            f.write(data.tobytes())
+        p = dev.alloc(nbytes)
+        fd = os.open(src, os.O_RDONLY)
+        dev.h2d_fd(p, fd, off, nbytes)
+        os.close(fd)
+        assert np.array_equal(dev.download(p, nbytes, np.uint8), data)
+        assert dev.sha256_device([p], [nbytes])[0] == hashlib.sha256(data.tobytes()).digest()
+        dst = tmp_path / "out.bin"
+        fd = os.open(dst, os.O_RDWR | os.O_CREAT | os.O_TRUNC)
+        dev.d2h_fd(fd, off, p, nbytes)
+        os.close(fd)
+        assert dst.read_bytes()[off:] == data.tobytes()
+        dev.free(p)
+    p = dev.alloc(1 << 20)
+    fd = os.open(tmp_path / "in.bin", os.O_RDONLY)
+    with pytest.raises(dev.BciError):
+        dev.h2d_fd(p, fd, 0, 1 << 30)      # the file ends first: an error, not a fault
+    os.close(fd)
+    dev.free(p)

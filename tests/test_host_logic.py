@@ -36,10 +36,12 @@ def names(calls):
 def test_benchmark_numpy_expression_is_two_launches(be):
     x = P.device_rand(be, (100_000,), seed=7)
     r = np.sum(np.square(x))                       # examples/benchmark-numpy.py:21
-    assert names(fake_device.calls) == ["rand", "reduce"]      # square never materialised
-    assert fake_device.calls[1][2] == (L.RED_SUM, L.PRE_SQUARE)
-    assert r == np.sum(np.square(np.asarray(x)))
-    assert isinstance(r, np.float64)
+    # ONE launch: the generator runs inside the reduction, neither rand(n) nor its square reaches memory
+    assert names(fake_device.calls) == ["reduce_rand"] and x._ptr is None
+    assert fake_device.calls[0][2] == (L.RED_SUM, L.PRE_SQUARE)
+    assert r == np.sum(np.square(np.asarray(x)))   # reading x materialises the SAME stream (same seed)
+    assert names(fake_device.calls)[1] == "rand" and isinstance(r, np.float64)
+    assert float(x.max()) == np.asarray(x).max() and names(fake_device.calls)[-1] == "reduce"   # materialised now: plain reduce
 
 
 def test_c3_request_mix_fuses_into_three_launches(be):
@@ -202,7 +204,7 @@ def test_broker_batches_concurrent_clients_and_scopes_buffers(built):
 
         for i in range(n_clients):
             assert np.isclose(results[i], np.sum(np.square(O.rand_f64(2000 + i, 100 + i))), rtol=1e-12)
-        red = [c for c in fake_device.calls if c[0] == "reduce"]
+        red = [c for c in fake_device.calls if c[0] == "reduce_rand"]
         assert sum(c[1] for c in red) == n_clients and max(c[1] for c in red) >= 2   # packed into shared launches
         # ownership: a client cannot name another client's buffer
         a, b = RemoteBackend(broker.socket_path), RemoteBackend(broker.socket_path)
@@ -212,10 +214,34 @@ def test_broker_batches_concurrent_clients_and_scopes_buffers(built):
         with pytest.raises(L.BciError):
             a.reduce(L.RED_SUM, np.float64, [pa], [101])                              # past the end of its own buffer
         assert np.isclose(a.reduce(L.RED_SUM, np.float64, [pa], [100])[0], O.rand_f64(100, 1).sum())
-        # big arrays cross through /dev/shm files, small ones inline
+        # big arrays cross behind a passed descriptor (SCM_RIGHTS), small ones inline
         big = np.random.default_rng(1).random(50_000)
         pb = a.upload(big)
         assert np.array_equal(a.download(pb, big.size, big.dtype), big)
+        # Generator(PCG64) draws, creation, casts over the wire
+        st64 = np.random.PCG64(9).state["state"]
+        pg, rej = a.rand_pcg(L.PCG_F32, 3001, st64["state"], st64["inc"])
+        assert rej == 0 and np.array_equal(a.download(pg, 3001, np.float32), np.random.default_rng(9).random(3001, dtype=np.float32))
+        pi, rej = a.rand_pcg(L.PCG_BOUNDED32_I64, 500, st64["state"], st64["inc"], -5, 2**31)
+        assert rej == 0 and np.array_equal(a.download(pi, 500, np.int64), np.random.default_rng(9).integers(-5, 2**31 - 5, 500))
+        pf = a.fill_new(L.FILL_ARANGE, np.float64, 1000, 0.5, 0.25, 0.75)
+        assert np.array_equal(a.download(pf, 1000, np.float64), np.arange(0.5, 250.5, 0.25))
+        pc = a.cast_new(np.float64, np.float32, pf, 1000)
+        assert np.array_equal(a.download(pc, 1000, np.float32), np.arange(0.5, 250.5, 0.25).astype(np.float32))
+        with pytest.raises(L.BciError):
+            b.cast_new(np.float64, np.float32, pf, 1000)                               # not b's buffer
+        # export: array -> file behind a header, digest of the file computed on the "device"
+        import os, tempfile
+        fd, path = tempfile.mkstemp()
+        digest = a.export(pf, 8000, fd, b"HEADER")
+        os.close(fd)
+        blob = open(path, "rb").read()
+        os.unlink(path)
+        assert blob == b"HEADER" + np.arange(0.5, 250.5, 0.25).tobytes() and digest == hashlib.sha256(blob).digest()
+        fd, path = tempfile.mkstemp()
+        os.write(fd, b"x" * 100_000)
+        assert a.sha256_fd(fd) == hashlib.sha256(b"x" * 100_000).digest()
+        os.close(fd); os.unlink(path)
         # seeded legacy generator over the wire: state in, same stream + advanced state out
         rs = np.random.RandomState(1234)
         rs.random_sample(5)                                                           # odd position in the block
@@ -293,8 +319,8 @@ def test_executor_runs_the_metric_script_on_the_device_backend(executor):
         assert lines[0].startswith("Result: ") and lines[1].startswith("Execution Time: ")
         assert abs(float(lines[0].split()[1]) / n - 1 / 3) < 6 * np.sqrt(4 / 45 / n)
     kinds = names(fake_device.calls)
-    assert kinds.count("ewise") == 0 and "rand" in kinds and "reduce" in kinds           # fused, on the "device"
-    assert sum(c[1] for c in fake_device.calls if c[0] == "rand") == 12
+    assert set(kinds) == {"reduce_rand"}                      # one fused launch class on the "device", nothing else
+    assert sum(c[1] for c in fake_device.calls if c[0] == "reduce_rand") == 12
 
 
 async def _many(ex, src, k):
@@ -473,3 +499,57 @@ def test_writes_through_an_exposed_host_copy_reach_later_device_ops(be):
     x = mk(); assert x[3] == 3.0 and x[[1, 2]].tolist() == [1.0, 2.0] and x._ptr is not None    # copies keep the device buffer
     x = mk(); np.cumsum(np.arange(8.0), out=x); assert x.sum() == float(np.cumsum(np.arange(8.0)).sum())
     x = mk(); y = np.square(x); x[0] = 7.0; assert np.asarray(y)[0] == 0.0                       # deferred reader saw the old value
+
+
+# ---- round 2: Generator / creation / load / save through the hook, whole request path on the fake device ---------
+CONFIG_SCRIPT = '''
+import numpy as np
+rng = np.random.default_rng(2005)
+x = rng.random(2**20, dtype=np.float32)
+y = rng.random(2**20, dtype=np.float32)
+print(type(x).__name__, repr(float(np.sum(np.square(x)))), repr(float(np.mean(x * y + 1.0))), repr(float(np.max(np.abs(x - y)))))
+k = np.random.default_rng(5001).integers(0, 2**31, 300_001, dtype=np.int64)
+c = np.cumsum(k)
+print(type(k).__name__, int(np.argmax(k)), int(c[-1]), repr(float(rng.random())), repr(rng.standard_normal(2).tolist()))
+z = np.load("in.npy")
+t = np.arange(z.size, dtype=np.float64)
+print(type(z).__name__, type(t).__name__, repr(float(np.dot(z, t))), repr(float(np.linspace(0.0, 1.0, 400_001).sum())))
+np.save("out.npy", z * 2.0)
+(z + 1.0).tofile("raw.bin")
+'''
+
+
+def test_generator_creation_load_save_through_the_executor(executor):
+    """A C3/C5-shaped request end to end on the fake device: default_rng draws, creation functions and np.load
+    produce device arrays (descriptor passing included), np.save / tofile export them, results equal numpy's."""
+    import io
+
+    zin = np.random.default_rng(3).random(300_000)
+    buf = io.BytesIO()
+    np.save(buf, zin)
+
+    async def go():
+        h = await executor.file_storage.write(buf.getvalue())
+        return await executor.execute(CONFIG_SCRIPT, files={"/workspace/in.npy": h}, env={"BCI_DEBUG_FALLBACK": "1"})
+
+    fake_device.calls.clear()
+    r = asyncio.run(go())
+    assert r.exit_code == 0 and r.stderr == "", r.stderr
+    rng = np.random.default_rng(2005)
+    x, y = rng.random(2**20, dtype=np.float32), rng.random(2**20, dtype=np.float32)
+    k = np.random.default_rng(5001).integers(0, 2**31, 300_001, dtype=np.int64)
+    lines = r.stdout.splitlines()
+    assert lines[0] == f"DeviceArray {float(np.sum(np.square(x)))!r} {float(np.mean(x * y + 1.0))!r} {float(np.max(np.abs(x - y)))!r}"
+    assert lines[1] == f"DeviceArray {int(np.argmax(k))} {int(np.cumsum(k)[-1])} {float(rng.random())!r} {rng.standard_normal(2).tolist()!r}"
+    t = np.arange(zin.size, dtype=np.float64)
+    assert lines[2] == f"DeviceArray DeviceArray {float(np.dot(zin, t))!r} {float(np.linspace(0.0, 1.0, 400_001).sum())!r}"
+    assert set(r.files) == {"/workspace/out.npy", "/workspace/raw.bin"}
+
+    async def blobs():
+        return [await executor.file_storage.read(r.files[f"/workspace/{n}"]) for n in ("out.npy", "raw.bin")]
+
+    out_npy, raw = asyncio.run(blobs())
+    assert np.array_equal(np.load(io.BytesIO(out_npy)), zin * 2.0) and raw == (zin + 1.0).tobytes()
+    assert r.files["/workspace/out.npy"] == hashlib.sha256(out_npy).hexdigest()
+    kinds = names(fake_device.calls)
+    assert kinds.count("rand_pcg") == 3 and "fill" in kinds and "reduce_fused" in kinds and "cumsum" in kinds

@@ -115,3 +115,23 @@ def test_cpu_executor_reproduces_reference_app_fixtures(built, tmp_path):
     assert (r.stdout, r.stderr, r.exit_code) == ("", "Execution timed out", -1)
     with pytest.raises(FileNotFoundError):
         _replay(ex, cases["unknown_object"])
+
+
+def test_pcg64_restatement_is_numpys_generator():
+    """oracle.pcg64_* against numpy itself: raw stream, the three draw kinds, and the affine jump
+    (P_k, G_k) against PCG64.advance — the arithmetic csrc/bci_rand_pcg.cu is built on."""
+    for seed in (0, 7, 1000, 2**63 + 5):
+        bg = np.random.PCG64(seed)
+        st = bg.state["state"]
+        state, inc = st["state"], st["inc"]
+        assert O.pcg64_raw(state, inc, 64) == [int(v) for v in np.random.PCG64(seed).random_raw(64)]
+        assert np.array_equal(O.pcg64_random(state, inc, 1001, "f64"), np.random.default_rng(seed).random(1001))
+        assert np.array_equal(O.pcg64_random(state, inc, 1001, "f32"), np.random.default_rng(seed).random(1001, dtype=np.float32))
+        assert np.array_equal(O.pcg64_random(state, inc, 999, "bounded", 0, 2**31),
+                              np.random.default_rng(seed).integers(0, 2**31, 999, dtype=np.int64))
+        assert O.pcg64_random(state, inc, 10, "u32").tobytes() == np.random.default_rng(seed).bytes(40)
+        for k in (1, 8, 2040, 16384, 16384 * 256, 3 * 16384 * 65536 + 12345):
+            P, G = O.pcg64_jump(k)
+            ref = np.random.PCG64(seed)
+            ref.advance(k)
+            assert (P * state + inc * G) % 2**128 == ref.state["state"]["state"]
