@@ -76,6 +76,7 @@ SIGNATURES = {
     "bci_device_info": (C.c_int, [C.POINTER(DevInfo)]),
     "bci_mem_info": (C.c_int, [_SZP, _SZP]),
     "bci_last_error": (C.c_char_p, []),
+    "bci_healthy": (C.c_int, []),
     "bci_alloc": (C.c_int, [C.c_size_t, _VPP]),
     "bci_free": (C.c_int, [C.c_void_p]),
     "bci_host_alloc": (C.c_int, [C.c_size_t, _VPP]),

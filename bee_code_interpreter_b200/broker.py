@@ -50,6 +50,9 @@ class NativeBroker:
         L.load().bci_broker_stats(arr)
         return {"jobs": arr[0], "batches": arr[1], "max_batch": arr[2], "connections": arr[3]}
 
+    def healthy(self) -> bool:
+        return bool(L.load().bci_healthy())
+
     def close(self):
         L.load().bci_broker_stop()
 
@@ -418,7 +421,6 @@ class BrokerProcess:
 
     def __init__(self, device: int | None = None, coalesce_us: int = 150, fake_device: str | None = None,
                  extra_pythonpath: str | None = None):
-        import subprocess
         import sys
 
         self._dir = tempfile.mkdtemp(prefix="bci-broker-")
@@ -433,10 +435,31 @@ class BrokerProcess:
             cmd += ["--device", str(device)]
         if fake_device:
             cmd += ["--fake-device", fake_device]
-        self._proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, env=env, cwd=root)
+        self._cmd, self._env, self._root = cmd, env, root
+        self.restarts = 0
+        self._start()
+
+    def _start(self):
+        import subprocess
+
+        self._proc = subprocess.Popen(self._cmd, stdout=subprocess.PIPE, env=self._env, cwd=self._root)
         line = self._proc.stdout.readline()
         if line.strip() != b"ready":
             raise L.BciError(L.ERR_NOT_INIT, "GPU broker process failed to start (is a B200 visible?)")
+
+    def alive(self) -> bool:
+        return self._proc.poll() is None
+
+    def restart(self) -> None:
+        """A broker that died (or gave up its poisoned CUDA context, see main()) is started again on the same socket."""
+        if self.alive():
+            return
+        try:
+            os.unlink(self.socket_path)
+        except OSError:
+            pass
+        self.restarts += 1
+        self._start()
 
     def close(self):
         if self._proc.poll() is None:
@@ -474,7 +497,12 @@ def main():  # python -m bee_code_interpreter_b200.broker --socket PATH [--devic
     signal.signal(signal.SIGTERM, lambda *_: sys.exit(0))
     try:
         while os.getppid() == parent:   # do not outlive the service that started us
-            time.sleep(1.0)
+            time.sleep(0.25)
+            # a sticky CUDA error (one request's faulting launch) poisons the whole context: hand the GPU back
+            # and let the executor start a fresh broker, instead of failing every later request
+            if hasattr(broker, "healthy") and not broker.healthy():
+                sys.stderr.write("bci broker: CUDA context is unusable, exiting for a restart\n")
+                os._exit(17)
     finally:
         broker.close()
 

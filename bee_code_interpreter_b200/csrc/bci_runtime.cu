@@ -28,8 +28,19 @@ void set_error(const char* fmt, ...) {
   g_err = buf;
 }
 
+static std::atomic<int> g_poisoned{0};
+
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   set_error("CUDA error %d (%s) at %s:%d in `%s`", (int)e, cudaGetErrorString(e), file, line, what);
+  switch (e) {   // errors that leave the context unusable: every later call would fail the same way
+    case cudaErrorIllegalAddress: case cudaErrorLaunchFailure: case cudaErrorHardwareStackError:
+    case cudaErrorIllegalInstruction: case cudaErrorMisalignedAddress: case cudaErrorInvalidAddressSpace:
+    case cudaErrorInvalidPc: case cudaErrorECCUncorrectable: case cudaErrorLaunchTimeout:
+    case cudaErrorAssert: case cudaErrorCudartUnloading: case cudaErrorContextIsDestroyed:
+      g_poisoned.store((int)e);
+      break;
+    default: break;
+  }
   cudaGetLastError();  // clear the sticky-less error state
   return e == cudaErrorMemoryAllocation ? BCI_ERR_OOM : BCI_ERR_CUDA;
 }
@@ -161,6 +172,8 @@ extern "C" {
 int bci_abi_version(void) { return BCI_ABI_VERSION; }
 
 const char* bci_last_error(void) { return g_err.c_str(); }
+
+int bci_healthy(void) { return g_poisoned.load() == 0 ? 1 : 0; }
 
 int bci_device_count(int* count) {
   if (!count) { set_error("count is NULL"); return BCI_ERR_INVALID; }

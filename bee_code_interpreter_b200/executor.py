@@ -52,7 +52,8 @@ class LocalGpuExecutor:
 
     def __init__(self, file_storage=None, *, max_inflight: int = 16, timeout: float = 60.0,
                  broker=None, device_module=None, storage_path: str | None = None,
-                 min_rand_elems: int | None = None, zygotes: int | None = None, device: int | None = None):
+                 min_rand_elems: int | None = None, zygotes: int | None = None, device: int | None = None,
+                 retry_attempts: int = 3, retry_wait: tuple[float, float] = (0.1, 2.0), zygote_pool: int | None = None):
         # max_inflight = requests admitted at once (the rest wait on a semaphore).  16 per GPU is the
         # measured optimum for short scripts: the broker needs ~2 dispatch groups of work to keep the
         # GPU busy, and every additional live script process lengthens the fork / set-up phase of
@@ -87,12 +88,43 @@ class LocalGpuExecutor:
         self._sem_loop = None
         n_zyg = zygotes if zygotes is not None else max(1, min(8, (os.cpu_count() or 2) // 8))
         from .zygote import ZygoteClient
-        self._zygotes = [ZygoteClient() for _ in range(n_zyg)]
+        self._zygotes = [ZygoteClient(pool=zygote_pool) for _ in range(n_zyg)]
         self._rr = 0
+        # backend failures (a warm interpreter or the broker died) are retried like the reference retries
+        # RuntimeError (kubernetes_code_executor.py:75-79: 3 attempts, exponential wait) after the dead part
+        # has been started again; a zygote comes back in ~0.3 s, so the waits are shorter than a pod's
+        self.retry_attempts, self.retry_wait = max(1, retry_attempts), retry_wait
+        self._heal_lock = threading.Lock()
 
     # ---- public API ---------------------------------------------------------------------
     async def execute(self, source_code: str, files: Mapping[str, str] = {}, env: Mapping[str, str] = {}) -> Result:
         _validate(source_code, files, env)
+        attempt = 0
+        while True:
+            try:
+                return await self._execute_once(source_code, files, env)
+            except RuntimeError:
+                attempt += 1
+                if attempt >= self.retry_attempts:
+                    raise
+                await asyncio.sleep(min(self.retry_wait[1], self.retry_wait[0] * 2 ** (attempt - 1)))
+                await asyncio.get_running_loop().run_in_executor(None, self.heal)
+
+    def heal(self) -> dict:
+        """Starts again whatever died: warm interpreters, and the broker process when this executor owns it."""
+        done = {"zygotes": 0, "broker": 0}
+        with self._heal_lock:
+            for z in self._zygotes:
+                if not z.alive():
+                    z.restart()
+                    done["zygotes"] += 1
+            alive = getattr(self.broker, "alive", None)
+            if self._own_broker and alive is not None and not alive():
+                self.broker.restart()
+                done["broker"] += 1
+        return done
+
+    async def _execute_once(self, source_code: str, files: Mapping[str, str], env: Mapping[str, str]) -> Result:
         loop = asyncio.get_running_loop()
         if self._sem is None or self._sem_loop is not loop:
             self._sem, self._sem_loop = asyncio.Semaphore(self.max_inflight), loop
@@ -100,9 +132,8 @@ class LocalGpuExecutor:
             # one directory per request on tmpfs when there is one: ~12 metadata operations per
             # request at thousands of requests/s is what a journalled /tmp serialises on
             base = Path(tempfile.mkdtemp(prefix="bci-req-", dir=_SCRATCH_DIR))
-            workspace, capture = base / "workspace", base / "io"
+            workspace, capture = base / "workspace", base
             workspace.mkdir()
-            capture.mkdir()
             try:
                 for file_path, object_id in files.items():
                     target = _workspace_target(workspace, file_path)
@@ -148,20 +179,41 @@ class LocalGpuExecutor:
         return w.hash
 
     def _run_process(self, source_code: str, workspace: str, env: dict, capture: Path):
-        out_path, err_path = str(capture / "stdout"), str(capture / "stderr")
-        script_path = str(capture / "script.py")
-        with open(script_path, "w", encoding="utf-8", errors="surrogatepass") as f:
-            f.write(source_code)
-        req = {"source_code": source_code, "workspace": workspace, "env": env, "stdout_path": out_path,
-               "stderr_path": err_path, "broker_socket": self.broker.socket_path,
-               "min_rand_elems": self.min_rand_elems, "script_path": script_path}
-        self._rr = (self._rr + 1) % len(self._zygotes)
-        code = self._zygotes[self._rr].run(req, self.timeout)
-        if code is None:
-            return "", "Execution timed out", -1   # executor/server.rs:169
-        if code < 0:
-            code = -1                               # died on a signal (executor/server.rs:165)
-        return _read_text(out_path), _read_text(err_path), code
+        # stdout / stderr are captured in two anonymous memory files whose descriptors travel with the
+        # request; the script's source file is written by the request's own process
+        out_fd, err_fd = _capture_fd("stdout"), _capture_fd("stderr")
+        try:
+            req = {"source_code": source_code, "workspace": workspace, "env": env,
+                   "broker_socket": self.broker.socket_path, "min_rand_elems": self.min_rand_elems,
+                   "script_path": str(capture / "script.py"), "write_script": True}
+            alive = getattr(self.broker, "alive", None)
+            if self._own_broker and alive is not None and not alive():
+                raise RuntimeError("the GPU broker process is gone")    # retried after heal(): scripts must not run on the host silently
+            self._rr = (self._rr + 1) % len(self._zygotes)
+            code = self._zygotes[self._rr].run(req, self.timeout, out_fd, err_fd)
+            if code is None:
+                return "", "Execution timed out", -1   # executor/server.rs:169
+            if code < 0:
+                code = -1                               # died on a signal (executor/server.rs:165)
+            return _read_fd(out_fd), _read_fd(err_fd), code
+        finally:
+            os.close(out_fd)
+            os.close(err_fd)
+
+
+def _capture_fd(name: str) -> int:
+    try:
+        return os.memfd_create("bci-" + name, os.MFD_CLOEXEC)
+    except (AttributeError, OSError):
+        fd, path = tempfile.mkstemp(prefix="bci-" + name + "-", dir=_SCRATCH_DIR)
+        os.unlink(path)
+        return fd
+
+
+def _read_fd(fd: int) -> str:
+    size = os.fstat(fd).st_size
+    data = os.pread(fd, size, 0) if size else b""
+    return data.decode("utf-8", "replace")               # lossy like server.rs:163-164
 
 
 def _read_text(path: str) -> str:

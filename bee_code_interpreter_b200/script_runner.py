@@ -31,7 +31,10 @@ def _finish_like_an_interpreter() -> None:
     atexit._run_exitfuncs()
 
 
-def run_in_child(req: dict) -> int:
+def run_in_child(req: dict, stdout_fd: int | None = None, stderr_fd: int | None = None) -> int:
+    """`stdout_fd` / `stderr_fd`: capture descriptors the service passed along with the request (anonymous
+    memory files); without them the request names capture FILES (`stdout_path`, `stderr_path`: the native
+    executor server's form)."""
     os.chdir(req["workspace"])
     env = req.get("env")
     if env:
@@ -44,8 +47,8 @@ def run_in_child(req: dict) -> int:
     os.dup2(null_fd, 0)
     os.close(null_fd)
     sys.stdin = os.fdopen(0, "r", closefd=False)
-    out_fd = os.open(req["stdout_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
-    err_fd = os.open(req["stderr_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    out_fd = stdout_fd if stdout_fd is not None else os.open(req["stdout_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    err_fd = stderr_fd if stderr_fd is not None else os.open(req["stderr_path"], os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
     os.dup2(out_fd, 1)
     os.dup2(err_fd, 2)
     os.close(out_fd)
@@ -55,6 +58,12 @@ def run_in_child(req: dict) -> int:
     # the service wrote the source next to the capture files (server.rs:124 writes script.py into a
     # temp dir): tracebacks quote the failing line and inspect / multiprocessing find a real file
     script = req.get("script_path") or "script.py"
+    if req.get("write_script"):       # the request's own process writes its source file (one less job for the service)
+        try:
+            with open(script, "w", encoding="utf-8", errors="surrogatepass") as f:
+                f.write(req["source_code"])
+        except OSError:
+            pass
     sys.argv = [script]
     numpy_hook.reset_request_state()
     numpy_hook.install(min_rand_elems=req.get("min_rand_elems"))

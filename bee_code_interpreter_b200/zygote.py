@@ -1,16 +1,22 @@
-"""Warm-interpreter zygote: forks one child per `/v1/execute` request.
+"""Warm-interpreter zygote: one fresh OS process per `/v1/execute` request, forked ahead of time.
 
 The reference keeps a queue of warm pods and spends one per request
 (kubernetes_code_executor.py:151-189,248-264); inside the pod each request still pays a fresh
 interpreter (`xonsh script.xsh`, executor/server.rs:152).  Here the warm resource is a Python
-process with numpy, the proxy layer and the import hook already imported; a request costs one
-fork() of it (~2 ms) and keeps the reference's isolation unit — one OS process per request.
+process with numpy, the proxy layer and the import hook already imported, and — like the
+reference's pod QUEUE — a few children of it that were forked BEFORE any request arrived and
+sit blocked on a socket pair.  A request is handed to one of them (its connection and capture
+descriptors travel as SCM_RIGHTS), and the replacement is forked after the hand-off, off the
+request's critical path.  The isolation unit stays the reference's: one OS process per request,
+never reused.
 
 The zygote is single-threaded and holds no CUDA context, so fork() is safe.  Protocol (Unix
 stream socket, one connection per request):
-    client -> zygote : 4-byte length + request dict (pickle from ZygoteClient, JSON from
-                       csrc/bci_executor_server.cpp)
-    child  -> client : 4-byte pid, first thing after the fork  (the zygote closes its copy)
+    client -> zygote : 4-byte length + request as a JSON object (ZygoteClient and
+                       csrc/bci_executor_server.cpp speak the same form; nothing is unpickled:
+                       any local process of the same user can reach this socket)
+                       + optionally two descriptors (SCM_RIGHTS): where stdout / stderr go
+    child  -> client : 4-byte pid, first thing              (the zygote closes its copy)
     child  -> client : 4-byte exit code, just before os._exit  (absent if the child was killed
                        or crashed: the client maps EOF to -1, like server.rs:165)
 Children are auto-reaped (SIGCHLD ignored).
@@ -19,28 +25,103 @@ from __future__ import annotations
 
 import json
 import os
-import pickle
 import signal
 import socket
 import struct
 import subprocess
 import sys
 import tempfile
-import time
+
+POOL_ENV = "BCI_ZYGOTE_POOL"      # children forked ahead of requests (0 = fork on arrival)
+MAX_REQUEST = 64 << 20
 
 
-def _recv_exact(conn: socket.socket, n: int) -> bytes:
+def _recv_exact(conn: socket.socket, n: int, fds: list | None = None) -> bytes:
     buf = b""
     while len(buf) < n:
-        chunk = conn.recv(n - len(buf))
+        if fds is not None:
+            chunk, got, _f, _a = socket.recv_fds(conn, n - len(buf), 4)
+            fds.extend(got)
+        else:
+            chunk = conn.recv(n - len(buf))
         if not chunk:
             return buf
         buf += chunk
     return buf
 
 
+def _send_with_fds(sock: socket.socket, data: bytes, fds: list[int]) -> None:
+    sent = socket.send_fds(sock, [data], fds) if fds else sock.send(data)
+    if sent < len(data):
+        sock.sendall(data[sent:])
+
+
+def _serve_request(conn: socket.socket, payload: bytes, out_fds: list[int]) -> None:
+    """Body of the per-request process: never returns."""
+    from . import script_runner
+
+    code = 1
+    try:
+        # the CHILD announces its pid: if the parent did, a short script could finish and
+        # write its exit code first, and the client would read the two words swapped
+        os.setsid()   # own process group: a timeout (and the end of the request) reaps what the script spawned
+        conn.sendall(struct.pack("<i", os.getpid()))
+        req = json.loads(payload)
+        if not isinstance(req, dict):
+            raise ValueError("request is not an object")
+        code = script_runner.run_in_child(req, out_fds[0] if len(out_fds) >= 2 else None,
+                                          out_fds[1] if len(out_fds) >= 2 else None)
+    finally:
+        try:
+            conn.sendall(struct.pack("<i", code))
+        except OSError:
+            pass
+        os._exit(code & 0xFF)
+
+
+class _Idle:
+    """A child forked ahead of time, blocked on its end of a socket pair."""
+
+    __slots__ = ("sock", "pid")
+
+    def __init__(self, sock, pid):
+        self.sock, self.pid = sock, pid
+
+
+def _spawn_idle(srv: socket.socket, idle: list) -> "_Idle | None":
+    a, b = socket.socketpair(socket.AF_UNIX, socket.SOCK_STREAM)
+    try:
+        pid = os.fork()
+    except OSError:
+        a.close()
+        b.close()
+        return None
+    if pid:
+        b.close()
+        return _Idle(a, pid)
+    # ---- pre-forked child: wait for a request (or for the zygote to go away) -------------------
+    try:
+        srv.close()
+        a.close()
+        for other in idle:            # siblings' hand-off sockets: keeping them open would hide the zygote's death
+            other.sock.close()
+        fds: list[int] = []
+        head = _recv_exact(b, 4, fds)
+        if len(head) < 4:
+            os._exit(0)               # the zygote exited
+        (length,) = struct.unpack("<I", head)
+        payload = _recv_exact(b, length, fds)
+        b.close()
+        if len(payload) < length or not fds:
+            os._exit(0)
+        conn = socket.socket(fileno=fds[0])
+        _serve_request(conn, payload, fds[1:])
+    finally:
+        os._exit(1)
+
+
 def serve(socket_path: str) -> None:
-    from . import script_runner  # imports numpy + proxy + hook once
+    from . import script_runner  # noqa: F401  imports numpy + proxy + hook once
 
     signal.signal(signal.SIGCHLD, signal.SIG_IGN)
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
@@ -50,6 +131,12 @@ def serve(socket_path: str) -> None:
         pass
     srv.bind(socket_path)
     srv.listen(1024)
+    pool_size = max(0, int(os.environ.get(POOL_ENV, "4") or 0))
+    idle: list[_Idle] = []
+    for _ in range(pool_size):
+        ch = _spawn_idle(srv, idle)
+        if ch is not None:
+            idle.append(ch)
     sys.stdout.write("ready\n")
     sys.stdout.flush()
     parent = os.getppid()
@@ -63,38 +150,56 @@ def serve(socket_path: str) -> None:
             continue
         except OSError:
             break
+        fds: list[int] = []
         try:
-            head = _recv_exact(conn, 4)
+            conn.settimeout(30.0)
+            head = _recv_exact(conn, 4, fds)
             if len(head) < 4:
-                conn.close()
                 continue
             (length,) = struct.unpack("<I", head)
-            payload = _recv_exact(conn, length)
-            # pickled dict from ZygoteClient, JSON object from the native executor server
-            req = json.loads(payload) if payload[:1] == b"{" else pickle.loads(payload)
-            if req.get("op") == "shutdown":
-                conn.close()
+            if length > MAX_REQUEST:
+                continue
+            payload = _recv_exact(conn, length, fds)
+            if len(payload) < length:
+                continue
+            if payload[:1] != b"{":
+                continue                    # only JSON objects are requests
+            if length < 64 and json.loads(payload).get("op") == "shutdown":
                 break
-            pid = os.fork()
-            if pid == 0:
-                srv.close()
-                code = 1
+            conn.settimeout(None)
+            handed = False
+            while idle and not handed:
+                ch = idle.pop(0)
                 try:
-                    # the CHILD announces its pid: if the parent did, a short script could finish and
-                    # write its exit code first, and the client would read the two words swapped
-                    os.setsid()   # own process group: a timeout (and the end of the request) reaps what the script spawned
-                    conn.sendall(struct.pack("<i", os.getpid()))
-                    code = script_runner.run_in_child(req)
+                    _send_with_fds(ch.sock, struct.pack("<I", length) + payload, [conn.fileno()] + fds)
+                    handed = True
+                except OSError:
+                    pass                    # that child is gone: try the next one
                 finally:
-                    try:
-                        conn.sendall(struct.pack("<i", code))
-                    except OSError:
-                        pass
-                    os._exit(code & 0xFF)
+                    ch.sock.close()
+            if not handed:
+                pid = os.fork()
+                if pid == 0:
+                    srv.close()
+                    for other in idle:
+                        other.sock.close()
+                    _serve_request(conn, payload, fds)
         except Exception:
             pass
         finally:
             conn.close()
+            for f in fds:
+                try:
+                    os.close(f)
+                except OSError:
+                    pass
+        while len(idle) < pool_size:        # the replacement is forked AFTER the hand-off
+            ch = _spawn_idle(srv, idle)
+            if ch is None:
+                break
+            idle.append(ch)
+    for ch in idle:
+        ch.sock.close()                     # EOF: the waiting children exit
     try:
         os.unlink(socket_path)
     except OSError:
@@ -112,12 +217,22 @@ def _kill_group(pid: int) -> None:
             pass
 
 
+class ZygoteDied(RuntimeError):
+    """The warm interpreter is gone (RuntimeError: the class the reference's retry policy acts on,
+    kubernetes_code_executor.py:75-79)."""
+
+
 class ZygoteClient:
     """Service-side handle: starts the zygote process and submits requests to it."""
 
-    def __init__(self):
+    def __init__(self, pool: int | None = None):
         self._dir = tempfile.mkdtemp(prefix="bci-zygote-")
         self.socket_path = os.path.join(self._dir, "zygote.sock")
+        self._pool = pool
+        self._proc = None
+        self._start()
+
+    def _start(self) -> None:
         env = dict(os.environ)
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         env["PYTHONPATH"] = root + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
@@ -125,23 +240,42 @@ class ZygoteClient:
         # process, and a sandboxed request gets one host thread (heavy array work goes to the GPU)
         for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
             env.setdefault(var, "1")
+        if self._pool is not None:
+            env[POOL_ENV] = str(self._pool)
         self._proc = subprocess.Popen([sys.executable, "-m", "bee_code_interpreter_b200.zygote", self.socket_path],
                                       stdout=subprocess.PIPE, env=env, cwd=root)
         line = self._proc.stdout.readline()
         if line.strip() != b"ready":
-            raise RuntimeError("zygote failed to start")
+            raise ZygoteDied("zygote failed to start")
 
-    def run(self, req: dict, timeout: float) -> int | None:
-        """Forks a child for `req`; returns its exit code, -1 if it died without reporting,
-        or None on timeout (the child is killed)."""
-        payload = pickle.dumps(req, protocol=pickle.HIGHEST_PROTOCOL)
+    def alive(self) -> bool:
+        return self._proc is not None and self._proc.poll() is None
+
+    def restart(self) -> None:
+        """A dead zygote is replaced (the reference respawns pods that failed, kubernetes_code_executor.py:176-182)."""
+        if self.alive():
+            return
+        try:
+            os.unlink(self.socket_path)
+        except OSError:
+            pass
+        self._start()
+
+    def run(self, req: dict, timeout: float, stdout_fd: int | None = None, stderr_fd: int | None = None) -> int | None:
+        """Hands `req` to a fresh child; returns its exit code, -1 if it died without reporting,
+        or None on timeout (the child is killed).  Raises ZygoteDied when no child could be had."""
+        payload = json.dumps(req).encode()
         conn = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
         try:
-            conn.connect(self.socket_path)
-            conn.sendall(struct.pack("<I", len(payload)) + payload)
-            head = _recv_exact(conn, 4)
+            try:
+                conn.connect(self.socket_path)
+                fds = [stdout_fd, stderr_fd] if stdout_fd is not None and stderr_fd is not None else []
+                _send_with_fds(conn, struct.pack("<I", len(payload)) + payload, fds)
+                head = _recv_exact(conn, 4)
+            except OSError as e:
+                raise ZygoteDied(f"zygote unreachable: {e}") from None
             if len(head) < 4:
-                raise RuntimeError("zygote closed the connection before forking")
+                raise ZygoteDied("zygote closed the connection before a child took the request")
             (pid,) = struct.unpack("<i", head)
             conn.settimeout(timeout)
             try:
@@ -158,7 +292,7 @@ class ZygoteClient:
 
     def close(self) -> None:
         try:
-            payload = pickle.dumps({"op": "shutdown"})
+            payload = json.dumps({"op": "shutdown"}).encode()
             conn = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
             conn.settimeout(1.0)
             conn.connect(self.socket_path)

@@ -115,6 +115,10 @@ int bci_device_count(int* count);
 int bci_device_info(bci_devinfo* info);
 int bci_mem_info(size_t* free_bytes, size_t* total_bytes);
 const char* bci_last_error(void);
+/* 0 once a CUDA error has left the context unusable (illegal address, launch failure, ECC...): the
+ * owner process should exit and be restarted — the executor does that for its broker, the way the
+ * reference discards a pod that failed (kubernetes_code_executor.py:176-182,262-264). */
+int bci_healthy(void);
 
 /* Device buffers (256-byte aligned, stream-ordered pool; freed memory is reused
  * by the next wave of requests without returning to the driver). */

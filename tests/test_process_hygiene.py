@@ -104,3 +104,34 @@ def test_files_map_cannot_leave_the_workspace(tmp_path):
     for bad in ("/workspace/../evil", "/workspace/a/../../evil", "/..", "/workspace/"):
         with pytest.raises(ValueError):
             E._workspace_target(ws, bad)
+
+
+def test_dead_zygote_and_dead_broker_are_restarted_and_the_request_retried(built):
+    """kubernetes_code_executor.py:75-79 retries `execute` on RuntimeError; here the dead part (warm interpreter,
+    broker process) is started again between the attempts, so the caller sees a normal result."""
+    import asyncio
+    import os
+    import signal
+    import sys
+    from pathlib import Path
+
+    from bee_code_interpreter_b200.broker import BrokerProcess
+    from bee_code_interpreter_b200.executor import LocalGpuExecutor
+
+    tests_dir = str(Path(__file__).resolve().parent)
+    broker = BrokerProcess(fake_device="fake_device", extra_pythonpath=tests_dir)
+    ex = LocalGpuExecutor(broker=broker, max_inflight=4, timeout=20, zygotes=1, min_rand_elems=1000, retry_wait=(0.05, 0.2))
+    ex._own_broker = True      # this executor is responsible for the broker it was given
+    try:
+        src = "import numpy as np\nx = np.random.rand(5000)\nprint(type(x).__name__, float(np.sum(x)) > 0)\n"
+        assert asyncio.run(ex.execute(src)).stdout == "DeviceArray True\n"
+        os.kill(ex._zygotes[0]._proc.pid, signal.SIGKILL)
+        ex._zygotes[0]._proc.wait()
+        r = asyncio.run(ex.execute(src))
+        assert r.exit_code == 0 and r.stdout == "DeviceArray True\n"
+        os.kill(broker._proc.pid, signal.SIGKILL)
+        broker._proc.wait()
+        r = asyncio.run(ex.execute(src))
+        assert r.exit_code == 0 and r.stdout == "DeviceArray True\n" and broker.restarts == 1
+    finally:
+        ex.close()
