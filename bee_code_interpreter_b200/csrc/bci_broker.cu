@@ -218,6 +218,27 @@ int run_group(std::vector<Job*>& grp) {
   return BCI_ERR_INVALID;
 }
 
+// Runs one group and wakes its waiters.  A failing group is retried job by job so that one bad request
+// cannot fail its neighbours.
+void complete_group(std::vector<Job*>& grp) {
+  int rc = run_group(grp);
+  if (rc != BCI_OK && grp.size() > 1) {
+    for (Job* j : grp) {  // isolate the offender
+      std::vector<Job*> one{j};
+      j->status = run_group(one);
+      if (j->status != BCI_OK) j->error = bci_last_error();
+    }
+  } else {
+    const std::string err = rc != BCI_OK ? bci_last_error() : "";
+    for (Job* j : grp) { j->status = rc; j->error = err; }
+  }
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    for (Job* j : grp) j->done = true;
+  }
+  g.cv_done.notify_all();
+}
+
 void dispatch_loop() {
   while (g.running.load()) {
     std::vector<Job*> jobs;
@@ -239,23 +260,17 @@ void dispatch_loop() {
       g.n_batches++;
       g.n_jobs += grp.size();
       if (grp.size() > g.max_batch.load()) g.max_batch = grp.size();
-      int rc = run_group(grp);
-      if (rc != BCI_OK && grp.size() > 1) {
-        for (Job* j : grp) {  // isolate the offender
-          std::vector<Job*> one{j};
-          j->status = run_group(one);
-          if (j->status != BCI_OK) j->error = bci_last_error();
-        }
+      const uint32_t op = grp[0]->rq.op;
+      const bool hashing = op == BRK_SHA256_DEV || op == BRK_SHA256_BYTES || op == BRK_SHA256_UPDATE || op == BRK_SHA256_FINAL;
+      if (hashing) {
+        // a hashing launch lasts as long as its longest message (one SHA-256 is a serial chain: ~1 s for
+        // 64 MiB) and runs on a side stream: it gets its own thread so that the dispatchers keep packing
+        // everybody else's ops meanwhile
+        std::thread([grp]() mutable { complete_group(grp); }).detach();
       } else {
-        const std::string err = rc != BCI_OK ? bci_last_error() : "";
-        for (Job* j : grp) { j->status = rc; j->error = err; }
+        complete_group(grp);
       }
     }
-    {
-      std::lock_guard<std::mutex> lk(g.mu);
-      for (Job* j : jobs) j->done = true;
-    }
-    g.cv_done.notify_all();
   }
 }
 

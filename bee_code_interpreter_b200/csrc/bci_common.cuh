@@ -44,7 +44,7 @@ struct Ctx {
     bool busy = false;
     cudaEvent_t done = nullptr;
   };
-  static constexpr int kResultSlots = 8;
+  static constexpr int kResultSlots = 32;
   ResultSlot rslot[kResultSlots];
   // L2 flush buffer
   uint8_t* flush = nullptr;

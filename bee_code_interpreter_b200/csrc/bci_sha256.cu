@@ -16,6 +16,7 @@
 // length works; data is read with 128-bit loads when the pointer is 16-byte aligned.
 #include "bci_common.cuh"
 #include <vector>
+#include <condition_variable>
 #include <cstring>
 
 namespace bci {
@@ -240,34 +241,92 @@ sha256_thread_kernel(const ShaMsg* __restrict__ msgs, int B, uint32_t* __restric
   o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4; o[5] = s5; o[6] = s6; o[7] = s7;
 }
 
+// Side streams for hashing.  One SHA-256 is a serial chain: a launch over a few large messages runs for as long as
+// its longest message (64 MiB: ~1 s) while using a handful of warps.  On the op stream it would stall every
+// other request's launches for that long, so hashing launches go to one of a few side streams (ordered after
+// the op stream by an event) and the library lock is released while the digests are awaited; launches of
+// different callers overlap on the GPU.
+namespace {
+constexpr int kShaStreams = 16;
+struct ShaLane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t order = nullptr, done = nullptr;
+  uint32_t* h_out = nullptr;   // pinned
+  uint32_t* d_out = nullptr;
+  ShaMsg* d_msgs = nullptr;
+  ShaMsg* h_msgs = nullptr;    // pinned
+  size_t cap = 0;              // messages
+  bool busy = false;
+};
+ShaLane g_sha_lanes[kShaStreams];
+std::condition_variable g_sha_cv;
+
+// called with the context lock held; may wait (lock released) for a free lane
+int sha_lane_acquire(std::unique_lock<std::mutex>& lk, size_t B, ShaLane** out) {
+  for (;;) {
+    for (auto& l : g_sha_lanes) {
+      if (l.busy) continue;
+      if (!l.stream) {
+        BCI_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        BCI_CUDA(cudaEventCreateWithFlags(&l.order, cudaEventDisableTiming));
+        BCI_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+      }
+      if (B > l.cap) {
+        if (l.h_out) cudaFreeHost(l.h_out);
+        if (l.h_msgs) cudaFreeHost(l.h_msgs);
+        if (l.d_out) cudaFree(l.d_out);
+        if (l.d_msgs) cudaFree(l.d_msgs);
+        l.h_out = nullptr; l.h_msgs = nullptr; l.d_out = nullptr; l.d_msgs = nullptr; l.cap = 0;
+        const size_t cap = B * 2 < 64 ? 64 : B * 2;
+        BCI_CUDA(cudaHostAlloc((void**)&l.h_out, cap * 32, cudaHostAllocDefault));
+        BCI_CUDA(cudaHostAlloc((void**)&l.h_msgs, cap * sizeof(ShaMsg), cudaHostAllocDefault));
+        BCI_CUDA(cudaMalloc((void**)&l.d_out, cap * 32));
+        BCI_CUDA(cudaMalloc((void**)&l.d_msgs, cap * sizeof(ShaMsg)));
+        l.cap = cap;
+      }
+      l.busy = true;
+      *out = &l;
+      return BCI_OK;
+    }
+    g_sha_cv.wait(lk);
+  }
+}
+}  // namespace
+
 // Runs one launch over `B` prepared messages; states come back to `h_states` (B x 8 words).
-// Called with the context lock held (`lk`); the digest read-back waits under the lock as before —
-// a hashing launch occupies the op stream for its whole duration anyway.
+// Called with the context lock held (`lk`): the launch is enqueued under it, the wait for the digests is not.
 static int sha_launch(std::unique_lock<std::mutex>& lk, std::vector<ShaMsg>& msgs, uint32_t* h_states) {
   Ctx& c = ctx();
   const int B = (int)msgs.size();
-  void* d_msgs = nullptr;
-  int rc = stage_upload(msgs.data(), sizeof(ShaMsg) * (size_t)B, &d_msgs);
+  ShaLane* lane = nullptr;
+  int rc = sha_lane_acquire(lk, (size_t)B, &lane);
   if (rc != BCI_OK) return rc;
-  void *h = nullptr, *d = nullptr;
-  ResultGuard guard;
-  guard.lock_held = true;
-  rc = result_acquire(lk, (size_t)B * 32, &guard.slot, &h, &d);
-  if (rc != BCI_OK) return rc;
+  struct Release {
+    ShaLane* l; std::unique_lock<std::mutex>& lk;
+    ~Release() { if (!lk.owns_lock()) lk.lock(); l->busy = false; g_sha_cv.notify_one(); }
+  } release{lane, lk};
+  memcpy(lane->h_msgs, msgs.data(), sizeof(ShaMsg) * (size_t)B);
+  // everything the messages refer to (uploads, producers) is already enqueued on the op stream
+  BCI_CUDA(cudaEventRecord(lane->order, c.stream));
+  BCI_CUDA(cudaStreamWaitEvent(lane->stream, lane->order, 0));
+  BCI_CUDA(cudaMemcpyAsync(lane->d_msgs, lane->h_msgs, sizeof(ShaMsg) * (size_t)B, cudaMemcpyHostToDevice, lane->stream));
   // many small messages: thread-per-message fills the lanes; few large: warp-per-message
   const int warp_slots = c.sm_count * 4 * 2;
   if (B > warp_slots) {
     const int threads = 128;
-    sha256_thread_kernel<<<(B + threads - 1) / threads, threads, 0, c.stream>>>(
-        reinterpret_cast<const ShaMsg*>(d_msgs), B, reinterpret_cast<uint32_t*>(d));
+    sha256_thread_kernel<<<(B + threads - 1) / threads, threads, 0, lane->stream>>>(lane->d_msgs, B, lane->d_out);
   } else {
-    sha256_warp_kernel<<<(B + kShaWarps - 1) / kShaWarps, kShaWarps * 32, 0, c.stream>>>(
-        reinterpret_cast<const ShaMsg*>(d_msgs), B, reinterpret_cast<uint32_t*>(d), 1u, 1u, 1u, 0xffffffffu);
+    sha256_warp_kernel<<<(B + kShaWarps - 1) / kShaWarps, kShaWarps * 32, 0, lane->stream>>>(
+        lane->d_msgs, B, lane->d_out, 1u, 1u, 1u, 0xffffffffu);
   }
   BCI_CHECK_LAUNCH();
-  if ((rc = result_enqueue_copy(guard.slot, (size_t)B * 32)) != BCI_OK) return rc;
-  if ((rc = result_wait(guard.slot)) != BCI_OK) return rc;
-  memcpy(h_states, h, (size_t)B * 32);
+  BCI_CUDA(cudaMemcpyAsync(lane->h_out, lane->d_out, (size_t)B * 32, cudaMemcpyDeviceToHost, lane->stream));
+  BCI_CUDA(cudaEventRecord(lane->done, lane->stream));
+  lk.unlock();                                   // other requests launch while this hash runs
+  cudaError_t e = cudaEventSynchronize(lane->done);
+  lk.lock();
+  if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize(sha)", __FILE__, __LINE__);
+  memcpy(h_states, lane->h_out, (size_t)B * 32);
   return BCI_OK;
 }
 

@@ -27,7 +27,7 @@ import types
 
 _real_import = builtins.__import__
 _state = {"backend": None, "backend_factory": None, "view": None, "seeded": False, "installed": False,
-          "min_rand": 1 << 16}
+          "min_rand": 1 << 16, "lib_views": {}}
 
 
 # ---- the reference's three post-import patches (executor/sitecustomize.py:9-27) -------------
@@ -333,6 +333,147 @@ def numpy_view():
     return _state["view"]
 
 
+# ---- pandas / scipy entry points agent code reaches device arrays through -----------------
+# examples/using_imports.py:25-36: pd.Series(x).mean() / .std(), scipy.stats.ttest_ind(a, b).  When `x` is a device
+# array these run as the fused mean / variance reductions; anything else is pandas / scipy itself on a host copy.
+def _build_pandas_view():
+    import numpy as real_np
+    import pandas as real_pd
+
+    from . import _lib as L
+    from . import numpy_proxy as P
+
+    class DeviceSeries:
+        """pd.Series over a 1-D float device array: the reductions of the reference's example run on the
+        device (pandas' own formulas: nanops.nanmean = sum / count, nanvar = two-pass with ddof); every other
+        attribute is the real pandas Series built from a host copy (once)."""
+
+        def __init__(self, data, kwargs):
+            self._dev, self._kwargs, self._real = data, kwargs, None
+
+        def _series(self):
+            if self._real is None:
+                self._real = real_pd.Series(real_np.asarray(self._dev), **self._kwargs)
+            return self._real
+
+        def _plain(self, args, kw, allowed=()):
+            return not args and all(k in allowed for k in kw)
+
+        def _clean(self):
+            """pandas skips NaN by default: only NaN-free data takes the device formulas (max propagates NaN)."""
+            try:
+                return not real_np.isnan(self._dev.max())
+            except Exception:
+                return False
+
+        def mean(self, *a, **kw):
+            if self._plain(a, kw) and self._clean():
+                return float(self._dev.mean())
+            return self._series().mean(*a, **kw)
+
+        def sum(self, *a, **kw):
+            if self._plain(a, kw) and self._clean():
+                return float(self._dev.sum())
+            return self._series().sum(*a, **kw)
+
+        def var(self, *a, **kw):
+            if self._plain(a, kw, ("ddof",)) and self._clean():
+                return float(self._dev.var(ddof=kw.get("ddof", 1)))       # pandas' default is ddof=1
+            return self._series().var(*a, **kw)
+
+        def std(self, *a, **kw):
+            if self._plain(a, kw, ("ddof",)) and self._clean():
+                return float(real_np.sqrt(self._dev.var(ddof=kw.get("ddof", 1))))
+            return self._series().std(*a, **kw)
+
+        def max(self, *a, **kw):
+            return float(self._dev.max()) if self._plain(a, kw) and self._clean() else self._series().max(*a, **kw)
+
+        def min(self, *a, **kw):
+            return float(self._dev.min()) if self._plain(a, kw) and self._clean() else self._series().min(*a, **kw)
+
+        def count(self):
+            return int(self._dev.size) if self._clean() else self._series().count()
+
+        def to_numpy(self, *a, **kw):
+            return self._dev if not a and not kw else self._series().to_numpy(*a, **kw)
+
+        @property
+        def values(self):
+            return self._dev
+
+        def __len__(self):
+            return len(self._dev)
+
+        def __repr__(self):
+            return repr(self._series())
+
+        def __getattr__(self, name):
+            if name.startswith("_"):
+                raise AttributeError(name)
+            return getattr(self._series(), name)
+
+    class _SeriesMeta(type):
+        def __instancecheck__(cls, obj):
+            return isinstance(obj, (real_pd.Series, DeviceSeries))
+
+        def __call__(cls, data=None, *args, **kwargs):
+            if (isinstance(data, P.DeviceArray) and not args and data.ndim == 1 and data.dtype.kind == "f"
+                    and all(k in ("name", "index") and (k == "name" or kwargs[k] is None) for k in kwargs)):
+                return DeviceSeries(data, kwargs)
+            return real_pd.Series(P._to_host(data), *P._to_host(args), **P._to_host(kwargs))
+
+        def __getattr__(cls, name):
+            return getattr(real_pd.Series, name)
+
+    class Series(metaclass=_SeriesMeta):
+        __doc__ = real_pd.Series.__doc__
+
+    return _ModuleView(real_pd, {"Series": Series})
+
+
+def _build_scipy_views():
+    import numpy as real_np
+    import scipy as real_scipy
+    import scipy.stats as real_stats
+
+    from . import numpy_proxy as P
+
+    def ttest_ind(a, b, *args, **kwargs):
+        """scipy.stats.ttest_ind for two 1-D float device arrays (default options, or equal_var / alternative):
+        sizes, means and ddof=1 variances come from the fused reductions, the statistic and p-value from
+        scipy's own ttest_ind_from_stats — the arrays themselves stay in HBM."""
+        dev = all(isinstance(x, P.DeviceArray) and x.ndim == 1 and x.dtype.kind == "f" and x.size > 1 for x in (a, b))
+        if dev and not args and all(k in ("equal_var", "alternative") for k in kwargs):
+            try:
+                m1, m2 = float(a.mean()), float(b.mean())
+                v1, v2 = float(a.var(ddof=1)), float(b.var(ddof=1))
+                if not (real_np.isnan(m1) or real_np.isnan(m2)):          # NaN handling (nan_policy) is scipy's business
+                    return real_stats.ttest_ind_from_stats(m1, real_np.sqrt(v1), a.size, m2, real_np.sqrt(v2), b.size, **kwargs)
+            except Exception:
+                pass
+        return real_stats.ttest_ind(P._to_host(a), P._to_host(b), *P._to_host(args), **P._to_host(kwargs))
+
+    ttest_ind.__doc__ = real_stats.ttest_ind.__doc__
+    stats_view = _ModuleView(real_stats, {"ttest_ind": ttest_ind})
+    return _ModuleView(real_scipy, {"stats": stats_view}), stats_view
+
+
+def _library_view(name: str, fromlist):
+    """Views of pandas / scipy(.stats) for agent code; built on first use, None when the library is not involved."""
+    if name == "pandas":
+        if "pandas" not in _state["lib_views"]:
+            _state["lib_views"]["pandas"] = _build_pandas_view()
+        return _state["lib_views"]["pandas"]
+    if name == "scipy" or name == "scipy.stats":
+        if "scipy" not in _state["lib_views"]:
+            _state["lib_views"]["scipy"], _state["lib_views"]["scipy.stats"] = _build_scipy_views()
+        if name == "scipy.stats" and fromlist:
+            return _state["lib_views"]["scipy.stats"]      # `from scipy.stats import ttest_ind`
+        return _state["lib_views"]["scipy"]                # `import scipy.stats`, `from scipy import stats`
+    return None
+
+
 def _from_agent_code(globals_) -> bool:
     return isinstance(globals_, dict) and globals_.get("__name__") == "__main__"
 
@@ -351,6 +492,13 @@ def patched_import(name, globals=None, locals=None, fromlist=(), level=0):
                 return view.random               # `from numpy.random import rand`
         except Exception:
             return module                        # hook failure must never break the script
+    elif level == 0 and name in ("pandas", "scipy", "scipy.stats") and _from_agent_code(globals):
+        try:
+            view = _library_view(name, fromlist)
+            if view is not None:
+                return view
+        except Exception:
+            return module
     return module
 
 

@@ -111,9 +111,11 @@ def c2_device(dev, L, idx, dist, peaks, reps=1):
             A = [dev.alloc(n * 4) for _ in ids]
             Bm = [dev.alloc(n * 4) for _ in ids]
             Cm = [dev.alloc(n * 4) for _ in ids]
+            sa = [_gen_state(1000 + i) for i in ids]                 # host-side seeding is not device time
+            sb = [_advanced(1000 + i, n // 2) for i in ids]          # the generator's next n words
             T.begin()
-            dev.rand_pcg64(L.PCG_F32, A, [n] * b, [_gen_state(1000 + i) for i in ids])
-            dev.rand_pcg64(L.PCG_F32, Bm, [n] * b, [_advanced(1000 + i, n // 2) for i in ids])     # the generator's next n words
+            dev.rand_pcg64(L.PCG_F32, A, [n] * b, sa)
+            dev.rand_pcg64(L.PCG_F32, Bm, [n] * b, sb)
             T.end("gen")
             T.begin()
             dev.matmul_f32(A, Bm, Cm, m, m, m)
@@ -153,10 +155,12 @@ def c3_device(dev, L, idx, dist, peaks, reps=5):
     Y = [dev.alloc(n * 4) for _ in idx]
     T = _Timer(dev)
     res = None
+    sx = [_gen_state(2000 + i) for i in idx]
+    sy = [_advanced(2000 + i, n // 2) for i in idx]
     for r in range(reps + 1):
         T.begin()
-        dev.rand_pcg64(L.PCG_F32, X, [n] * b, [_gen_state(2000 + i) for i in idx])
-        dev.rand_pcg64(L.PCG_F32, Y, [n] * b, [_advanced(2000 + i, n // 2) for i in idx])
+        dev.rand_pcg64(L.PCG_F32, X, [n] * b, sx)
+        dev.rand_pcg64(L.PCG_F32, Y, [n] * b, sy)
         T.end("gen" if r else "warm")
         T.begin()
         r1 = dev.reduce(L.RED_SUM, np.float32, X, [n] * b, pre=L.PRE_SQUARE)
@@ -207,7 +211,7 @@ def _hashlib_rate(buffers, threads) -> float:
     return sum(len(b) for b in buffers) / (time.perf_counter() - t0) / 1e9
 
 
-def c4_device(dev, L, idx, dist, peaks, reps=2, host_sample=32):
+def c4_device(dev, L, idx, dist, peaks, reps=2, host_sample=256):
     nbytes, b = C4_BYTES, len(idx)
     words = nbytes // 4
     free_b, _ = dev.mem_info()
@@ -226,6 +230,12 @@ def c4_device(dev, L, idx, dist, peaks, reps=2, host_sample=32):
         ok &= digests[j] == hashlib.sha256(np.random.default_rng(3000 + idx[j]).bytes(nbytes)).digest()
     # host-resident: the same bytes start in host memory, the H2D copy is inside the timed call
     hs = min(host_sample, b)
+    try:
+        import psutil
+
+        hs = max(1, min(hs, int(psutil.virtual_memory().available * 0.4) // nbytes))
+    except Exception:
+        hs = min(hs, 64)
     host = [dev.download(P[j], nbytes, np.uint8) for j in range(hs)]
     t0 = time.perf_counter()
     hd = dev.sha256_host(host)
@@ -264,10 +274,12 @@ def c5_device(dev, L, idx, dist, peaks, reps=2):
     Cs = [dev.alloc(n * 8) for _ in idx]
     T = _Timer(dev)
     am = None
+    sv = [_gen_state(4000 + i) for i in idx]
+    sk = [_gen_state(5000 + i) + (0, 2**31) for i in idx]
     for r in range(reps + 1):
         T.begin()
-        dev.rand_pcg64(L.PCG_F32, V, [n] * b, [_gen_state(4000 + i) for i in idx])
-        rej = dev.rand_pcg64(L.PCG_BOUNDED32_I64, K, [n] * b, [_gen_state(5000 + i) + (0, 2**31) for i in idx])
+        dev.rand_pcg64(L.PCG_F32, V, [n] * b, sv)
+        rej = dev.rand_pcg64(L.PCG_BOUNDED32_I64, K, [n] * b, sk)
         T.end("gen" if r else "warm")
         assert not rej.any()
         T.begin()

@@ -553,3 +553,45 @@ def test_generator_creation_load_save_through_the_executor(executor):
     assert r.files["/workspace/out.npy"] == hashlib.sha256(out_npy).hexdigest()
     kinds = names(fake_device.calls)
     assert kinds.count("rand_pcg") == 3 and "fill" in kinds and "reduce_fused" in kinds and "cumsum" in kinds
+
+
+PANDAS_SCIPY_SCRIPT = '''
+import numpy as np
+import pandas as pd
+from scipy.stats import ttest_ind
+import scipy.stats as st
+rng = np.random.default_rng(42)
+control = rng.random(300_000) * 2 + 10
+experimental = rng.random(300_000) * 2 + 10.01
+s = pd.Series(control)
+print(type(control).__name__, type(s).__name__, isinstance(s, pd.Series), isinstance(pd.Series([1.0]), pd.Series))
+print(repr(s.mean()), repr(pd.Series(experimental).mean()), repr(s.std()), repr(pd.Series(experimental).std()))
+t, p = ttest_ind(control, experimental)
+print(repr(float(t)), repr(float(p)), repr(float(st.ttest_ind(control, experimental, equal_var=False).statistic)))
+print(repr(float(s.median())))
+'''
+
+
+def test_pandas_and_scipy_entry_points_run_as_device_reductions(executor):
+    """examples/using_imports.py:25-36 at a size where it matters: pd.Series(x).mean()/.std() and scipy's
+    ttest_ind on device arrays run as fused reductions (no host copy), equal to pandas / scipy on the host
+    within float64 summation-order tolerance; anything else (median) is pandas itself."""
+    import pandas as pd
+    import scipy.stats as st
+
+    fake_device.calls.clear()
+    r = asyncio.run(executor.execute(PANDAS_SCIPY_SCRIPT, env={"BCI_DEBUG_FALLBACK": "1"}))
+    assert r.exit_code == 0 and r.stderr == "", r.stderr
+    rng = np.random.default_rng(42)
+    a, b = rng.random(300_000) * 2 + 10, rng.random(300_000) * 2 + 10.01
+    lines = r.stdout.splitlines()
+    assert lines[0] == "DeviceArray DeviceSeries True True"
+    got = [float(t) for t in lines[1].split()]
+    want = [pd.Series(a).mean(), pd.Series(b).mean(), pd.Series(a).std(), pd.Series(b).std()]
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    t, p = st.ttest_ind(a, b)
+    got = [float(x) for x in lines[2].split()]
+    assert np.allclose(got, [t, p, st.ttest_ind(a, b, equal_var=False).statistic], rtol=1e-9, atol=0)
+    assert float(lines[3]) == float(pd.Series(a).median())
+    kinds = names(fake_device.calls)
+    assert kinds.count("rand_pcg") == 2 and "reduce_fused" in kinds
