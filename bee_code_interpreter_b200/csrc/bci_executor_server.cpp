@@ -592,6 +592,7 @@ bool run_via_exec(const std::string& source, const std::map<std::string, std::st
     usleep((useconds_t)nap_us);
     if (nap_us < 5000) nap_us *= 2;
   }
+  kill(-pid, SIGKILL);   // whatever the script left running goes with the request (the reference deletes the pod)
   oc.out = read_file(out_path); oc.err = read_file(err_path);
   oc.exit_code = WIFEXITED(status) ? WEXITSTATUS(status) : -1;
   return true;

@@ -247,7 +247,7 @@ sha256_thread_kernel(const ShaMsg* __restrict__ msgs, int B, uint32_t* __restric
 // the op stream by an event) and the library lock is released while the digests are awaited; launches of
 // different callers overlap on the GPU.
 namespace {
-constexpr int kShaStreams = 16;
+constexpr int kShaStreams = 64;
 struct ShaLane {
   cudaStream_t stream = nullptr;
   cudaEvent_t order = nullptr, done = nullptr;

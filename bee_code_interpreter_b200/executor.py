@@ -131,18 +131,18 @@ class LocalGpuExecutor:
         async with self._sem:  # admission: at most `max_inflight` requests resident on the GPU
             # one directory per request on tmpfs when there is one: ~12 metadata operations per
             # request at thousands of requests/s is what a journalled /tmp serialises on
-            base = Path(tempfile.mkdtemp(prefix="bci-req-", dir=_SCRATCH_DIR))
-            workspace, capture = base / "workspace", base
-            workspace.mkdir()
+            base = tempfile.mkdtemp(prefix="bci-req-", dir=_SCRATCH_DIR)
+            workspace = Path(base, "workspace")
+            os.mkdir(workspace)
             try:
                 for file_path, object_id in files.items():
                     target = _workspace_target(workspace, file_path)
                     target.parent.mkdir(parents=True, exist_ok=True)
                     target.write_bytes(await self.file_storage.read(object_id))
                 start_ns = time.time_ns()
-                before = _snapshot(workspace)
+                before = _snapshot(workspace) if files else {}
                 stdout, stderr, exit_code = await loop.run_in_executor(
-                    self._pool, self._run_process, source_code, str(workspace), dict(env), capture)
+                    self._pool, self._run_process, source_code, str(workspace), dict(env), Path(base))
                 stored = {}
                 names = _changed_files(workspace, start_ns, before)
                 if names:
@@ -150,7 +150,7 @@ class LocalGpuExecutor:
                     stored = {WORKSPACE_PREFIX + n: i for n, i in zip(names, ids)}
                 return Result(stdout=stdout, stderr=stderr, exit_code=exit_code, files=stored)
             finally:
-                shutil.rmtree(base, ignore_errors=True)
+                _remove_request_dir(base, str(workspace))
 
     def close(self) -> None:
         self._pool.shutdown(wait=False, cancel_futures=True)
@@ -201,6 +201,25 @@ class LocalGpuExecutor:
             os.close(err_fd)
 
 
+def _remove_request_dir(base: str, workspace: str) -> None:
+    """The common case by hand (a flat workspace + the script file): a generic tree walk costs several times the
+    syscalls and this runs on the service's event-loop thread for every request."""
+    try:
+        with os.scandir(workspace) as it:
+            for entry in it:
+                if entry.is_dir(follow_symlinks=False):
+                    raise OSError("nested")
+                os.unlink(entry.path)
+        os.rmdir(workspace)
+        try:
+            os.unlink(os.path.join(base, "script.py"))
+        except FileNotFoundError:
+            pass
+        os.rmdir(base)
+    except OSError:
+        shutil.rmtree(base, ignore_errors=True)
+
+
 def _capture_fd(name: str) -> int:
     try:
         return os.memfd_create("bci-" + name, os.MFD_CLOEXEC)
@@ -241,8 +260,8 @@ def _snapshot(workspace: Path) -> dict:
     """Top-level regular files with what a change cannot leave untouched."""
     snap = {}
     for entry in os.scandir(workspace):
-        if entry.is_file(follow_symlinks=False):    # DirEntry::metadata() does not follow links either (server.rs:103-106)
-            st = entry.stat(follow_symlinks=False)
+        if entry.is_file():                         # Path::is_file follows links (server.rs:103) ...
+            st = entry.stat(follow_symlinks=False)   # ... DirEntry::metadata does not (server.rs:106)
             snap[entry.name] = (st.st_ino, st.st_size, st.st_mtime_ns, st.st_ctime_ns)
     return snap
 
@@ -254,7 +273,7 @@ def _changed_files(workspace: Path, since_ns: int, before: dict | None = None) -
     `since_ns`.  Hence also: anything new or different from the snapshot taken at the start."""
     out = []
     for entry in os.scandir(workspace):
-        if not entry.is_file(follow_symlinks=False):   # a symlink is not a regular file: never stored
+        if not entry.is_file():       # like the reference, a link to a regular file counts (its CONTENT is stored, never the link)
             continue
         st = entry.stat(follow_symlinks=False)
         if st.st_ctime_ns > since_ns or (before is not None and

@@ -124,6 +124,10 @@ def _build_view():
         _state["seeded"] = True  # from here on the legacy stream is deterministic: numpy owns it
         return real_random.seed(*a, **kw)
 
+    def set_state(*a, **kw):
+        _state["seeded"] = True  # a restored state is as deterministic as a seed
+        return real_random.set_state(*a, **kw)
+
     def _device_normal(shape, loc, scale, fallback):
         # unseeded only: the seeded legacy normal is MT19937 + polar rejection, numpy keeps that stream
         try:
@@ -233,7 +237,7 @@ def _build_view():
         return g if isinstance(g, DeviceGenerator) else DeviceGenerator(g.bit_generator)
 
     random_view = _ModuleView(real_random, {"default_rng": default_rng, "Generator": DeviceGenerator, "rand": rand, "random": random_sample, "random_sample": random_sample,
-                                            "ranf": random_sample, "sample": random_sample, "seed": seed,
+                                            "ranf": random_sample, "sample": random_sample, "seed": seed, "set_state": set_state,
                                             "randn": randn, "standard_normal": standard_normal, "normal": normal})
 
     def _offloading(device_fn, real_fn, n_arrays):

@@ -235,14 +235,17 @@ class ContentAddressedStorage:
         lies, then moved into the store (copy across filesystems).  Not in the reference's
         Storage; the streaming `writer()` above is the protocol-compatible path.
 
-        Only regular files get in: the source is opened with O_NOFOLLOW and the bytes that were
-        hashed are the bytes of that descriptor, so a symlink a script planted can neither enter
-        the store nor redirect the id to another file.  Dedupe is a hard link with O_EXCL semantics
-        (`os.link` fails if the id exists), so two writers of the same content cannot race."""
+        Only regular-file CONTENT gets in: the bytes that are hashed and the bytes that are stored are
+        those of one open descriptor.  A symlink (the reference lists links to regular files as changed
+        files, server.rs:103, and downloads what they point to) is read through, its bytes are COPIED,
+        and the link itself never reaches the store, so it can neither dangle there nor redirect an id
+        to a file that changes later.  Dedupe is a hard link with O_EXCL semantics (`os.link` fails if
+        the id exists), so two writers of the same content cannot race."""
         import shutil
         import stat as stat_mod
 
-        fd = await asyncio.to_thread(os.open, str(path), os.O_RDONLY | os.O_NOFOLLOW | os.O_CLOEXEC)
+        is_link = os.path.islink(str(path))
+        fd = await asyncio.to_thread(os.open, str(path), os.O_RDONLY | os.O_CLOEXEC | (0 if is_link else os.O_NOFOLLOW))
         try:
             st = os.fstat(fd)
             if not stat_mod.S_ISREG(st.st_mode):
@@ -255,6 +258,8 @@ class ContentAddressedStorage:
 
                 def place():
                     try:
+                        if is_link:
+                            raise OSError("links are copied, never moved")
                         os.rename(str(path), tmp)                       # same filesystem: the inode we hashed
                         if os.stat(tmp, follow_symlinks=False).st_ino != st.st_ino:
                             raise OSError("source changed under the store")

@@ -32,6 +32,10 @@ import subprocess
 import sys
 import tempfile
 
+_ENV_ALLOW = {"PATH", "HOME", "USER", "LOGNAME", "SHELL", "LANG", "LANGUAGE", "TZ", "TMPDIR", "TERM", "PWD", "VIRTUAL_ENV",
+              "LD_LIBRARY_PATH", "PYTHONPATH", "PYTHONHOME", "PYTHONHASHSEED", "PYTHONIOENCODING", "PYTHONUNBUFFERED",
+              "PYTHONDONTWRITEBYTECODE", "MPLBACKEND", "MPLCONFIGDIR", "XDG_CACHE_HOME", "XDG_CONFIG_HOME"}
+_ENV_ALLOW_PREFIXES = ("LC_", "BCI_", "OMP_", "OPENBLAS_", "MKL_", "NUMEXPR_")
 POOL_ENV = "BCI_ZYGOTE_POOL"      # children forked ahead of requests (0 = fork on arrival)
 MAX_REQUEST = 64 << 20
 
@@ -233,7 +237,10 @@ class ZygoteClient:
         self._start()
 
     def _start(self) -> None:
-        env = dict(os.environ)
+        # the scripts inherit the zygote's environment: start it from an allow-list, not from the service's
+        # own environment (tokens, cloud credentials ... have no business in agent code; a pod of the
+        # reference only sees the executor image's environment plus the request's `env`)
+        env = {k: v for k, v in os.environ.items() if k in _ENV_ALLOW or k.startswith(_ENV_ALLOW_PREFIXES)}
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         env["PYTHONPATH"] = root + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
         # no BLAS/OpenMP worker threads in the zygote: fork() must copy a single-threaded

@@ -135,3 +135,33 @@ def test_dead_zygote_and_dead_broker_are_restarted_and_the_request_retried(built
         assert r.exit_code == 0 and r.stdout == "DeviceArray True\n" and broker.restarts == 1
     finally:
         ex.close()
+
+
+def test_symlinks_in_the_workspace_are_stored_by_content_never_as_links(built, tmp_path):
+    """`latest.csv -> data.csv` must not put a (dangling) link into the content-addressed store.
+    The reference reports links to regular files as changed files (Path::is_file follows them, server.rs:103)
+    and stores what they point to; so do we — as a copy of the bytes that were hashed."""
+    import asyncio
+    import hashlib
+    import os
+    import sys
+    from pathlib import Path
+
+    from bee_code_interpreter_b200.executor import LocalGpuExecutor
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import fake_device
+
+    ex = LocalGpuExecutor(device_module=fake_device, max_inflight=2, timeout=20, zygotes=1, storage_path=str(tmp_path / "store"))
+    try:
+        src = ("import os\nopen('data.csv', 'w').write('a,b\\n1,2\\n')\nos.symlink('data.csv', 'latest.csv')\n"
+               "os.symlink('/nonexistent/target', 'dangling')\nos.mkdir('sub')\n")
+        r = asyncio.run(ex.execute(src))
+        assert r.exit_code == 0, r.stderr
+        assert set(r.files) == {"/workspace/data.csv", "/workspace/latest.csv"}
+        digest = hashlib.sha256(b"a,b\n1,2\n").hexdigest()
+        assert r.files["/workspace/data.csv"] == r.files["/workspace/latest.csv"] == digest
+        stored = list((tmp_path / "store").iterdir())
+        assert [p.name for p in stored] == [digest] and not stored[0].is_symlink() and stored[0].read_bytes() == b"a,b\n1,2\n"
+    finally:
+        ex.close()

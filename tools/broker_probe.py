@@ -13,6 +13,9 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 
+RECONNECT = "--reconnect" in sys.argv
+
+
 def client(sock, threads, per_thread, n, start, out):
     import numpy as np
     from bee_code_interpreter_b200 import numpy_proxy as P
@@ -24,6 +27,9 @@ def client(sock, threads, per_thread, n, start, out):
         be = RemoteBackend(sock)
         for i in range(per_thread):
             t = time.perf_counter()
+            if RECONNECT:            # like a script process: one connection per request
+                be.close()
+                be = RemoteBackend(sock)
             x = P.device_rand(be, (n,), seed=i)
             float(np.sum(np.square(x)))
             del x
@@ -43,7 +49,7 @@ def client(sock, threads, per_thread, n, start, out):
 def main():
     from bee_code_interpreter_b200.broker import BrokerProcess
 
-    configs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(4, 4), (4, 8), (4, 16), (4, 32), (8, 16), (16, 8)]
+    configs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:] if not a.startswith("--")] or [(4, 4), (4, 8), (4, 16), (4, 32), (8, 16), (16, 8)]
     n = 10**8
     broker = BrokerProcess(device=0)
     ctx = mp.get_context("spawn")

@@ -146,6 +146,35 @@ def main():
     add("reduce sum(square) f64 fused (K1+K2)", f"C1 n=1e8 x{B1}", 24 * n1 * B1,
         timed(k_reduce(L.RED_SUM, np.float64, bufs, ns, pre=L.PRE_SQUARE), flush=False), moved_bytes=8 * n1 * B1)
     add("ewise add f64 (K1)", f"n=1e8 x{B1}", 24 * n1 * B1, timed(k_ewise(L.EW_ADD, np.float64, bufs, outs, None, outs, ns), flush=False))
+    # ---- round 2: generator fused into the reduction, PCG64 Generator streams, creation, casts
+    seeds = (C.c_uint64 * B1)(*range(B1))
+    raw = np.zeros(B1, dtype=np.uint64)
+    nn = L.size_array(ns)
+    ms = timed(lambda: L.check(lib.bci_reduce_rand_f64(L.RED_SUM, L.PRE_SQUARE, B1, nn, seeds, C.c_void_p(raw.ctypes.data))), flush=False)
+    add("reduce sum(square(rand)) f64 fused (K1+K2+K8)", f"C1 n=1e8 x{B1}", 32 * n1 * B1, ms, moved_bytes=0,
+        extra={"bound": "fma pipe (Philox4x32-10: 10 IMAD.WIDE per float64), no HBM traffic", "requests_per_s": B1 / (ms / 1e3),
+               "imad_wide_lane_ops_per_s": 10.0 * n1 * B1 / (ms / 1e3)})
+    st = np.random.PCG64(1).state["state"]
+    gens = (L.Pcg64Gen * B1)()
+    m64 = (1 << 64) - 1
+    for i in range(B1):
+        gens[i].state_lo, gens[i].state_hi = st["state"] & m64, st["state"] >> 64
+        gens[i].inc_lo, gens[i].inc_hi = st["inc"] & m64, st["inc"] >> 64
+        gens[i].low, gens[i].range = 0, 2**31
+    o_ = L.ptr_array(bufs)
+    rej = (C.c_uint32 * B1)()
+    n32 = L.size_array([2 * n1] * B1)
+    add("pcg64 random f64 (K8d)", f"n=1e8 x{B1}", 8 * n1 * B1, timed(lambda: L.check(lib.bci_rand_pcg64(L.PCG_F64, B1, o_, nn, gens, None)), flush=False))
+    add("pcg64 random f32 (K8d)", f"n=2e8 x{B1}", 8 * n1 * B1, timed(lambda: L.check(lib.bci_rand_pcg64(L.PCG_F32, B1, o_, n32, gens, None)), flush=False))
+    add("pcg64 integers(0, 2^31) int64 (K8d)", f"n=1e8 x{B1}", 8 * n1 * B1,
+        timed(lambda: L.check(lib.bci_rand_pcg64(L.PCG_BOUNDED32_I64, B1, o_, nn, gens, rej)), flush=False))
+    sa = dev._scalars([0.5] * B1, L.F64, B1)
+    sb = dev._scalars([0.25] * B1, L.F64, B1)
+    add("fill arange f64", f"n=1e8 x{B1}", 8 * n1 * B1, timed(lambda: L.check(lib.bci_fill(L.FILL_ARANGE, L.F64, B1, o_, nn, sa, sb, None)), flush=False))
+    add("fill const f64", f"n=1e8 x{B1}", 8 * n1 * B1, timed(lambda: L.check(lib.bci_fill(L.FILL_CONST, L.F64, B1, o_, nn, sa, None, None)), flush=False))
+    oo = L.ptr_array(outs)
+    add("cast f64 -> f32", f"n=1e8 x{B1}", 12 * n1 * B1, timed(lambda: L.check(lib.bci_cast(L.F64, L.F32, B1, o_, oo, nn)), flush=False))
+    add("cast i64 -> f64", f"n=1e8 x{B1}", 16 * n1 * B1, timed(lambda: L.check(lib.bci_cast(L.I64, L.F64, B1, o_, oo, nn)), flush=False))
     for p in bufs + outs:
         dev.free(p)
 
