@@ -158,3 +158,30 @@ def test_descriptor_transfers_round_trip(dev, tmp_path):
         dev.h2d_fd(p, fd, 0, 1 << 30)      # the file ends first: an error, not a fault
     os.close(fd)
     dev.free(p)
+
+
+def test_c2_matmul_on_the_configs_own_inputs(dev):
+    """BASELINE C2 names its inputs: A, B = default_rng(1000 + i).random((4096, 4096), float32).  Generated ON the
+    device (bit-exact with numpy, asserted), multiplied by the tcgen05 kernel, compared with numpy's own sgemm on
+    the whole matrix (bar 1e-5 of max|C|) and with a float64 product on sampled rows (bar 2e-6)."""
+    m = 4096
+    n = m * m
+    for i in (0, 3):
+        rng = np.random.default_rng(1000 + i)
+        a_h, b_h = rng.random((m, m), dtype=np.float32), rng.random((m, m), dtype=np.float32)
+        st = np.random.PCG64(1000 + i)
+        s0 = st.state["state"]
+        st.advance(n // 2)
+        s1 = st.state["state"]
+        A, B, C = dev.alloc(n * 4), dev.alloc(n * 4), dev.alloc(n * 4)
+        dev.rand_pcg64(L.PCG_F32, [A, B], [n, n], [(s0["state"], s0["inc"]), (s1["state"], s1["inc"])])
+        assert np.array_equal(dev.download(A, n, np.float32), a_h.ravel()) and np.array_equal(dev.download(B, n, np.float32), b_h.ravel())
+        dev.matmul_f32([A], [B], [C], m, m, m)
+        c = dev.download(C, n, np.float32).reshape(m, m)
+        ref32 = a_h @ b_h
+        assert np.abs(c - ref32).max() <= 1e-5 * np.abs(ref32).max()
+        rows = [0, 17, m // 2, m - 1]
+        ref64 = a_h[rows].astype(np.float64) @ b_h.astype(np.float64)
+        assert np.abs(c[rows] - ref64).max() <= 2e-6 * np.abs(ref64).max()
+        for p in (A, B, C):
+            dev.free(p)

@@ -595,3 +595,96 @@ def test_pandas_and_scipy_entry_points_run_as_device_reductions(executor):
     assert float(lines[3]) == float(pd.Series(a).median())
     kinds = names(fake_device.calls)
     assert kinds.count("rand_pcg") == 2 and "reduce_fused" in kinds
+
+
+# ---- creation functions and Generator draws through the view: host-side parameter derivation vs numpy -------------
+def _view_with_fake(min_elems=64):
+    from bee_code_interpreter_b200 import numpy_hook as H
+
+    H._state["view"] = None
+    H._state["backend"] = None
+    H.install(backend_factory=lambda: LocalBackend(fake_device), min_rand_elems=min_elems)
+    return H.numpy_view()
+
+
+def test_arange_linspace_full_match_numpy_for_random_parameters(be, monkeypatch):
+    from hypothesis import given, settings, strategies as st
+
+    monkeypatch.setattr(P, "OFFLOAD_MIN_ELEMS", 64)
+    vnp = _view_with_fake()
+    finite = st.floats(-1e6, 1e6, allow_nan=False, allow_infinity=False)
+
+    @settings(max_examples=150, deadline=None)
+    @given(start=finite, span=st.floats(1.0, 5e3), step=st.floats(1e-3, 7.0), neg=st.booleans(),
+           dt=st.sampled_from([None, np.float32, np.float64]))
+    def floats(start, span, step, neg, dt):
+        stop = start + span
+        args = (stop, start, -step) if neg else (start, stop, step)
+        kw = {} if dt is None else {"dtype": dt}
+        want = np.arange(*args, **kw)
+        got = vnp.arange(*args, **kw)
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert np.array_equal(np.asarray(got), want)
+
+    @settings(max_examples=100, deadline=None)
+    @given(start=st.integers(-10**6, 10**6), n=st.integers(1, 5000), step=st.integers(1, 9), dt=st.sampled_from([None, np.int32, np.int64, np.float32]))
+    def ints(start, n, step, dt):
+        kw = {} if dt is None else {"dtype": dt}
+        want = np.arange(start, start + n * step, step, **kw)
+        got = vnp.arange(start, start + n * step, step, **kw)
+        assert got.dtype == want.dtype and np.array_equal(np.asarray(got), want)
+
+    @settings(max_examples=100, deadline=None)
+    @given(start=finite, stop=finite, num=st.integers(2, 4000), endpoint=st.booleans())
+    def lin(start, stop, num, endpoint):
+        want = np.linspace(start, stop, num, endpoint=endpoint)
+        got = vnp.linspace(start, stop, num, endpoint=endpoint)
+        assert np.array_equal(np.asarray(got), want)
+
+    floats(); ints(); lin()
+    for shape, val, dt in [((100,), 2.5, None), ((8, 16), 7, np.int32), (300, -1.0, np.float32), ((70,), 3, None)]:
+        kw = {} if dt is None else {"dtype": dt}
+        got, want = vnp.full(shape, val, **kw), np.full(shape, val, **kw)
+        assert type(got) is P.DeviceArray and got.dtype == want.dtype and got.shape == want.shape and np.array_equal(np.asarray(got), want)
+    assert type(vnp.zeros(10)) is np.ndarray and type(vnp.arange(5)) is np.ndarray          # small: numpy itself
+
+
+def test_generator_draws_track_numpys_stream_for_random_call_sequences(be):
+    """Any interleaving of device-sized and scalar draws leaves the Generator exactly where numpy's would be
+    (values and bit-generator state, including the buffered 32-bit word)."""
+    from hypothesis import given, settings, strategies as st
+
+    vnp = _view_with_fake(min_elems=32)
+    call = st.one_of(
+        st.tuples(st.just("random64"), st.integers(1, 300)), st.tuples(st.just("random32"), st.integers(1, 301)),
+        st.tuples(st.just("integers"), st.integers(1, 300), st.integers(-50, 50), st.sampled_from([2, 3, 100, 2**16, 2**31, 2**32 - 1])),
+        st.tuples(st.just("int32"), st.integers(1, 300)), st.tuples(st.just("uniform"), st.integers(1, 300)),
+        st.tuples(st.just("normal"), st.integers(1, 5)), st.tuples(st.just("scalar")), st.tuples(st.just("bytes"), st.integers(1, 50)))
+
+    @settings(max_examples=120, deadline=None)
+    @given(seed=st.integers(0, 2**32), calls=st.lists(call, min_size=1, max_size=8))
+    def run(seed, calls):
+        g, r = vnp.random.default_rng(seed), np.random.default_rng(seed)
+        assert isinstance(g, np.random.Generator)
+        for c in calls:
+            if c[0] == "random64":
+                a, b = g.random(c[1]), r.random(c[1])
+            elif c[0] == "random32":
+                a, b = g.random(c[1], dtype=np.float32), r.random(c[1], dtype=np.float32)
+            elif c[0] == "integers":
+                a, b = g.integers(c[2], c[2] + c[3], c[1]), r.integers(c[2], c[2] + c[3], c[1])
+            elif c[0] == "int32":
+                a, b = g.integers(0, 1000, c[1], dtype=np.int32), r.integers(0, 1000, c[1], dtype=np.int32)
+            elif c[0] == "uniform":
+                a, b = g.uniform(-2.0, 3.5, c[1]), r.uniform(-2.0, 3.5, c[1])
+            elif c[0] == "normal":
+                a, b = g.standard_normal(c[1]), r.standard_normal(c[1])
+            elif c[0] == "bytes":
+                a, b = np.frombuffer(g.bytes(c[1]), np.uint8), np.frombuffer(r.bytes(c[1]), np.uint8)
+            else:
+                a, b = np.array(g.random()), np.array(r.random())
+            a = np.asarray(a)
+            assert a.dtype == b.dtype and np.array_equal(a, b), c
+            assert g.bit_generator.state == r.bit_generator.state, c
+
+    run()
