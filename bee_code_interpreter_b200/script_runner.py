@@ -67,6 +67,9 @@ def run_in_child(req: dict, stdout_fd: int | None = None, stderr_fd: int | None 
     sys.argv = [script]
     numpy_hook.reset_request_state()
     numpy_hook.install(min_rand_elems=req.get("min_rand_elems"))
+    import gc
+
+    gc.enable()      # the zygote runs with the collector off (its objects are frozen); the script gets a normal one
     code = 0
     try:
         compiled = compile(req["source_code"], script, "exec")

@@ -31,11 +31,14 @@ import struct
 import subprocess
 import sys
 import tempfile
+import time
 
 _ENV_ALLOW = {"PATH", "HOME", "USER", "LOGNAME", "SHELL", "LANG", "LANGUAGE", "TZ", "TMPDIR", "TERM", "PWD", "VIRTUAL_ENV",
               "LD_LIBRARY_PATH", "PYTHONPATH", "PYTHONHOME", "PYTHONHASHSEED", "PYTHONIOENCODING", "PYTHONUNBUFFERED",
               "PYTHONDONTWRITEBYTECODE", "MPLBACKEND", "MPLCONFIGDIR", "XDG_CACHE_HOME", "XDG_CONFIG_HOME"}
 _ENV_ALLOW_PREFIXES = ("LC_", "BCI_", "OMP_", "OPENBLAS_", "MKL_", "NUMEXPR_")
+_TRACE = bool(os.environ.get("BCI_TRACE"))
+_YIELD = bool(os.environ.get("BCI_ZYGOTE_YIELD"))
 POOL_ENV = "BCI_ZYGOTE_POOL"      # children forked ahead of requests (0 = fork on arrival)
 MAX_REQUEST = 64 << 20
 
@@ -68,11 +71,15 @@ def _serve_request(conn: socket.socket, payload: bytes, out_fds: list[int]) -> N
     try:
         # the CHILD announces its pid: if the parent did, a short script could finish and
         # write its exit code first, and the client would read the two words swapped
+        t_child = time.time() if _TRACE else 0.0
         os.setsid()   # own process group: a timeout (and the end of the request) reaps what the script spawned
         conn.sendall(struct.pack("<i", os.getpid()))
         req = json.loads(payload)
         if not isinstance(req, dict):
             raise ValueError("request is not an object")
+        if _TRACE:
+            tz = req.get("_t_zygote") or [0.0, 0.0]
+            conn.sendall(struct.pack("<3d", tz[0], tz[1], t_child))
         code = script_runner.run_in_child(req, out_fds[0] if len(out_fds) >= 2 else None,
                                           out_fds[1] if len(out_fds) >= 2 else None)
     finally:
@@ -125,8 +132,18 @@ def _spawn_idle(srv: socket.socket, idle: list) -> "_Idle | None":
 
 
 def serve(socket_path: str) -> None:
+    import gc
+
     from . import script_runner  # noqa: F401  imports numpy + proxy + hook once
 
+    # Everything imported so far lives as long as the zygote: move it to the permanent generation and stop
+    # collecting here.  Without this (measured, profiles/r2f_*): the cyclic collector's generation counters are
+    # inherited by every child, a few percent of the requests start with a FULL collection over ~10^5 module
+    # objects (30-60 ms, p99 of the request latency) — and each such pass dirties the pages it walks, i.e.
+    # copy-on-write faults on top.  Children re-enable the collector for the script's own objects.
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     signal.signal(signal.SIGCHLD, signal.SIG_IGN)
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
     try:
@@ -155,6 +172,7 @@ def serve(socket_path: str) -> None:
         except OSError:
             break
         fds: list[int] = []
+        t_accept = time.time() if _TRACE else 0.0
         try:
             conn.settimeout(30.0)
             head = _recv_exact(conn, 4, fds)
@@ -170,6 +188,9 @@ def serve(socket_path: str) -> None:
                 continue                    # only JSON objects are requests
             if length < 64 and json.loads(payload).get("op") == "shutdown":
                 break
+            if _TRACE and payload.endswith(b"}"):      # tools/e2e_cost.py: when did the zygote see this request
+                payload = payload[:-1] + (',"_t_zygote":[%r,%r]}' % (t_accept, time.time())).encode()
+                length = len(payload)
             conn.settimeout(None)
             handed = False
             while idle and not handed:
@@ -197,6 +218,8 @@ def serve(socket_path: str) -> None:
                     os.close(f)
                 except OSError:
                     pass
+        if _YIELD:
+            os.sched_yield()                # let the request's process run before this loop goes on forking
         while len(idle) < pool_size:        # the replacement is forked AFTER the hand-off
             ch = _spawn_idle(srv, idle)
             if ch is None:
@@ -234,6 +257,7 @@ class ZygoteClient:
         self.socket_path = os.path.join(self._dir, "zygote.sock")
         self._pool = pool
         self._proc = None
+        self.trace = [] if os.environ.get("BCI_TRACE") else None      # tools/e2e_cost.py: per-request phase times
         self._start()
 
     def _start(self) -> None:
@@ -273,6 +297,9 @@ class ZygoteClient:
         or None on timeout (the child is killed).  Raises ZygoteDied when no child could be had."""
         payload = json.dumps(req).encode()
         conn = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        trace = self.trace
+        t0 = time.perf_counter() if trace is not None else 0.0
+        t0_wall = time.time() if trace is not None else 0.0
         try:
             try:
                 conn.connect(self.socket_path)
@@ -284,12 +311,17 @@ class ZygoteClient:
             if len(head) < 4:
                 raise ZygoteDied("zygote closed the connection before a child took the request")
             (pid,) = struct.unpack("<i", head)
+            t1 = time.perf_counter() if trace is not None else 0.0
+            stamps = struct.unpack("<3d", _recv_exact(conn, 24)) if trace is not None else None
             conn.settimeout(timeout)
             try:
                 tail = _recv_exact(conn, 4)
             except socket.timeout:
                 _kill_group(pid)
                 return None
+            if trace is not None:
+                # (submit -> child announced itself, child -> exit code, wall stamps: submit, zygote accept, zygote hand-off, child start)
+                trace.append((t1 - t0, time.perf_counter() - t1, t0_wall) + stamps)
             _kill_group(pid)   # whatever the script left running goes with the request (the reference deletes the pod)
             if len(tail) < 4:
                 return -1

@@ -450,6 +450,7 @@ class E2EHarness:
                 # would make this number meaningless
                 "broker_jobs": jobs, "broker_launch_groups": after["batches"] - before["batches"],
                 "all_requests_on_gpu": jobs >= MIN_JOBS[workload] * done,
+                "host_cores": effective_cores()[0], "host_cores_note": effective_cores()[1],
                 "api": "LocalGpuExecutor.execute(source_code, files, env)"}
 
     def close(self):
@@ -476,9 +477,16 @@ def e2e_worker(args):
     from bee_code_interpreter_b200 import workloads as W
     import bench_configs as BC
 
+    import gc
+
     shared = types.SimpleNamespace(socket_path=args.broker_socket, close=lambda: None)
+    gc.collect()
+    gc.freeze()      # a service worker's module objects are permanent too: full collections cost tens of ms on the event loop
+    # throughput arm: children are forked on arrival (zygote_pool=0).  The pre-forked pool (the default, 4) halves the
+    # time to script start but costs ~8 % of the requests/s when the host CPU quota is the limit, which it is here
+    # (profiles/r2_e2e_host_cost.md)
     execu = LocalGpuExecutor(broker=shared, max_inflight=64, timeout=600, zygotes=args.e2e_zygotes or None,
-                             min_rand_elems=1000 if DRY else None)
+                             min_rand_elems=1000 if DRY else None, zygote_pool=0)
     print("ready", flush=True)
     while True:
         line = sys.stdin.readline()
@@ -554,8 +562,29 @@ def cpu_round(n: int, procs: int) -> tuple[float, list[float]]:
         return time.perf_counter() - t0, lat
 
 
+def effective_cores() -> tuple[int, str]:
+    """Host cores this process tree may actually use: the cgroup CPU quota when there is one (the boxes of this pool
+    show 128 logical CPUs but run the job under `cpu.max = 1600000 100000`, i.e. 16 CPUs — profiles/r2i_cgroup.log),
+    else the affinity mask."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    note = "%d logical CPUs visible" % n
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            q = max(1, int(round(int(quota) / int(period))))
+            if q < n:
+                note += ", cgroup cpu.max quota = %d CPUs" % q
+                n = q
+    except (OSError, ValueError):
+        pass
+    return n, note
+
+
 def cpu_procs(n: int) -> int:
-    cores = os.cpu_count() or 1
+    cores = effective_cores()[0]
     try:
         import psutil
 
@@ -579,7 +608,7 @@ def cpu_baseline(n: int, budget_s: float = 25.0) -> dict:
         rounds += 1
         if time.perf_counter() - t0 + w > budget_s:
             break
-    return {"value": done / wall, "unit": "requests/s", "cores": procs, "kind": "port",
+    return {"value": done / wall, "unit": "requests/s", "cores": procs, "cores_note": effective_cores()[1], "kind": "port",
             "p50_latency_s": statistics.median(lats),
             "sample": "%d rounds x %d concurrent literal benchmark-numpy.py requests (n=%d), python subprocess + stock numpy per request" % (rounds, procs, n)}
 
@@ -610,7 +639,7 @@ def run_reference(args) -> dict | None:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "benchmark-numpy.py (rand(%d) f64 -> square -> sum), reference CPU executor path" % n,
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "requests/s", "cores": procs, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "requests/s", "cores": procs, "cores_note": effective_cores()[1], "kind": "port", "sample": sample,
                          "p50_latency_s": statistics.median(lats)},
         "e2e": {"value": value, "unit": "requests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -241,7 +241,9 @@ def c4_device(dev, L, idx, dist, peaks, reps=2, host_sample=256):
     hd = dev.sha256_host(host)
     host_s = time.perf_counter() - t0
     ok &= hd == digests[:hs]
-    cores = os.cpu_count() or 1
+    from bench import effective_cores
+
+    cores = effective_cores()[0]
     lib = _hashlib_rate([h.data for h in host], min(cores, hs))
     for p in P:
         dev.free(p)
@@ -390,7 +392,9 @@ def cpu_baseline(name: str, budget_s: float = 12.0) -> dict:
 
     from oracle.cpu_executor import LocalCpuExecutor, RefStorage
 
-    cores = os.cpu_count() or 1
+    from bench import effective_cores
+
+    cores = effective_cores()[0]
     try:
         import psutil
 

@@ -51,18 +51,25 @@ def main():
                     cmd = [sys.executable, __file__, "--requests", str(args.requests), "--inflight", inflight, "--zygotes", str(args.zygotes),
                            "--n", str(args.n), "--broker-socket", broker.socket_path, "--scripts", name]
                     t0 = time.time()
-                    ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True) for _ in range(args.procs)]
+                    ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True, env=dict(os.environ, BCI_TRACE="1")) for _ in range(args.procs)]
                     outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in ps]
                     print(json.dumps({"procs": args.procs, "script": name, "inflight_per_proc": int(inflight),
                                       "sum_req_per_s": round(sum(o["req_per_s"] for o in outs), 1),
-                                      "latency_ms_p50": [o["latency_ms"]["p50"] for o in outs][:4],
+                                      "latency_ms_p50": [o["latency_ms"]["p50"] for o in outs][:4], "latency_ms_proc0": outs[0]["latency_ms"],
+                                      "wall_s": round(time.time() - t0, 2), "total_requests": args.requests * args.procs,
                                       "start_body_end_ms": [(o["submit_to_script_start_ms_p50"], o["script_body_ms_p50"], o["script_end_to_result_ms_p50"]) for o in outs][:2],
-                                      "service_cpu_ms": outs[0]["service_cpu_ms_per_request"], "child_cpu_ms": outs[0]["child_cpu_ms"]}), flush=True)
+                                      "service_cpu_ms": outs[0]["service_cpu_ms_per_request"], "child_cpu_ms": outs[0]["child_cpu_ms"],
+                                      "zygote_phase_ms_mean": outs[0].get("zygote_phase_ms_mean")}), flush=True)
         finally:
             broker.close()
         return
     if args.broker_socket:
+        import gc
         import types
+
+        if not os.environ.get("BCI_NO_FREEZE"):
+            gc.collect()
+            gc.freeze()
 
         ex = LocalGpuExecutor(broker=types.SimpleNamespace(socket_path=args.broker_socket, close=lambda: None),
                               max_inflight=64, timeout=300, zygotes=args.zygotes)
@@ -106,6 +113,18 @@ def main():
                     "child_minor_faults": round(statistics.mean(r[6] for r in rows)),
                     "child_ctx_switches": {"voluntary": round(statistics.mean(r[7] for r in rows), 1), "involuntary": round(statistics.mean(r[8] for r in rows), 1)},
                     "service_cpu_ms_per_request": {"user": ms((s1.ru_utime - s0.ru_utime) / args.requests), "sys": ms((s1.ru_stime - s0.ru_stime) / args.requests)},
+                    "zygote_phase_ms_mean": (lambda tr: {"submit_to_child_pid": ms(statistics.mean(t[0] for t in tr)), "child_pid_to_exit": ms(statistics.mean(t[1] for t in tr)),
+                                                         "p99_submit_to_child_pid": ms(sorted(t[0] for t in tr)[int(len(tr) * 0.99)]),
+                                                         # of the SLOW requests (submit -> pid over 15 ms): where did the time go
+                                                         "slow": (lambda sl: {"count": len(sl), "submit_to_zygote_accept": ms(statistics.mean(t[3] - t[2] for t in sl)),
+                                                                              "zygote_accept_to_handoff": ms(statistics.mean(t[4] - t[3] for t in sl)),
+                                                                              "handoff_to_child_running": ms(statistics.mean(t[5] - t[4] for t in sl))} if sl else None)(
+                                                             [t for t in tr if len(t) >= 6 and t[0] > 0.015]),
+                                                         "fast": (lambda sl: {"count": len(sl), "submit_to_zygote_accept": ms(statistics.mean(t[3] - t[2] for t in sl)),
+                                                                              "zygote_accept_to_handoff": ms(statistics.mean(t[4] - t[3] for t in sl)),
+                                                                              "handoff_to_child_running": ms(statistics.mean(t[5] - t[4] for t in sl))} if sl else None)(
+                                                             [t for t in tr if len(t) >= 6 and t[0] <= 0.015])} if tr else None)(
+                        [t for z in ex._zygotes if z.trace for t in z.trace[-args.requests:]]),
                 }), flush=True)
     finally:
         ex.close()
