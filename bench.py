@@ -33,6 +33,7 @@ sys.path.insert(0, str(ROOT))
 
 PER_GPU_BATCH = 1024
 DRY = bool(os.environ.get("BCI_BENCH_DRY"))
+TDEV = "cpu" if DRY else "cuda"        # where the few scalars that cross ranks live (all_reduce of times)
 METRIC = "requests/sec on benchmark-numpy.py at batch=1024 per GPU"
 
 
@@ -172,8 +173,11 @@ def run_ours(args) -> dict | None:
         import torch
         import torch.distributed as dist_mod
 
-        torch.cuda.set_device(local)
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if DRY:      # control flow of the multi-rank arm on CPU (tests/test_bench_contract.py): gloo, no CUDA
+            dist_mod.init_process_group("gloo")
+        else:
+            torch.cuda.set_device(local)
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
     dev.init(local)
     n = args.n
@@ -185,7 +189,8 @@ def run_ours(args) -> dict | None:
         if dist is not None:
             import torch
 
-            torch.cuda.synchronize()
+            if not DRY:
+                torch.cuda.synchronize()
             dist.barrier()
 
     seed_base = 0x5EED0000 + rank * 10_000_019
@@ -218,7 +223,7 @@ def run_ours(args) -> dict | None:
     if dist is not None:
         import torch
 
-        t = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([step_ms], device=TDEV, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         step_ms = float(t.item())
     value = requests * world / (step_ms / 1e3)
@@ -234,21 +239,24 @@ def run_ours(args) -> dict | None:
     # strong scaling datum (north star: "batch 1024 on 8 x B200"): the SAME global batch of 1024 split over the ranks
     strong = None
     if world > 1:
-        share = max(1, PER_GPU_BATCH // world)
-        c1_step(dev, L, n, share, min(wave, share), seed_base + 7_000_000, None)
-        barrier()
-        dev.timer_begin()
-        for s_ in range(args.steps):
-            c1_step(dev, L, n, share, min(wave, share), seed_base + 8_000_000 + s_ * share, None)
-        s_ms = dev.timer_end() / args.steps
-        t = torch.tensor([s_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        strong = {"global_batch": share * world, "per_gpu_batch": share, "ms_per_step": float(t.item()),
-                  "value": share * world / (float(t.item()) / 1e3), "unit": "requests/s", "scaling": "strong"}
+        try:
+            share = max(1, PER_GPU_BATCH // world)
+            c1_step(dev, L, n, share, min(wave, share), seed_base + 7_000_000, None)
+            barrier()
+            dev.timer_begin()
+            for s_ in range(args.steps):
+                c1_step(dev, L, n, share, min(wave, share), seed_base + 8_000_000 + s_ * share, None)
+            s_ms = dev.timer_end() / args.steps
+            t = torch.tensor([s_ms], device=TDEV, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            strong = {"global_batch": share * world, "per_gpu_batch": share, "ms_per_step": float(t.item()),
+                      "value": share * world / (float(t.item()) / 1e3), "unit": "requests/s", "scaling": "strong"}
+        except Exception as e:      # an extra datum must never cost the bench line
+            strong = {"error": repr(e)}
 
     # hardware evidence of the split-operand collectives: only when >= 2 GPUs are here
     split_parity = None
-    if world > 1 and not args.no_split_check:
+    if world > 1 and not args.no_split_check and not DRY:
         try:
             from bee_code_interpreter_b200 import split_check
 
@@ -435,7 +443,7 @@ class E2EHarness:
         if dist is not None:
             import torch
 
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            t = torch.tensor([dt], device=TDEV, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         lat = sorted(x for o in outs for x in o["latencies"])

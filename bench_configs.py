@@ -88,8 +88,9 @@ def _agg(dist, seconds: float, units: int) -> tuple[float, int]:
         return seconds, units
     import torch
 
-    t = torch.tensor([seconds], device="cuda", dtype=torch.float64)
-    u = torch.tensor([units], device="cuda", dtype=torch.float64)
+    dev_ = "cpu" if os.environ.get("BCI_BENCH_DRY") else "cuda"
+    t = torch.tensor([seconds], device=dev_, dtype=torch.float64)
+    u = torch.tensor([units], device=dev_, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(t.item()), int(u.item())

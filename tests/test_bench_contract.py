@@ -67,3 +67,27 @@ def test_our_arm_control_flow_on_the_cpu_test_double(built):
         assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(c["roofline"])
         assert c["e2e"]["value"] > 0 and c["e2e"]["parity"], (name, c["e2e"])
         assert c["cpu_baseline"]["value"] > 0 and c["cpu_baseline"]["kind"] == "port"
+
+
+def test_our_arm_under_torchrun_on_the_cpu_test_double(built):
+    """The multi-rank control flow of bench.py (round-robin sharding, max-over-ranks timing, strong-scaling datum,
+    per-rank e2e harness, configs block) with gloo and the test double: rank 0 alone prints the line."""
+    import os
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, BCI_BENCH_DRY="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(ROOT / "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "1",
+                        "--array-elems", "20000", "--requests", "8", "--wave", "4", "--e2e-requests", "8", "--cpu-budget", "1",
+                        "--cfg-cpu-budget", "1"], capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["config"]["global_batch"] == 16
+    assert d["strong_scaling"]["scaling"] == "strong" and d["strong_scaling"]["global_batch"] == 1024 and d["strong_scaling"]["value"] > 0
+    assert d["e2e"]["value"] > 0 and d["e2e"]["requests_per_gpu"] == 8
+    for name, c in d["configs"].items():
+        assert "error" not in c and c["n_gpus"] == 2 and c["value"] > 0 and c["e2e"]["value"] > 0, (name, c)
