@@ -54,6 +54,10 @@ struct Ctx {
 };
 Ctx& ctx();
 void set_error(const char* fmt, ...);
+// A/B switches of the kernels (BCI_SCAN, BCI_SORT, BCI_MATMUL, BCI_GEMM_*, *_PREFETCH) are development tools:
+// they are honoured only when the process was started with BCI_TUNING=1 (read once), so a stray variable in a
+// production environment cannot select an untested path.  Returns nullptr otherwise.
+const char* tuning_env(const char* name);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define BCI_CUDA(expr)                                                     \

@@ -174,7 +174,7 @@ extern "C" int bci_matmul_f32(int B, const void* const* A, const void* const* Bm
     for (int i = 0; i < B; ++i) BCI_CUDA(cudaMemsetAsync(C[i], 0, (size_t)M * N * sizeof(float), c.stream));
     return BCI_OK;
   }
-  const char* force = getenv("BCI_MATMUL");
+  const char* force = tuning_env("BCI_MATMUL");
   const bool want_simt = force && strcmp(force, "simt") == 0;
   if (!want_simt && matmul_tc_supported(M, N, K, A, Bm, C, B)) return matmul_tc_launch(B, A, Bm, C, M, N, K);
   if (force && strcmp(force, "tc") == 0) {

@@ -401,23 +401,23 @@ int matmul_tc_launch(int B, const void* const* A, const void* const* Bm, void* c
     attr_set = true;
   }
   int raster_group = 8;
-  if (const char* g = getenv("BCI_GEMM_GROUP")) raster_group = atoi(g);
+  if (const char* g = tuning_env("BCI_GEMM_GROUP")) raster_group = atoi(g);
   // L2 prefetch of the k-block `prefetch_kb` ahead (cp.async.bulk.prefetch.tensor): measured
   // 4096^3 x 8: off 204 TFLOP/s, 4/8/16/32 ahead 196 — the extra TMA traffic costs more than the
   // shorter load latency returns, so it stays off (kept as an experiment switch)
   int prefetch_kb = 0;
-  if (const char* g = getenv("BCI_GEMM_PREFETCH")) prefetch_kb = atoi(g);
+  if (const char* g = tuning_env("BCI_GEMM_PREFETCH")) prefetch_kb = atoi(g);
   // CTA tile width: 256 whenever N allows (measured 4096^3 x 8: 230.5 vs 205.9 TFLOP/s algorithmic
   // for the 128-wide tile; the GEMM launches alone run at 267 = 0.95 of the 3xTF32 ceiling, the
   // rest is the split pass); BCI_GEMM_TILE_N=128 forces the narrow tile
   int tile_n = N % 256 == 0 ? 256 : 128;
-  if (const char* g = getenv("BCI_GEMM_TILE_N")) tile_n = (atoi(g) == 256 && N % 256 == 0) ? 256 : 128;
+  if (const char* g = tuning_env("BCI_GEMM_TILE_N")) tile_n = (atoi(g) == 256 && N % 256 == 0) ? 256 : 128;
   // Optional two-deep pipeline over slices of the batch (BCI_GEMM_PIPE=1): split(i+1) on a second
   // stream under gemm(i).  Measured slower both times it was tried (8 x 4096^3: 5.35 vs 5.31 ms
   // with the 128-wide tile, 5.35 vs 4.75 ms with the 256-wide one): one-matrix slices leave a
   // 3.46-wave tail per GEMM launch and the HBM-saturating split delays the operand loads.  Off.
   bool pipe = false;
-  if (const char* g = getenv("BCI_GEMM_PIPE")) pipe = atoi(g) != 0;
+  if (const char* g = tuning_env("BCI_GEMM_PIPE")) pipe = atoi(g) != 0;
 
   // split planes: hi + lo of A and of B^T, 8 bytes per input element; two buffers when pipelined,
   // at most ~8 GiB of scratch in total

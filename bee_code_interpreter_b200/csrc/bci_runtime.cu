@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <condition_variable>
 #include <cerrno>
@@ -46,6 +47,11 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 static constexpr size_t kStageBytes = 8u << 20;  // descriptor ring
+
+const char* tuning_env(const char* name) {
+  static const bool enabled = [] { const char* t = getenv("BCI_TUNING"); return t && t[0] == '1'; }();
+  return enabled ? getenv(name) : nullptr;
+}
 
 int stage_upload(const void* host, size_t bytes, void** dptr) {
   Ctx& c = ctx();

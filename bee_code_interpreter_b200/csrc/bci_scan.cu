@@ -743,7 +743,7 @@ static int launch_cumsum_pipe(Req* reqs, int B) {
   // prefetch distance in tiles (BCI_SCAN_PREFETCH, 0 = off).  Measured, int64 1e7 x 32: off 0.79,
   // 74 tiles 0.86, 148-592 0.88 (flat), 888 0.81, 1776 0.67 (evicted before use) -> 2 x SMs
   unsigned int prefetch_dist = (unsigned int)(c.sm_count * 2);
-  if (const char* pd = getenv("BCI_SCAN_PREFETCH")) prefetch_dist = (unsigned int)atoi(pd);
+  if (const char* pd = tuning_env("BCI_SCAN_PREFETCH")) prefetch_dist = (unsigned int)atoi(pd);
   scan_pipe_kernel<T><<<(unsigned)grid, kWsThreads, Pipe<T>::SMEM, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, bt.total_tiles, st, counter,
                                                                               prefetch_dist);
   BCI_CHECK_LAUNCH();
@@ -755,7 +755,7 @@ static int launch_cumsum(Req* reqs, int B) {
   {
     // Measured on B200, int64 1e7 x 32 (tools/prof_scan.py): three-pass 4.42 TB/s algorithmic
     // (0.67), one-tile-per-CTA look-back 3.88 (0.59), warp-specialised pipeline 5.15 (0.78), 5.75 (0.88) with the L2 prefetch.
-    const char* force = getenv("BCI_SCAN");
+    const char* force = tuning_env("BCI_SCAN");
     if (force && strcmp(force, "lookback") == 0) return launch_cumsum_lookback<T>(reqs, B);
     if (force && strcmp(force, "pipe") == 0) return launch_cumsum_pipe<T>(reqs, B);
     // Integers: the warp-specialised single-pass kernel (two's-complement sums are associative, so

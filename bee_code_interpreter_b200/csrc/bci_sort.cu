@@ -334,7 +334,7 @@ static int sort_common(bool pairs, int dtype, int B, const void* const* in, void
   std::lock_guard<std::mutex> lk(c.mu);
   // default: one-sweep passes with decoupled look-back (bci_sort_onesweep.cu); the
   // reduce-then-scan passes below stay as the fallback for n >= 2^30 and for A/B runs
-  const char* force = getenv("BCI_SORT");
+  const char* force = tuning_env("BCI_SORT");
   bool legacy = force && strcmp(force, "legacy") == 0;
   for (int i = 0; i < B && !legacy; ++i) legacy = n[i] >= (1ull << 30);
   if (!legacy) return sort_onesweep(pairs, dtype, B, in, out, n);

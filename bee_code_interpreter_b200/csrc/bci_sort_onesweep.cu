@@ -446,7 +446,7 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     // ~ one wave of resident CTAs ahead; measured f32/i64/argsort: off 8.37/22.24/10.94 ms,
     // 600 tiles 8.28/21.64/10.66, 1200 8.31/22.21/10.89, 2400 = off
     unsigned int prefetch_tiles = 600;
-    if (const char* pf = getenv("BCI_SORT_PREFETCH")) prefetch_tiles = (unsigned int)atoi(pf);
+    if (const char* pf = tuning_env("BCI_SORT_PREFETCH")) prefetch_tiles = (unsigned int)atoi(pf);
     if (first)
       onesweep_kernel<K, PAIRS, true, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, status, counters + p, prefetch_tiles);
     else if (last)

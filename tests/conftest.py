@@ -4,6 +4,8 @@ from pathlib import Path
 
 import pytest
 
+os.environ.setdefault("BCI_TUNING", "1")   # the kernel A/B switches some GPU tests flip (BCI_SCAN, BCI_SORT, BCI_MATMUL) are tuning-mode only
+
 ROOT = Path(__file__).resolve().parents[1]
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))

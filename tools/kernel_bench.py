@@ -11,6 +11,8 @@ import argparse
 import ctypes as C
 import json
 import os
+
+os.environ.setdefault("BCI_TUNING", "1")      # the kernels' A/B switches are honoured only in tuning mode
 import sys
 from pathlib import Path
 

@@ -2,6 +2,8 @@
 """One launch of every kernel class at BASELINE-config sizes, for a single
 `ncu --set full` capture (profiles/r1_ncu_all_kernels.csv is its summary)."""
 import os
+
+os.environ.setdefault("BCI_TUNING", "1")      # the kernels' A/B switches are honoured only in tuning mode
 import sys
 from pathlib import Path
 

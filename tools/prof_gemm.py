@@ -2,6 +2,8 @@
 """tcgen05 3xTF32 GEMM at C2 shape (4096^3 f32) under different rasterisation groups.
     python tools/prof_gemm.py [groups...]      default: 1 4 8 16 32"""
 import os
+
+os.environ.setdefault("BCI_TUNING", "1")      # the kernels' A/B switches are honoured only in tuning mode
 import sys
 from pathlib import Path
 

@@ -3,6 +3,8 @@
     python tools/prof_scan.py            # table: legacy / lookback / pipe, i64 + f32 + f64
     BCI_SCAN=pipe python tools/prof_scan.py --once   # a few launches of one form (ncu target)"""
 import os
+
+os.environ.setdefault("BCI_TUNING", "1")      # the kernels' A/B switches are honoured only in tuning mode
 import sys
 from pathlib import Path
 

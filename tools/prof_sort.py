@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """Small driver for ncu: one batched sort (and cumsum/argmax) launch sequence."""
+import os
 import sys
+
+os.environ.setdefault("BCI_TUNING", "1")      # the kernels' A/B switches are honoured only in tuning mode
 from pathlib import Path
 import numpy as np
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
