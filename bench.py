@@ -289,6 +289,13 @@ def run_ours(args) -> dict | None:
                     got = {"value": None, "error": repr(e)}
                 if isinstance(cfg.get(name), dict):
                     cfg[name]["e2e"] = got
+                if name == "c4" and isinstance(cfg.get(name), dict):
+                    # the same config with the 64 MiB output born on the device: generated, hashed in HBM and written
+                    # out through the pinned path (BRK_EXPORT) — the object store never reads the file back
+                    try:
+                        cfg[name]["e2e_device_born_output"] = harness.run("c4dev", BC.E2E_SAMPLE["c4dev"], dist, rank, n, BC_INFLIGHT["c4dev"])
+                    except Exception as e:
+                        cfg[name]["e2e_device_born_output"] = {"value": None, "error": repr(e)}
         except Exception as e:  # executor layer not usable: no end-to-end number
             e2e = {"value": None, "unit": "requests/s", "error": repr(e)}
         finally:
@@ -366,8 +373,8 @@ def run_ours(args) -> dict | None:
     return out
 
 
-BC_INFLIGHT = {"c2": 16, "c3": 16, "c4": 48, "c5": 16}      # admitted requests per GPU in the e2e arm of each config
-MIN_JOBS = {"c1": 1, "c2": 6, "c3": 5, "c4": 1, "c5": 5}     # broker jobs one request of each workload must cause
+BC_INFLIGHT = {"c2": 16, "c3": 16, "c4": 48, "c4dev": 48, "c5": 16}      # admitted requests per GPU in the e2e arm of each config
+MIN_JOBS = {"c1": 1, "c2": 6, "c3": 5, "c4": 1, "c4dev": 2, "c5": 5}     # broker jobs one request of each workload must cause
 
 
 class E2EHarness:
@@ -534,8 +541,8 @@ def e2e_worker(args):
             for i, r in list(zip(ids, res))[: cmd.get("check", 0)]:
                 parity = parity and BC.check_result(name, i, r)
                 checked += 1
-        h2d = sum(len(s.encode()) for s in srcs) + (BC.C4_BYTES * count if name == "c4" else 0)
-        d2h = sum(len(r.stdout.encode()) for r in res) if name != "c1" else 8 * count
+        h2d = sum(len(s.encode()) for s in srcs) + (BC.C4_BYTES * count if name == "c4" else 0)       # c4: the file goes to the GPU to be hashed
+        d2h = (sum(len(r.stdout.encode()) for r in res) if name != "c1" else 8 * count) + (BC.C4_BYTES * count if name == "c4dev" else 0)
         print(json.dumps({"t_start": t0, "t_end": t1, "requests": count, "parity": parity, "checked": checked, "latencies": lat,
                           "h2d_bytes": h2d, "d2h_bytes": d2h,
                           "first_error": next((r.stderr[-300:] for r in res if r.exit_code != 0), None)}), flush=True)

@@ -342,9 +342,9 @@ def run_device_arms(dev, L, rank, world, dist, peaks, which, log) -> dict:
 
 
 # ---- request scripts + expected stdout for the e2e arms and the CPU baselines -----------------------------------------
-E2E_SAMPLE = {"c2": 192, "c3": 2048, "c4": 48, "c5": 192}       # requests per GPU in the e2e arms (bounded samples)
+E2E_SAMPLE = {"c2": 192, "c3": 2048, "c4": 96, "c4dev": 96, "c5": 192}       # requests per GPU in the e2e arms (bounded samples)
 if os.environ.get("BCI_BENCH_DRY"):
-    E2E_SAMPLE = {"c2": 4, "c3": 8, "c4": 4, "c5": 4}
+    E2E_SAMPLE = {"c2": 4, "c3": 8, "c4": 4, "c4dev": 4, "c5": 4}
 CPU_SAMPLE_ROUNDS = {"c2": 1, "c3": 2, "c4": 1, "c5": 1}
 
 
@@ -352,7 +352,8 @@ def source_for(name: str, i: int) -> str:
     from bee_code_interpreter_b200 import workloads as W
 
     return {"c2": lambda: W.c2_source(i, C2_M), "c3": lambda: W.c3_source(i, C3_N),
-            "c4": lambda: W.c4_source(i, C4_BYTES), "c5": lambda: W.c5_source(i, C5_N)}[name]()
+            "c4": lambda: W.c4_source(i, C4_BYTES), "c4dev": lambda: W.c4_source(i, C4_BYTES, device=True),
+            "c5": lambda: W.c5_source(i, C5_N)}[name]()
 
 
 def check_result(name: str, i: int, result) -> bool:
@@ -374,6 +375,9 @@ def check_result(name: str, i: int, result) -> bool:
         return all(abs(float(t) - float(w)) <= 1e-5 * abs(float(w)) for t, w in zip(toks, want))
     if name == "c4":
         want = hashlib.sha256(np.random.default_rng(3000 + i).bytes(C4_BYTES)).hexdigest()
+        return result.files.get("/workspace/out.bin") == want
+    if name == "c4dev":     # the output was born in HBM (default_rng(...).random(n).tofile): hashed there, written through the pinned path
+        want = hashlib.sha256(np.random.default_rng(3000 + i).random(C4_BYTES // 8).tobytes()).hexdigest()
         return result.files.get("/workspace/out.bin") == want
     if name == "c5":
         v = np.random.default_rng(4000 + i).random(C5_N, dtype=np.float32)
