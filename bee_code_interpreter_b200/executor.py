@@ -53,7 +53,8 @@ class LocalGpuExecutor:
     def __init__(self, file_storage=None, *, max_inflight: int = 16, timeout: float = 60.0,
                  broker=None, device_module=None, storage_path: str | None = None,
                  min_rand_elems: int | None = None, zygotes: int | None = None, device: int | None = None,
-                 retry_attempts: int = 3, retry_wait: tuple[float, float] = (0.1, 2.0), zygote_pool: int | None = None):
+                 retry_attempts: int = 3, retry_wait: tuple[float, float] = (0.1, 2.0), zygote_pool: int | None = None,
+                 pin_zygotes: bool | None = None):
         # max_inflight = requests admitted at once (the rest wait on a semaphore).  16 per GPU is the
         # measured optimum for short scripts: the broker needs ~2 dispatch groups of work to keep the
         # GPU busy, and every additional live script process lengthens the fork / set-up phase of
@@ -88,7 +89,10 @@ class LocalGpuExecutor:
         self._sem_loop = None
         n_zyg = zygotes if zygotes is not None else max(1, min(8, (os.cpu_count() or 2) // 8))
         from .zygote import ZygoteClient
-        self._zygotes = [ZygoteClient(pool=zygote_pool) for _ in range(n_zyg)]
+        if pin_zygotes is None:
+            pin_zygotes = bool(os.environ.get("BCI_PIN_ZYGOTES"))
+        # pinned: zygote k of this process sits on CPU (pid * 7 + k) mod ncpus, so several service processes spread out
+        self._zygotes = [ZygoteClient(pool=zygote_pool, pin_cpu=(os.getpid() * 7 + k) if pin_zygotes else None) for k in range(n_zyg)]
         self._rr = 0
         # backend failures (a warm interpreter or the broker died) are retried like the reference retries
         # RuntimeError (kubernetes_code_executor.py:75-79: 3 attempts, exponential wait) after the dead part

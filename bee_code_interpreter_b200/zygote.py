@@ -39,6 +39,7 @@ _ENV_ALLOW = {"PATH", "HOME", "USER", "LOGNAME", "SHELL", "LANG", "LANGUAGE", "T
 _ENV_ALLOW_PREFIXES = ("LC_", "BCI_", "OMP_", "OPENBLAS_", "MKL_", "NUMEXPR_")
 _TRACE = bool(os.environ.get("BCI_TRACE"))
 _YIELD = bool(os.environ.get("BCI_ZYGOTE_YIELD"))
+PIN_ENV = "BCI_ZYGOTE_PIN"
 POOL_ENV = "BCI_ZYGOTE_POOL"      # children forked ahead of requests (0 = fork on arrival)
 MAX_REQUEST = 64 << 20
 
@@ -134,16 +135,28 @@ def _spawn_idle(srv: socket.socket, idle: list) -> "_Idle | None":
 def serve(socket_path: str) -> None:
     import gc
 
-    from . import script_runner  # noqa: F401  imports numpy + proxy + hook once
+    from . import script_runner  # imports numpy + proxy + hook once
 
     # Everything imported so far lives as long as the zygote: move it to the permanent generation and stop
     # collecting here.  Without this (measured, profiles/r2f_*): the cyclic collector's generation counters are
     # inherited by every child, a few percent of the requests start with a FULL collection over ~10^5 module
     # objects (30-60 ms, p99 of the request latency) — and each such pass dirties the pages it walks, i.e.
     # copy-on-write faults on top.  Children re-enable the collector for the script's own objects.
-    gc.collect()
-    gc.freeze()
-    gc.disable()
+    if not os.environ.get("BCI_ZYGOTE_NOFREEZE"):
+        gc.collect()
+        gc.freeze()
+        gc.disable()
+    # BCI_ZYGOTE_PIN=<cpu>: this zygote and the first milliseconds of every child run on ONE CPU — a forked child
+    # placed on another core starts with cold caches for the whole interpreter (measured: 1.7 ms of user time for
+    # a `pass` script); the child widens its affinity again before the agent's code runs (script_runner).
+    pin = os.environ.get(PIN_ENV)
+    if pin not in (None, ""):
+        try:
+            cpus = set(os.sched_getaffinity(0))
+            os.sched_setaffinity(0, {sorted(cpus)[int(pin) % len(cpus)]})
+            script_runner.ALL_CPUS = cpus
+        except (OSError, ValueError, AttributeError):
+            pass
     signal.signal(signal.SIGCHLD, signal.SIG_IGN)
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
     try:
@@ -160,6 +173,7 @@ def serve(socket_path: str) -> None:
             idle.append(ch)
     sys.stdout.write("ready\n")
     sys.stdout.flush()
+    script_runner.prepare_zygote_stdio()
     parent = os.getppid()
     srv.settimeout(2.0)
     while True:
@@ -252,7 +266,8 @@ class ZygoteDied(RuntimeError):
 class ZygoteClient:
     """Service-side handle: starts the zygote process and submits requests to it."""
 
-    def __init__(self, pool: int | None = None):
+    def __init__(self, pool: int | None = None, pin_cpu: int | None = None):
+        self._pin = pin_cpu
         self._dir = tempfile.mkdtemp(prefix="bci-zygote-")
         self.socket_path = os.path.join(self._dir, "zygote.sock")
         self._pool = pool
@@ -273,6 +288,8 @@ class ZygoteClient:
             env.setdefault(var, "1")
         if self._pool is not None:
             env[POOL_ENV] = str(self._pool)
+        if self._pin is not None:
+            env[PIN_ENV] = str(self._pin)
         self._proc = subprocess.Popen([sys.executable, "-m", "bee_code_interpreter_b200.zygote", self.socket_path],
                                       stdout=subprocess.PIPE, env=env, cwd=root)
         line = self._proc.stdout.readline()
