@@ -312,10 +312,13 @@ def run_ours(args) -> dict | None:
     tot_b = sum(timing["wave_b"])
     fused_s = sum(timing["fused_ms"]) / 1e3
     sm_mhz = (clocks.get("sm_mhz") or 1965.0)
-    # instruction roofline of the fused kernel: Philox4x32-10 = 20 IMAD.WIDE per counter = 10 per float64;
-    # the fma pipe issues one warp instruction per SMSP every 2 cycles -> 148 SMs x 4 SMSPs x 16 lanes per clock
-    imad_rate = 10.0 * n * tot_b / fused_s if fused_s else None
-    imad_peak = 148 * 4 * 16 * sm_mhz * 1e6
+    # instruction roofline of the fused kernel.  ncu (profiles/r2_ncu_new_kernels.csv, `--set full` of a 16-request
+    # launch): 0.986 warp-instructions = 31.5 thread-instructions per float64 (Philox4x32-10: 10 IMAD.WIDE + 10 LOP3,
+    # numpy's 53-bit double: 2 SHF + 2 I2F + DMUL + DFMA, square + add); an SM issues at most 4 warp-instructions per
+    # clock, so the ceiling is 4 x 32 / 31.5 = 4.06 float64 per clock per SM.
+    instr_per_elem = 31.5
+    elem_rate = n * tot_b / fused_s if fused_s else None
+    elem_peak = 148 * 128.0 / instr_per_elem * sm_mhz * 1e6
     algo = float(W.C1_ALGO_BYTES) * n / W.C1_N      # numpy's unfused traffic per request (32 n bytes)
     k_fused = {"kernel": "reduce_rand_kernel<SUM,PRE_SQUARE>", "requests_per_launch": wave,
                "algorithmic_bytes_per_launch": algo * wave, "moved_bytes_per_launch": 8 * wave,
@@ -323,14 +326,17 @@ def run_ours(args) -> dict | None:
                "achieved": algo * tot_b / fused_s / 1e9 if fused_s else None}
     roofline = {"bound": "hbm", "kernel": k_fused["kernel"], "achieved": k_fused["achieved"], "peak": peak,
                 "unit": "GB/s", "frac": (k_fused["achieved"] / peak) if k_fused["achieved"] else None,
-                "traffic": None,
+                # dram__bytes_read + write of the ncu capture: 29.7 KB for a 16-request launch (descriptors, partials)
+                "traffic": 29696.0 / 16 * wave,
                 "traffic_note": "the kernel reads no array and writes 8 B per request + one partial per CTA: rand(n), its square "
                                 "and the sum live in registers.  `achieved` counts numpy's UNFUSED algorithmic bytes (32 n per "
-                                "request, SURVEY.md a9), which is why frac > 1; bytes actually moved are ~0",
-                "bound_note": "not HBM: the fma pipe (IMAD.WIDE of Philox4x32-10, 10 per float64) — see `issue`",
-                "issue": {"unit": "IMAD.WIDE lane-ops/s", "achieved": imad_rate, "peak": imad_peak,
-                          "frac": (imad_rate / imad_peak) if imad_rate else None,
-                          "peak_how": "148 SMs x 4 SMSPs x 16 lanes/clk (fma pipe, one warp instruction per 2 cycles) x median SM clock under load"},
+                                "request, SURVEY.md a9), which is why frac > 1; bytes actually moved are ~2 KB per request",
+                "bound_note": "not HBM: instruction issue.  ncu: issue slots 59 % active with 6.5 eligible warps per scheduler per "
+                              "cycle and 99 % occupancy — IMAD.WIDE and FP64 instructions hold the dispatch port for two cycles; fma "
+                              "pipe 38 %, ALU 45 %, XU (I2F) 30 %, FP64 16 % busy — see `issue`",
+                "issue": {"unit": "float64 elements/s", "achieved": elem_rate, "peak": elem_peak,
+                          "frac": (elem_rate / elem_peak) if elem_rate else None, "thread_instructions_per_element": instr_per_elem,
+                          "peak_how": "148 SMs x 4 schedulers x 32 lanes per clock / 31.5 instructions per element x median SM clock under load"},
                 "peak_kind": peak_kind, "kernels": [k_fused],
                 "share_of_step": {"fused": fused_s / (dev_ms / 1e3)}}
     if unfused:
