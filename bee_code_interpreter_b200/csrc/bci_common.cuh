@@ -86,6 +86,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 // Copies `bytes` of host data into the staging ring and schedules the H2D copy
 // on the op stream; returns the DEVICE address (256-byte aligned).
 int stage_upload(const void* host, size_t bytes, void** dptr);
+// Host memory -> device through a pinned transfer lane; thread-safe, does not take the context lock for the copy.
+int h2d_pinned(void* dst_dev, const void* src_host, size_t bytes);
 // Grow-only device scratch; contents undefined. 256-byte aligned.
 int scratch_get(size_t bytes, void** dptr);
 // Result hand-back without holding the context lock while the GPU works:

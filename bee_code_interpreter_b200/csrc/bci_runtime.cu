@@ -413,6 +413,35 @@ int lane_order_after_ops(Lane* l) {
 }
 }  // namespace
 
+}  // extern "C"
+
+namespace bci {
+// Host memory -> device through a transfer lane (pinned bounce buffers, copy stream): what cudaMemcpyAsync
+// from pageable memory does internally, minus holding the library lock and the op stream while it happens.
+// Several callers (threads) run in parallel on different lanes.
+int h2d_pinned(void* dst_dev, const void* src_host, size_t bytes) {
+  if (bytes == 0) return BCI_OK;
+  LaneGuard g;
+  int rc = lane_acquire(&g.l);
+  if (rc != BCI_OK) return rc;
+  if ((rc = lane_order_after_ops(g.l)) != BCI_OK) return rc;
+  size_t done = 0;
+  for (int k = 0; done < bytes; ++k) {
+    const int b = k & 1;
+    if (k >= 2) BCI_CUDA(cudaEventSynchronize(g.l->done[b]));
+    const size_t want = bytes - done < kLaneChunk ? bytes - done : kLaneChunk;
+    memcpy(g.l->buf[b], static_cast<const uint8_t*>(src_host) + done, want);
+    BCI_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst_dev) + done, g.l->buf[b], want, cudaMemcpyHostToDevice, g.l->stream));
+    BCI_CUDA(cudaEventRecord(g.l->done[b], g.l->stream));
+    done += want;
+  }
+  BCI_CUDA(cudaStreamSynchronize(g.l->stream));
+  return BCI_OK;
+}
+}  // namespace bci
+
+extern "C" {
+
 int bci_h2d_fd(void* dst_dev, int fd, uint64_t file_offset, size_t bytes) {
   BCI_REQUIRE_INIT();
   if (bytes == 0) return BCI_OK;

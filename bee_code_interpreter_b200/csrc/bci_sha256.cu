@@ -15,6 +15,9 @@
 // Padding (0x80, zeros, 64-bit big-endian bit length) is built in-kernel, so any byte
 // length works; data is read with 128-bit loads when the pointer is 16-byte aligned.
 #include "bci_common.cuh"
+#include <thread>
+#include <atomic>
+#include <string>
 #include <vector>
 #include <condition_variable>
 #include <cstring>
@@ -347,43 +350,58 @@ extern "C" int bci_sha256(int B, const void* const* data, const size_t* len, int
                           uint8_t* digests) {
   BCI_REQUIRE_INIT();
   if (B <= 0 || !data || !len || !digests) { set_error("bci_sha256: bad arguments"); return BCI_ERR_INVALID; }
+  for (int i = 0; i < B; ++i)
+    if (len[i] && !data[i]) { set_error("bci_sha256: NULL data in message %d", i); return BCI_ERR_INVALID; }
   Ctx& c = ctx();
-  std::unique_lock<std::mutex> lk(c.mu);
   std::vector<ShaMsg> msgs((size_t)B);
   uint8_t* staging = nullptr;
+  std::vector<size_t> offs((size_t)B, 0);
   if (!on_device) {
+    // host messages: one device staging block, filled through the pinned transfer lanes by up to four copy
+    // threads in parallel — the library lock is NOT held while the bytes cross PCIe
     size_t total = 0;
-    for (int i = 0; i < B; ++i) total += (len[i] + 255) & ~size_t(255);
+    for (int i = 0; i < B; ++i) { offs[i] = total; total += (len[i] + 255) & ~size_t(255); }
     if (total) {
-      cudaError_t e = cudaMallocFromPoolAsync((void**)&staging, total, c.pool, c.stream);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync(sha staging)", __FILE__, __LINE__);
+      {
+        std::lock_guard<std::mutex> lk(c.mu);
+        cudaError_t e = cudaMallocFromPoolAsync((void**)&staging, total, c.pool, c.stream);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMallocFromPoolAsync(sha staging)", __FILE__, __LINE__);
+      }
+      const int workers = B < 4 ? B : 4;
+      std::vector<int> rcs((size_t)workers, BCI_OK);
+      std::vector<std::string> errs((size_t)workers);
+      std::atomic<int> next{0};
+      auto work = [&](int w) {
+        (void)cudaSetDevice(c.device);
+        for (int i = next.fetch_add(1); i < B; i = next.fetch_add(1)) {
+          int rc = h2d_pinned(staging + offs[i], data[i], len[i]);
+          if (rc != BCI_OK) { rcs[w] = rc; errs[w] = bci_last_error(); return; }
+        }
+      };
+      std::vector<std::thread> th;
+      for (int w = 1; w < workers; ++w) th.emplace_back(work, w);
+      work(0);
+      for (auto& t : th) t.join();
+      for (int w = 0; w < workers; ++w)
+        if (rcs[w] != BCI_OK) {
+          std::lock_guard<std::mutex> lk(c.mu);
+          cudaFreeAsync(staging, c.stream);
+          set_error("%s", errs[w].c_str());
+          return rcs[w];
+        }
     }
   }
-  size_t off = 0;
   for (int i = 0; i < B; ++i) {
     ShaMsg& m = msgs[i];
     memset(&m, 0, sizeof m);
-    if (len[i] && !data[i]) {
-      if (staging) cudaFreeAsync(staging, c.stream);
-      set_error("bci_sha256: NULL data in message %d", i);
-      return BCI_ERR_INVALID;
-    }
-    if (on_device) {
-      m.data = reinterpret_cast<const uint8_t*>(data[i]);
-    } else {
-      m.data = staging + off;
-      if (len[i]) {
-        cudaError_t e = cudaMemcpyAsync(staging + off, data[i], len[i], cudaMemcpyHostToDevice, c.stream);
-        if (e != cudaSuccess) { cudaFreeAsync(staging, c.stream); return cuda_fail(e, "cudaMemcpyAsync(sha h2d)", __FILE__, __LINE__); }
-      }
-      off += (len[i] + 255) & ~size_t(255);
-    }
+    m.data = on_device ? reinterpret_cast<const uint8_t*>(data[i]) : staging + offs[i];
     m.len = len[i];
     m.prior = 0;
     memcpy(m.h, kSha256IV, sizeof m.h);
     m.finalize = 1;
   }
   std::vector<uint32_t> states((size_t)B * 8);
+  std::unique_lock<std::mutex> lk(c.mu);
   int rc = sha_launch(lk, msgs, states.data());
   if (staging) cudaFreeAsync(staging, c.stream);
   if (rc != BCI_OK) return rc;
