@@ -257,6 +257,11 @@ class RemoteBackend:
         """SHA-256 of an open regular file; the broker reads it through the descriptor."""
         return self._call(W.SHA256_FD, fd=fd)[1]
 
+    def sha256_fd_ex(self, fd: int) -> tuple[bytes, bool]:
+        """-> (digest, answered from the export table without reading the file)."""
+        value, payload = self._call(W.SHA256_FD, fd=fd)
+        return payload, bool(value)
+
     def sha256_bytes(self, data: bytes) -> bytes:
         return self._call(W.SHA256_BYTES, payload=bytes(data))[1]
 

@@ -185,3 +185,47 @@ def test_c2_matmul_on_the_configs_own_inputs(dev):
         assert np.abs(c[rows] - ref64).max() <= 2e-6 * np.abs(ref64).max()
         for p in (A, B, C):
             dev.free(p)
+
+
+def test_exported_array_is_hashed_on_the_device_and_not_read_back(dev, tmp_path):
+    """BRK_EXPORT: a device array goes to a file behind an .npy header through the pinned path while the device
+    hashes header||array; a later BRK_SHA256_FD of the untouched file is answered from the export table, and
+    any write to the file invalidates the entry."""
+    import io
+
+    from bee_code_interpreter_b200.broker import BrokerProcess
+    from bee_code_interpreter_b200.broker_client import RemoteBackend
+
+    broker = BrokerProcess(device=0)     # its own CUDA context beside this process's
+    try:
+        be = RemoteBackend(broker.socket_path)
+        st = np.random.PCG64(77).state["state"]
+        n = (8 << 20) + 3
+        ptr, rej = be.rand_pcg(L.PCG_F64, n, st["state"], st["inc"])
+        want = np.random.default_rng(77).random(n)
+        head = io.BytesIO()
+        np.lib.format.write_array_header_1_0(head, {"descr": "<f8", "fortran_order": False, "shape": (n,)})
+        path = tmp_path / "out.npy"
+        fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC)
+        digest = be.export(ptr, n * 8, fd, head.getvalue())
+        os.close(fd)
+        blob = path.read_bytes()
+        assert digest == hashlib.sha256(blob).digest()
+        assert np.array_equal(np.load(path), want)
+        fd = os.open(path, os.O_RDONLY)
+        d2, cached = be.sha256_fd_ex(fd)
+        assert d2 == digest and cached
+        d3, cached = be.sha256_fd_ex(fd)            # one consumer: the entry is gone, the file is read and hashed
+        assert d3 == digest and not cached
+        os.close(fd)
+        fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC)
+        be.export(ptr, n * 8, fd, b"")
+        os.pwrite(fd, b"\x01", 5)                    # the script touches the file afterwards
+        os.close(fd)
+        fd = os.open(path, os.O_RDONLY)
+        d4, cached = be.sha256_fd_ex(fd)
+        os.close(fd)
+        assert not cached and d4 == hashlib.sha256(path.read_bytes()).digest()
+        be.close()
+    finally:
+        broker.close()
