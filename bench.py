@@ -284,7 +284,8 @@ def run_ours(args) -> dict | None:
             e2e["parity_6sigma"] = e2e["parity"]
             for name in which:
                 try:
-                    got = harness.run(name, BC.E2E_SAMPLE[name], dist, rank, n, BC_INFLIGHT[name] if world <= 2 else max(8, BC_INFLIGHT[name] // 2))
+                    sample = BC.E2E_SAMPLE[name] if not name.startswith("c4") else max(16, BC.E2E_SAMPLE[name] // world)
+                    got = harness.run(name, sample, dist, rank, n, BC_INFLIGHT[name] if world <= 2 else max(8, BC_INFLIGHT[name] // 2))
                 except Exception as e:
                     got = {"value": None, "error": repr(e)}
                 if isinstance(cfg.get(name), dict):
@@ -293,7 +294,8 @@ def run_ours(args) -> dict | None:
                     # the same config with the 64 MiB output born on the device: generated, hashed in HBM and written
                     # out through the pinned path (BRK_EXPORT) — the object store never reads the file back
                     try:
-                        cfg[name]["e2e_device_born_output"] = harness.run("c4dev", BC.E2E_SAMPLE["c4dev"], dist, rank, n, BC_INFLIGHT["c4dev"])
+                        cfg[name]["e2e_device_born_output"] = harness.run("c4dev", max(16, BC.E2E_SAMPLE["c4dev"] // world), dist, rank, n,
+                                                                          BC_INFLIGHT["c4dev"] if world <= 2 else BC_INFLIGHT["c4dev"] // 2)
                     except Exception as e:
                         cfg[name]["e2e_device_born_output"] = {"value": None, "error": repr(e)}
         except Exception as e:  # executor layer not usable: no end-to-end number
@@ -445,7 +447,8 @@ class E2EHarness:
         counts = [requests_per_gpu // w + (1 if i < requests_per_gpu % w else 0) for i in range(w)]
         inflight = max(1, inflight_per_gpu // w)
         base = {"workload": workload, "n": n, "inflight": inflight, "stride": world * w}
-        warm = [dict(base, count=min(c, max(8, 2 * inflight)), first=rank + world * i + world * w * 100_000, check=0) for i, c in enumerate(counts)]
+        warm_n = 4 if workload.startswith("c4") else max(8, 2 * inflight)      # C4 requests are 64 MiB each: a short warm-up
+        warm = [dict(base, count=min(c, warm_n), first=rank + world * i + world * w * 100_000, check=0) for i, c in enumerate(counts)]
         self._command(warm)                                       # untimed: page cache, pool growth, zygote warm-up
         before = self._stats()
         if dist is not None:
@@ -549,6 +552,13 @@ def e2e_worker(args):
                 checked += 1
         h2d = sum(len(s.encode()) for s in srcs) + (BC.C4_BYTES * count if name == "c4" else 0)       # c4: the file goes to the GPU to be hashed
         d2h = (sum(len(r.stdout.encode()) for r in res) if name != "c1" else 8 * count) + (BC.C4_BYTES * count if name == "c4dev" else 0)
+        if name.startswith("c4"):      # 64 MiB objects: do not let the worker's temporary object store pile up on disk
+            try:
+                store = str(execu.file_storage.storage_path)
+                for entry in os.scandir(store):
+                    os.unlink(entry.path)
+            except OSError:
+                pass
         print(json.dumps({"t_start": t0, "t_end": t1, "requests": count, "parity": parity, "checked": checked, "latencies": lat,
                           "h2d_bytes": h2d, "d2h_bytes": d2h,
                           "first_error": next((r.stderr[-300:] for r in res if r.exit_code != 0), None)}), flush=True)
