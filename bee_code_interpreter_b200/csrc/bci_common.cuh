@@ -88,6 +88,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int stage_upload(const void* host, size_t bytes, void** dptr);
 // Host memory -> device through a pinned transfer lane; thread-safe, does not take the context lock for the copy.
 int h2d_pinned(void* dst_dev, const void* src_host, size_t bytes);
+int d2h_pinned(void* dst_host, const void* src_dev, size_t bytes);
 // Grow-only device scratch; contents undefined. 256-byte aligned.
 int scratch_get(size_t bytes, void** dptr);
 // Result hand-back without holding the context lock while the GPU works:

@@ -325,6 +325,14 @@ int bci_h2d(void* dst_dev, const void* src_host, size_t bytes) {
   BCI_REQUIRE_INIT();
   if (bytes == 0) return BCI_OK;
   if (!dst_dev || !src_host) { set_error("bci_h2d: NULL pointer"); return BCI_ERR_INVALID; }
+  if (bytes > (256u << 10)) {
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, src_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    // a large pageable source would be staged by the runtime WHILE the library lock is held: move it through a
+    // transfer lane instead (returns when the copy is done); pinned sources keep the asynchronous path
+    if (!pinned) return bci::h2d_pinned(dst_dev, src_host, bytes);
+  }
   Ctx& c = ctx();
   std::lock_guard<std::mutex> lk(c.mu);
   BCI_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, c.stream));
@@ -335,11 +343,27 @@ int bci_d2h(void* dst_host, const void* src_dev, size_t bytes) {
   BCI_REQUIRE_INIT();
   if (bytes == 0) return BCI_OK;
   if (!dst_host || !src_dev) { set_error("bci_d2h: NULL pointer"); return BCI_ERR_INVALID; }
-  Ctx& c = ctx();
-  std::lock_guard<std::mutex> lk(c.mu);
-  BCI_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c.stream));
-  BCI_CUDA(cudaStreamSynchronize(c.stream));
-  return BCI_OK;
+  // Never wait for the GPU with the library lock held: a script printing `s[0], s[-1]` after a sort would otherwise
+  // stall every other request's launches for as long as the op stream is busy.  Small reads (an element, a scalar
+  // result) go through a pinned result slot and wait on its event; bulk reads through a transfer lane.
+  if (bytes <= (64u << 10)) {
+    Ctx& c = ctx();
+    void *h = nullptr, *d = nullptr;
+    ResultGuard guard;
+    {
+      std::unique_lock<std::mutex> lk(c.mu);
+      int rc = result_acquire(lk, bytes, &guard.slot, &h, &d);
+      if (rc != BCI_OK) return rc;
+      Ctx::ResultSlot& r = c.rslot[guard.slot];
+      BCI_CUDA(cudaMemcpyAsync(r.h, src_dev, bytes, cudaMemcpyDeviceToHost, c.stream));
+      BCI_CUDA(cudaEventRecord(r.done, c.stream));
+    }
+    int rc = result_wait(guard.slot);
+    if (rc != BCI_OK) return rc;
+    memcpy(dst_host, h, bytes);
+    return BCI_OK;
+  }
+  return bci::d2h_pinned(dst_host, src_dev, bytes);
 }
 
 int bci_d2d(void* dst_dev, const void* src_dev, size_t bytes) {
@@ -436,6 +460,30 @@ int h2d_pinned(void* dst_dev, const void* src_host, size_t bytes) {
     done += want;
   }
   BCI_CUDA(cudaStreamSynchronize(g.l->stream));
+  return BCI_OK;
+}
+
+// Device -> host memory through a transfer lane (the mirror of h2d_pinned).
+int d2h_pinned(void* dst_host, const void* src_dev, size_t bytes) {
+  if (bytes == 0) return BCI_OK;
+  LaneGuard g;
+  int rc = lane_acquire(&g.l);
+  if (rc != BCI_OK) return rc;
+  if ((rc = lane_order_after_ops(g.l)) != BCI_OK) return rc;
+  const size_t chunks = (bytes + kLaneChunk - 1) / kLaneChunk;
+  auto issue = [&](size_t k) -> int {
+    const size_t off = k * kLaneChunk, want = bytes - off < kLaneChunk ? bytes - off : kLaneChunk;
+    BCI_CUDA(cudaMemcpyAsync(g.l->buf[k & 1], static_cast<const uint8_t*>(src_dev) + off, want, cudaMemcpyDeviceToHost, g.l->stream));
+    BCI_CUDA(cudaEventRecord(g.l->done[k & 1], g.l->stream));
+    return BCI_OK;
+  };
+  if ((rc = issue(0)) != BCI_OK) return rc;
+  for (size_t k = 0; k < chunks; ++k) {
+    if (k + 1 < chunks && (rc = issue(k + 1)) != BCI_OK) return rc;
+    BCI_CUDA(cudaEventSynchronize(g.l->done[k & 1]));
+    const size_t off = k * kLaneChunk, want = bytes - off < kLaneChunk ? bytes - off : kLaneChunk;
+    memcpy(static_cast<uint8_t*>(dst_host) + off, g.l->buf[k & 1], want);
+  }
   return BCI_OK;
 }
 }  // namespace bci
