@@ -305,6 +305,16 @@ class DeviceArray(NDArrayOperatorsMixin):
         out = _h(self).astype(dtype, *a, **kw)
         return out.copy() if out is self._host else out   # astype(copy=False) must not leak the cache
 
+    def __copy__(self):
+        return self.copy()
+
+    def __deepcopy__(self, memo):
+        return self.copy()
+
+    def __reduce__(self):
+        # pickles (multiprocessing, joblib, caches) as the ndarray it stands for
+        return (np.asarray, (np.array(_h(self)),))
+
     def copy(self, order="C"):
         out = self._backend.copy_buffer(self._device_ptr(), self.nbytes)
         return DeviceArray(self._backend, out, self._shape, self._dtype)
