@@ -389,7 +389,7 @@ int bci_memset(void* dst_dev, int byte, size_t bytes) {
 // ---- pinned file <-> device transfers ---------------------------------------------------------
 namespace {
 constexpr size_t kLaneChunk = 8u << 20;
-constexpr int kLanes = 4;
+constexpr int kLanes = 8;
 struct Lane {
   cudaStream_t stream = nullptr;
   uint8_t* buf[2] = {nullptr, nullptr};
