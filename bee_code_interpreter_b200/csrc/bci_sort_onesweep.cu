@@ -104,8 +104,11 @@ digit_hist_kernel(const Req* __restrict__ reqs, const unsigned long long* __rest
 }
 
 // one CTA per (request, pass): ghist[..][256] counts -> exclusive offsets, in place
+// Also: trivial[request * P + pass] = 1 when ONE digit holds every key of the request in that pass (the high bytes of
+// small integers, the sign/exponent byte of same-magnitude floats): such a pass is the identity permutation and the
+// sweep kernel copies its tiles instead of ranking them.
 __global__ void __launch_bounds__(kThreads)
-digit_scan_kernel(uint32_t* __restrict__ ghist) {
+digit_scan_kernel(uint32_t* __restrict__ ghist, uint32_t* __restrict__ trivial) {
   __shared__ uint32_t wsum[kSortWarps];
   uint32_t* h = ghist + (size_t)blockIdx.x * 256;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -118,9 +121,11 @@ digit_scan_kernel(uint32_t* __restrict__ ghist) {
   }
   if (lane == 31) wsum[warp] = inc;
   __syncthreads();
-  uint32_t wprefix = 0;
-  for (int w = 0; w < warp; ++w) wprefix += wsum[w];
+  uint32_t wprefix = 0, total = 0;
+  for (int w = 0; w < kSortWarps; ++w) { if (w < warp) wprefix += wsum[w]; total += wsum[w]; }
   h[threadIdx.x] = wprefix + inc - c;
+  const int one_digit = __syncthreads_or(total != 0 && c == total);
+  if (threadIdx.x == 0) trivial[blockIdx.x] = one_digit ? 1u : 0u;
 }
 
 // ---- one pass -----------------------------------------------------------------------------------
@@ -133,7 +138,7 @@ template <typename K, bool PAIRS, bool FIRST, bool LAST>
 // (4 resident CTAs at 64 registers with 24 spilled words beat 3 at 80 registers: 8.38 vs 8.61 ms)
 __global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 4 : 2)
 onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
-                int pass, int dtype, const uint32_t* __restrict__ gbase,
+                int pass, int dtype, const uint32_t* __restrict__ gbase, const uint32_t* __restrict__ trivial,
                 uint32_t* __restrict__ status, uint32_t* __restrict__ counter, unsigned int prefetch_tiles) {
   constexpr int P = (int)sizeof(K);
   constexpr bool WRITE_KEYS = !(PAIRS && LAST);
@@ -169,6 +174,28 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   const int shift = pass * 8;
   const K* __restrict__ src = reinterpret_cast<const K*>(q.in0) + base;
   const uint32_t* __restrict__ srci = reinterpret_cast<const uint32_t*>(q.in1) + base;  // !FIRST only
+  if (__ldg(trivial + (size_t)r * P + pass)) {
+    // every key of this request carries the same digit in this pass: nothing moves.  Copy the tile (with the key
+    // transform of a first / last pass) — ~10 instructions per key instead of a ranking pass; no status is published,
+    // the other tiles of this request take the same branch.
+    K* __restrict__ dstk = reinterpret_cast<K*>(q.out) + base;
+#pragma unroll
+    for (int k = 0; k < kSortItems; ++k) {
+      const int i = k * kThreads + (int)threadIdx.x;
+      if (i < m) {
+        K x = src[i];
+        if constexpr (FIRST) x = to_key<K>(x, dtype);
+        if constexpr (WRITE_KEYS) dstk[i] = LAST ? from_key<K>(x, dtype) : x;
+        if constexpr (PAIRS) {
+          uint32_t ix;
+          if constexpr (FIRST) ix = (uint32_t)(base + i); else ix = srci[i];
+          if constexpr (LAST) reinterpret_cast<long long*>(q.s0.i)[base + i] = (long long)ix;
+          else reinterpret_cast<uint32_t*>(q.s0.i)[base + i] = ix;
+        }
+      }
+    }
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   // this request's run start for digit d of this pass (independent load, issued early)
@@ -379,7 +406,8 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
   if (total_tiles == 0) return BCI_OK;
   if (total_tiles > 0x7fffffffull) { set_error("bci_sort: batch too large for one launch"); return BCI_ERR_INVALID; }
   // scratch: [counters P][ghist B*P*256][status total_tiles*256] [per request: keysA (+keysB, idxA, idxB)]
-  const size_t hdr_words = 64 + (size_t)B * P * 256;
+  const size_t flag_words = ((size_t)B * P + 63) & ~size_t(63);
+  const size_t hdr_words = 64 + (size_t)B * P * 256 + flag_words;
   size_t bytes = (hdr_words + total_tiles * 256) * sizeof(uint32_t);
   bytes = (bytes + 255) & ~size_t(255);
   std::vector<size_t> koff((size_t)B);
@@ -395,6 +423,7 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
   uint8_t* sbase = reinterpret_cast<uint8_t*>(sc);
   uint32_t* counters = reinterpret_cast<uint32_t*>(sbase);
   uint32_t* ghist = counters + 64;
+  uint32_t* trivial = ghist + (size_t)B * P * 256;
   uint32_t* status = reinterpret_cast<uint32_t*>(sbase) + hdr_words;
   BCI_CUDA(cudaMemsetAsync(sbase, 0, hdr_words * sizeof(uint32_t), c.stream));
 
@@ -412,7 +441,7 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     const unsigned grid = (unsigned)(total_tiles < (size_t)c.sm_count * 8 ? total_tiles : (size_t)c.sm_count * 8);
     digit_hist_kernel<K><<<grid, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, total_tiles, dtype, ghist);
     BCI_CHECK_LAUNCH();
-    digit_scan_kernel<<<(unsigned)(B * P), kThreads, 0, c.stream>>>(ghist);
+    digit_scan_kernel<<<(unsigned)(B * P), kThreads, 0, c.stream>>>(ghist, trivial);
     BCI_CHECK_LAUNCH();
   }
   for (int p = 0; p < P; ++p) {
@@ -448,11 +477,11 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     unsigned int prefetch_tiles = 600;
     if (const char* pf = tuning_env("BCI_SORT_PREFETCH")) prefetch_tiles = (unsigned int)atoi(pf);
     if (first)
-      onesweep_kernel<K, PAIRS, true, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, status, counters + p, prefetch_tiles);
+      onesweep_kernel<K, PAIRS, true, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
     else if (last)
-      onesweep_kernel<K, PAIRS, false, true><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, status, counters + p, prefetch_tiles);
+      onesweep_kernel<K, PAIRS, false, true><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
     else
-      onesweep_kernel<K, PAIRS, false, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, status, counters + p, prefetch_tiles);
+      onesweep_kernel<K, PAIRS, false, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
     BCI_CHECK_LAUNCH();
   }
   return BCI_OK;

@@ -229,3 +229,33 @@ def test_exported_array_is_hashed_on_the_device_and_not_read_back(dev, tmp_path)
         be.close()
     finally:
         broker.close()
+
+
+def test_sort_passes_whose_digit_is_constant_are_copied_not_ranked(dev):
+    """One batch mixing requests whose passes are trivial (all keys share the digit: small non-negative int64, a
+    constant array, floats of one binade) with requests whose passes are not: sort and stable argsort stay bit-exact."""
+    rng = np.random.default_rng(12)
+    n = 300_007
+    cases = {
+        np.int64: [rng.integers(0, 2**31, n, dtype=np.int64), np.full(n, 7, dtype=np.int64), rng.integers(-2**62, 2**62, n, dtype=np.int64),
+                   rng.integers(0, 200, 5000, dtype=np.int64), rng.integers(-3, 3, n, dtype=np.int64)],
+        np.float32: [(1.0 + rng.random(n, dtype=np.float32)), np.zeros(n, dtype=np.float32), rng.standard_normal(n).astype(np.float32),
+                     np.full(777, np.nan, dtype=np.float32)],
+        np.float64: [rng.random(n) + 4.0, rng.standard_normal(n), np.full(n, -1.5)],
+        np.int32: [rng.integers(0, 255, n, dtype=np.int32), rng.integers(-2**31, 2**31 - 1, n, dtype=np.int32)],
+    }
+    for dt, arrs in cases.items():
+        ins = [dev.upload(a) for a in arrs]
+        outs = [dev.alloc(a.nbytes) for a in arrs]
+        idx = [dev.alloc(a.size * 8) for a in arrs]
+        ns = [a.size for a in arrs]
+        dev.sort(dt, ins, outs, ns)
+        dev.argsort(dt, ins, idx, ns)
+        for a, o, ix in zip(arrs, outs, idx):
+            got = dev.download(o, a.size, dt)
+            assert np.array_equal(got, np.sort(a), equal_nan=True), dt
+            perm = dev.download(ix, a.size, np.int64)
+            want = np.argsort(a, kind="stable")
+            assert np.array_equal(a[perm], a[want], equal_nan=True) and (np.array_equal(perm, want) or np.isnan(a).any() or (a == 0).any()), dt
+        for p in ins + outs + idx:
+            dev.free(p)
