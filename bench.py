@@ -279,13 +279,15 @@ def run_ours(args) -> dict | None:
         harness = None
         try:
             harness = E2EHarness(args, world, local)
-            inflight = args.e2e_inflight if args.e2e_inflight > 0 else (16 if world <= 2 else 8)
+            # admission per GPU: 16 is the optimum while the host CPUs keep up; with more GPUs than that the
+            # job's CPU quota is shared — one admitted request per available CPU, at least 8 (N = 8 on a 96-CPU quota: 12)
+            inflight = args.e2e_inflight if args.e2e_inflight > 0 else (16 if world <= 2 else max(8, min(16, effective_cores()[0] // world)))
             e2e = harness.run("c1", args.e2e_requests, dist, rank, n, inflight)
             e2e["parity_6sigma"] = e2e["parity"]
             for name in which:
                 try:
                     sample = BC.E2E_SAMPLE[name] if not name.startswith("c4") else max(16, BC.E2E_SAMPLE[name] // world)
-                    got = harness.run(name, sample, dist, rank, n, BC_INFLIGHT[name] if world <= 2 else max(8, BC_INFLIGHT[name] // 2))
+                    got = harness.run(name, sample, dist, rank, n, BC_INFLIGHT[name] if world <= 2 else max(inflight, BC_INFLIGHT[name] // 2))
                 except Exception as e:
                     got = {"value": None, "error": repr(e)}
                 if isinstance(cfg.get(name), dict):
