@@ -278,10 +278,10 @@ def run_ours(args) -> dict | None:
     if args.e2e_requests > 0:
         harness = None
         try:
-            harness = E2EHarness(args, world, local)
             # admission per GPU: 16 is the optimum while the host CPUs keep up; with more GPUs than that the
             # job's CPU quota is shared — one admitted request per available CPU, at least 8 (N = 8 on a 96-CPU quota: 12)
             inflight = args.e2e_inflight if args.e2e_inflight > 0 else (16 if world <= 2 else max(8, min(16, effective_cores()[0] // world)))
+            harness = E2EHarness(args, world, local, inflight)
             e2e = harness.run("c1", args.e2e_requests, dist, rank, n, inflight)
             e2e["parity_6sigma"] = e2e["parity"]
             for name in which:
@@ -392,7 +392,7 @@ class E2EHarness:
     one GPU), each with its own LocalGpuExecutor (zygotes, object store), all sharing this rank's broker process.
     Workers are started once and then run one workload after the other on command."""
 
-    def __init__(self, args, world: int, local: int):
+    def __init__(self, args, world: int, local: int, inflight_per_gpu: int = 16):
         from bee_code_interpreter_b200.broker import BrokerProcess
 
         self.args, self.world = args, world
@@ -403,7 +403,9 @@ class E2EHarness:
         self.workers = max(1, args.e2e_workers if args.e2e_workers > 0 else (4 if world <= 2 else 2))
         # forking processes box-wide: the kernel's fork path peaks at 16-32 of them and degrades beyond
         # (profiles/r1_fork_scale.md), so the warm interpreters per service process shrink with world size
-        zygotes = args.e2e_zygotes if args.e2e_zygotes > 0 else max(1, min(4, 32 // (world * self.workers)))
+        # one warm interpreter per admitted request of a worker (each is pinned to its own CPU, executor.py): a request
+        # then never waits behind another one's fork, and children start on a CPU nobody else is starting on
+        zygotes = args.e2e_zygotes if args.e2e_zygotes > 0 else max(1, min(8, inflight_per_gpu // self.workers))
         self.broker = (BrokerProcess(fake_device="fake_device", extra_pythonpath=str(ROOT / "tests")) if DRY
                        else BrokerProcess(device=local))
         self.procs = []
