@@ -15,6 +15,7 @@
 // index from an atomic counter, so a tile only ever waits for tiles that already started:
 // no deadlock; spins are bounded and trap instead of hanging the GPU.  Bit-exact with numpy.
 #include "bci_sort_common.cuh"
+#include <algorithm>
 #include <vector>
 #include <cstring>
 #include <cstdlib>
@@ -444,8 +445,44 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     digit_scan_kernel<<<(unsigned)(B * P), kThreads, 0, c.stream>>>(ghist, trivial);
     BCI_CHECK_LAUNCH();
   }
-  for (int p = 0; p < P; ++p) {
-    const bool first = p == 0, last = p == P - 1;
+  // Passes in which EVERY request of the batch has one digit only (the high bytes of small integers, for instance) move
+  // nothing: they are left out altogether — int64 keys below 2^31 take 5 sweeps instead of 8.  The flags come back
+  // with one small synchronous copy, so this is only done for batches big enough to pay for it; the first and the
+  // last pass always run (they carry the key transforms and fix where the result lands).  Mixed batches keep the
+  // in-kernel copy path.
+  std::vector<int> passes;
+  {
+    size_t total_keys = 0;
+    for (int i = 0; i < B; ++i) total_keys += n[i];
+    std::vector<uint32_t> hflags;
+    if (total_keys >= (1u << 20) && P > 2) {
+      hflags.resize((size_t)B * P);
+      BCI_CUDA(cudaMemcpyAsync(hflags.data(), trivial, hflags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+      BCI_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    for (int p = 0; p < P; ++p) {
+      bool skip = !hflags.empty() && p != 0 && p != P - 1;
+      for (int i = 0; i < B && skip; ++i) skip = n[i] == 0 || hflags[(size_t)i * P + p] != 0;
+      if (!skip) passes.push_back(p);
+    }
+  }
+  if (!PAIRS && (passes.size() & 1)) {
+    // an odd number of sweeps makes the first one write `out` directly, which an in-place sort (in == out) cannot take:
+    // put one of the left-out passes back (the kernel copies it through)
+    bool in_place = false;
+    for (int i = 0; i < B; ++i) in_place = in_place || in[i] == out[i];
+    if (in_place) {
+      for (int p = 1; p < P - 1; ++p)
+        if (std::find(passes.begin(), passes.end(), p) == passes.end()) {
+          passes.insert(std::lower_bound(passes.begin(), passes.end(), p), p);
+          break;
+        }
+    }
+  }
+  const int S = (int)passes.size();
+  for (int j = 0; j < S; ++j) {
+    const int p = passes[j];
+    const bool first = j == 0, last = j == S - 1;
     for (int i = 0; i < B; ++i) {
       Req& q = reqs[i];
       memset(&q, 0, sizeof q);
@@ -454,17 +491,18 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
       uint8_t* keysA = sbase + koff[i];
       q.n = n[i];
       if (!PAIRS) {
-        // in -> A -> out -> A -> out ... (an even number of passes ends in out)
-        q.in0 = first ? in[i] : ((p & 1) ? (const void*)keysA : (const void*)out[i]);
-        q.out = (p & 1) ? out[i] : (void*)keysA;
+        // in -> ... -> A -> out: the buffers alternate so that the LAST sweep writes `out`
+        auto dst_of = [&](int jj) -> void* { return ((S - 1 - jj) & 1) ? (void*)keysA : out[i]; };
+        q.in0 = first ? in[i] : (const void*)dst_of(j - 1);
+        q.out = dst_of(j);
       } else {
         uint8_t* keysB = keysA + kb;
         uint8_t* idxA = keysB + kb;
         uint8_t* idxB = idxA + ib;
-        q.in0 = first ? in[i] : ((p & 1) ? (const void*)keysA : (const void*)keysB);
-        q.in1 = first ? nullptr : ((p & 1) ? (const void*)idxA : (const void*)idxB);
-        q.out = last ? nullptr : ((p & 1) ? (void*)keysB : (void*)keysA);
-        q.s0.i = last ? (int64_t)(intptr_t)out[i] : (int64_t)(intptr_t)((p & 1) ? idxB : idxA);
+        q.in0 = first ? in[i] : ((j & 1) ? (const void*)keysA : (const void*)keysB);
+        q.in1 = first ? nullptr : ((j & 1) ? (const void*)idxA : (const void*)idxB);
+        q.out = last ? nullptr : ((j & 1) ? (void*)keysB : (void*)keysA);
+        q.s0.i = last ? (int64_t)(intptr_t)out[i] : (int64_t)(intptr_t)((j & 1) ? idxB : idxA);
       }
     }
     rc = upload_batch(reqs.data(), B, kSortTile, &bt);

@@ -177,7 +177,8 @@ int bci_argext(int op, int dtype, int B, const void* const* in, const size_t* n,
 /* ---- K7 cumulative sum (numpy.cumsum, 1-D): i32 widens to i64 like numpy ---- */
 int bci_cumsum(int dtype, int B, const void* const* in, void* const* out, const size_t* n);
 
-/* ---- K5 sort (numpy.sort) and stable argsort (numpy.argsort(kind="stable")) -- */
+/* ---- K5 sort (numpy.sort) and stable argsort (numpy.argsort(kind="stable")) --
+ * bci_sort accepts out[i] == in[i] (ndarray.sort, in place); other overlaps are not allowed. */
 int bci_sort(int dtype, int B, const void* const* in, void* const* out, const size_t* n);
 int bci_argsort(int dtype, int B, const void* const* in, int64_t* const* out_idx,
                 const size_t* n);

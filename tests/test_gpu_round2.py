@@ -259,3 +259,36 @@ def test_sort_passes_whose_digit_is_constant_are_copied_not_ranked(dev):
             assert np.array_equal(a[perm], a[want], equal_nan=True) and (np.array_equal(perm, want) or np.isnan(a).any() or (a == 0).any()), dt
         for p in ins + outs + idx:
             dev.free(p)
+
+
+@pytest.mark.gpu
+def test_sort_leaves_out_passes_that_are_constant_for_the_whole_batch(dev):
+    """Batches above 2^20 keys in which every request shares the constant digits run fewer sweeps (odd and even counts,
+    so both ping-pong parities), also when sorting in place: sort and stable argsort stay bit-exact."""
+    rng = np.random.default_rng(13)
+    n = 700_001
+    batches = [
+        [rng.integers(0, 2**31, n, dtype=np.int64), rng.integers(0, 2**24, n, dtype=np.int64)],        # 8 -> 5 sweeps
+        [rng.integers(0, 2**16, n, dtype=np.int64), rng.integers(0, 2**9, n, dtype=np.int64)],         # 8 -> 3
+        [rng.integers(0, 2**24, n, dtype=np.int64)] * 2,                                                # 8 -> 4
+        [rng.integers(0, 256, n, dtype=np.int32), rng.integers(0, 3, n, dtype=np.int32)],               # 4 -> 2
+        [rng.integers(0, 2**16, n, dtype=np.int32), rng.integers(0, 2**16, n, dtype=np.int32)],         # 4 -> 3
+        [rng.integers(0, 2**8, n, dtype=np.int64) << 40, (rng.integers(0, 2**8, n, dtype=np.int64) << 40) + 5],  # middle digit only
+        [1.0 + rng.random(n), 1.5 + rng.random(n) / 4],                                                 # f64 in one binade
+    ]
+    for arrs in batches:
+        dt = arrs[0].dtype.type
+        ns = [a.size for a in arrs]
+        ins = [dev.upload(a) for a in arrs]
+        outs = [dev.alloc(a.nbytes) for a in arrs]
+        idx = [dev.alloc(a.size * 8) for a in arrs]
+        dev.sort(dt, ins, outs, ns)
+        dev.argsort(dt, ins, idx, ns)
+        for a, o, ix in zip(arrs, outs, idx):
+            assert np.array_equal(dev.download(o, a.size, dt), np.sort(a))
+            assert np.array_equal(dev.download(ix, a.size, np.int64), np.argsort(a, kind="stable"))
+        dev.sort(dt, ins, ins, ns)  # in place
+        for a, o in zip(arrs, ins):
+            assert np.array_equal(dev.download(o, a.size, dt), np.sort(a))
+        for p in ins + outs + idx:
+            dev.free(p)
