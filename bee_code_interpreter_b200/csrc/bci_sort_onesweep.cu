@@ -38,6 +38,23 @@ __device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ uint4 ld_status4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// Tile shape of a sweep.  32-bit keys alone: 512 threads x 16 keys = 8192 keys per CTA, 2 CTAs per SM — the same 32
+// resident warps as 4 CTAs of 256, but half the tiles: half the status words to publish and read back, half the
+// look-back depth (the depth is set by how many tiles finish ranking per L2 round trip), half the per-tile prologues
+// (ncu r2r: look-back was 28 % of the instructions and 25 % of the stall samples of the 4096-key form).
+template <typename K, bool PAIRS> struct Sweep {
+  static constexpr int T = (sizeof(K) == 4 && !PAIRS) ? 512 : kThreads;
+  static constexpr int W = T / 32;
+  static constexpr int TILE = T * kSortItems;
+  static constexpr int CTAS = 2;
+};
+
 // ---- all digit histograms in one read ---------------------------------------------------------
 template <typename K>
 __global__ void __launch_bounds__(kThreads)
@@ -136,42 +153,43 @@ digit_scan_kernel(uint32_t* __restrict__ ghist, uint32_t* __restrict__ trivial) 
 // FIRST / LAST pass and full / ragged tile are compile-time: the first version carried them as
 // runtime flags and spent 40 of its 145 instructions per key on predicates and branches (ncu r1c).
 template <typename K, bool PAIRS, bool FIRST, bool LAST>
-// (4 resident CTAs at 64 registers with 24 spilled words beat 3 at 80 registers: 8.38 vs 8.61 ms)
-__global__ void __launch_bounds__(kThreads, (sizeof(K) == 4 && !PAIRS) ? 4 : 2)
+__global__ void __launch_bounds__((Sweep<K, PAIRS>::T), (Sweep<K, PAIRS>::CTAS))
 onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restrict__ tile_start, int B,
                 int pass, int dtype, const uint32_t* __restrict__ gbase, const uint32_t* __restrict__ trivial,
                 uint32_t* __restrict__ status, uint32_t* __restrict__ counter, unsigned int prefetch_tiles) {
   constexpr int P = (int)sizeof(K);
+  constexpr int T = Sweep<K, PAIRS>::T, W = Sweep<K, PAIRS>::W, TILE = Sweep<K, PAIRS>::TILE;
   constexpr bool WRITE_KEYS = !(PAIRS && LAST);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K* skeys = reinterpret_cast<K*>(smem_raw);
-  uint32_t* sidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * kSortTile);
-  uint32_t* warp_hist = sidx + (PAIRS ? kSortTile : 0);  // [kSortWarps][256]
-  uint32_t* goff = warp_hist + kSortWarps * 256;          // [256] global offset - tile-local offset
-  uint32_t* match = goff + 256;                           // [kSortWarps][2][256] peer masks (16-byte aligned: cleared with STS.128)
-  uint32_t* wsum = match + kSortWarps * 512;              // [kSortWarps] (+1: dynamic tile id)
+  uint32_t* sidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * TILE);
+  uint32_t* warp_hist = sidx + (PAIRS ? TILE : 0);  // [W][256]
+  uint32_t* goff = warp_hist + W * 256;             // [256] global offset - tile-local offset
+  uint32_t* match = goff + 256;                     // [W][2][256] peer masks (16-byte aligned: cleared with STS.128);
+                                                    // after the ranking: [W][256] status words of W earlier tiles
+  uint32_t* wsum = match + W * 512;                 // [W] (+1: dynamic tile id)
 
   // tiles are taken in the order CTAs start: whoever a tile waits for is already running
-  if (threadIdx.x == 0) wsum[kSortWarps] = atomicAdd(counter, 1u);
+  if (threadIdx.x == 0) wsum[W] = atomicAdd(counter, 1u);
   {
     // 6 x STS.128 per thread (the scalar loops were 120 of the 1455 warp-instructions per tile)
-    static_assert((kSortWarps * 256) % (4 * kThreads) == 0 && (kSortWarps * 512) % (4 * kThreads) == 0, "vector clear");
+    static_assert((W * 256) % (4 * T) == 0 && (W * 512) % (4 * T) == 0, "vector clear");
     uint4* wh4 = reinterpret_cast<uint4*>(warp_hist);
     uint4* mm4 = reinterpret_cast<uint4*>(match);
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int i = 0; i < kSortWarps * 256 / (4 * kThreads); ++i) wh4[i * kThreads + threadIdx.x] = z;
+    for (int i = 0; i < W * 256 / (4 * T); ++i) wh4[i * T + threadIdx.x] = z;
 #pragma unroll
-    for (int i = 0; i < kSortWarps * 512 / (4 * kThreads); ++i) mm4[i * kThreads + threadIdx.x] = z;
+    for (int i = 0; i < W * 512 / (4 * T); ++i) mm4[i * T + threadIdx.x] = z;
   }
   __syncthreads();
-  const unsigned long long tile = wsum[kSortWarps];
+  const unsigned long long tile = wsum[W];
   const int r = find_req_block(tile_start, B, tile);
   const Req q = reqs[r];
   const unsigned long long tl = tile - q.tile_start;
-  const size_t base = (size_t)tl * kSortTile;
+  const size_t base = (size_t)tl * TILE;
   const size_t rem = (size_t)q.n - base;
-  const int m = rem < (size_t)kSortTile ? (int)rem : kSortTile;
+  const int m = rem < (size_t)TILE ? (int)rem : TILE;
   const int shift = pass * 8;
   const K* __restrict__ src = reinterpret_cast<const K*>(q.in0) + base;
   const uint32_t* __restrict__ srci = reinterpret_cast<const uint32_t*>(q.in1) + base;  // !FIRST only
@@ -182,7 +200,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     K* __restrict__ dstk = reinterpret_cast<K*>(q.out) + base;
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
-      const int i = k * kThreads + (int)threadIdx.x;
+      const int i = k * T + (int)threadIdx.x;
       if (i < m) {
         K x = src[i];
         if constexpr (FIRST) x = to_key<K>(x, dtype);
@@ -200,13 +218,13 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   // this request's run start for digit d of this pass (independent load, issued early)
-  const uint32_t run_start = __ldg(gbase + ((size_t)r * P + pass) * 256 + threadIdx.x);
+  const uint32_t run_start = __ldg(gbase + ((size_t)r * P + pass) * 256 + (threadIdx.x & 255));
   // L2 prefetch of the tile `prefetch_tiles` further on in the same request (whoever takes it):
   // the key loads of a tile are then L2 hits instead of ~1 us HBM round trips under load
   if (prefetch_tiles != 0 && threadIdx.x == 32) {
-    const size_t b2 = base + (size_t)prefetch_tiles * kSortTile;
+    const size_t b2 = base + (size_t)prefetch_tiles * TILE;
     if (b2 < (size_t)q.n) {
-      const size_t cnt = (size_t)q.n - b2 < (size_t)kSortTile ? (size_t)q.n - b2 : (size_t)kSortTile;
+      const size_t cnt = (size_t)q.n - b2 < (size_t)TILE ? (size_t)q.n - b2 : (size_t)TILE;
       const K* a2 = reinterpret_cast<const K*>(q.in0) + b2;
       const uint32_t bytes = (uint32_t)(cnt * sizeof(K)) & ~15u;
       if (bytes != 0 && (reinterpret_cast<uintptr_t>(a2) & 15) == 0)
@@ -298,44 +316,22 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
       }
     }
     __syncthreads();
-    // thread d owns digit d: counts over warps, publish, look back, tile-local digit offsets
+    // Thread d < 256 owns digit d.  Order of the rest of the tile: (1) counts over warps, publish them, tile-local
+    // digit offsets; (2) every thread places its keys in digit order in shared memory — after which the 32 key and
+    // rank registers are free; (3) look back for the counts of the earlier tiles; (4) write the digit runs out.
+    const int d = threadIdx.x;
+    const bool owner = T == 256 || d < 256;
+    uint32_t* my_status = status + (size_t)tile * 256 + d;
+    uint32_t run = 0, local = 0;
     {
-      const int d = threadIdx.x;
-      uint32_t run = 0;
+      if (owner) {
 #pragma unroll
-      for (int w = 0; w < kSortWarps; ++w) {
-        const uint32_t c = warp_hist[w * 256 + d];
-        warp_hist[w * 256 + d] = run;
-        run += c;
-      }
-      uint32_t* my_status = status + (size_t)tile * 256 + d;
-      st_status(my_status, (tl == 0 ? kInclusive : kPartial) | run);
-      uint32_t excl = 0;
-      if (tl > 0) {
-        // walk back over the earlier tiles of this request, 4 status words per round trip
-        // (speculative: words beyond the first INCLUSIVE one are simply ignored)
-        long long back = 1;                        // distance of the next tile to read
-        const long long max_back = (long long)tl;  // down to the request's first tile
-        bool done = false;
-        while (!done) {
-          uint32_t v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            v[j] = (back + j <= max_back) ? ld_status(my_status - (back + j) * 256) : kInclusive;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (done) break;
-            uint32_t x = v[j];
-            for (unsigned spins = 0; (x & kFlagMask) == 0; ++spins) {
-              if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
-              x = ld_status(my_status - (back + j) * 256);
-            }
-            excl += x & kValMask;
-            if (x & kInclusive) done = true;
-          }
-          back += 4;
+        for (int w = 0; w < W; ++w) {
+          const uint32_t c = warp_hist[w * 256 + d];
+          warp_hist[w * 256 + d] = run;
+          run += c;
         }
-        st_status(my_status, kInclusive | (excl + run));
+        st_status(my_status, (tl == 0 ? kInclusive : kPartial) | run);
       }
       uint32_t inc = run;
 #pragma unroll
@@ -343,31 +339,84 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
         const uint32_t y = __shfl_up_sync(0xffffffffu, inc, s);
         if (lane >= s) inc += y;
       }
-      if (lane == 31) wsum[warp] = inc;
+      if (lane == 31 && owner) wsum[warp] = inc;
       __syncthreads();
-      uint32_t wprefix = 0;
-      for (int w = 0; w < warp; ++w) wprefix += wsum[w];
-      const uint32_t local = wprefix + inc - run;  // tile-local start of digit d
-      // fold it into the per-warp prefixes: one shared load per key in the placement below
+      if (owner) {
+        uint32_t wprefix = 0;
+        for (int w = 0; w < warp; ++w) wprefix += wsum[w];
+        local = wprefix + inc - run;  // tile-local start of digit d
+        // fold it into the per-warp prefixes: one shared load per key in the placement below
 #pragma unroll
-      for (int w = 0; w < kSortWarps; ++w) warp_hist[w * 256 + d] += local;
-      goff[d] = run_start + excl - local;
+        for (int w = 0; w < W; ++w) warp_hist[w * 256 + d] += local;
+      }
     }
     __syncthreads();
+    // Look-back by the whole CTA: warp w fetches all 256 status words of the tile (round * W + w + 1) back with two
+    // 16-byte loads per lane and parks them in shared memory; digit d's owner then walks the W words of its digit in
+    // order.  One L2 round trip covers W earlier tiles (the per-thread form took a round trip per 4 tiles and 85
+    // instructions per round, ncu r2r).  Words beyond the first INCLUSIVE one are ignored; a word that is not
+    // published yet is polled by its owner.  The first round's loads are in flight during the placement.
+    const uint32_t tl32 = (uint32_t)tl;
+    uint32_t* lb = match;  // all mask words are zero again and no longer needed
+    auto fetch = [&](uint32_t back0, uint4& v0, uint4& v1) {
+      const uint32_t b = back0 + (uint32_t)warp;
+      v0 = make_uint4(kInclusive, kInclusive, kInclusive, kInclusive);
+      v1 = v0;
+      if (b <= tl32) {
+        const uint32_t* ps = status + ((size_t)tile - b) * 256 + 4 * lane;
+        v0 = ld_status4(ps);
+        v1 = ld_status4(ps + 128);
+      }
+    };
+    uint4 v0, v1;
+    if (tl32 > 0) fetch(1u, v0, v1);
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
       if (FULL || p0 + k * 32 < m) {
-        const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-        const uint32_t lp = wh[d] + rank[k];
+        const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
+        const uint32_t lp = wh[dg] + rank[k];
         skeys[lp] = key[k];
         if constexpr (PAIRS) sidx[lp] = idx[k];
       }
     }
-    __syncthreads();
+    if (tl32 > 0) {
+      uint32_t excl = 0;
+      bool done = !owner;
+      for (uint32_t back0 = 1;;) {
+        *reinterpret_cast<uint4*>(lb + warp * 256 + 4 * lane) = v0;
+        *reinterpret_cast<uint4*>(lb + warp * 256 + 128 + 4 * lane) = v1;
+        __syncthreads();
+        if (!done) {
+#pragma unroll 4
+          for (int j = 0; j < W; ++j) {
+            uint32_t x = lb[j * 256 + d];
+            if ((x & kFlagMask) == 0) {
+              const uint32_t* ps = status + ((size_t)tile - (back0 + (uint32_t)j)) * 256 + d;
+              for (unsigned spins = 0; (x & kFlagMask) == 0; ++spins) {
+                if (spins > (1u << 24)) __trap();  // a protocol bug must not hang the GPU
+                x = ld_status(ps);
+              }
+            }
+            excl += x & kValMask;
+            if (x & kInclusive) { done = true; break; }
+          }
+          if (done) {
+            st_status(my_status, kInclusive | (excl + run));
+            goff[d] = run_start + excl - local;
+          }
+        }
+        if (__syncthreads_and(done)) break;  // also: goff and the staged keys are visible
+        back0 += W;
+        fetch(back0, v0, v1);
+      }
+    } else {
+      if (owner) goff[d] = run_start - local;
+      __syncthreads();
+    }
     K* __restrict__ dst = reinterpret_cast<K*>(q.out);
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
-      const int i = k * kThreads + (int)threadIdx.x;
+      const int i = k * T + (int)threadIdx.x;
       if (FULL || i < m) {
         const K x = skeys[i];
         const uint32_t d = (uint32_t)(x >> shift) & 255u;
@@ -380,14 +429,14 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
       }
     }
   };
-  if (m == kSortTile) body(std::true_type{});
+  if (m == TILE) body(std::true_type{});
   else body(std::false_type{});
 }
 
 template <typename K, bool PAIRS>
 size_t onesweep_smem() {
-  return sizeof(K) * kSortTile + (PAIRS ? sizeof(uint32_t) * kSortTile : 0) +
-         sizeof(uint32_t) * (kSortWarps * 256 + 256 + kSortWarps + 1 + kSortWarps * 512);
+  constexpr int W = Sweep<K, PAIRS>::W, TILE = Sweep<K, PAIRS>::TILE;
+  return sizeof(K) * TILE + (PAIRS ? sizeof(uint32_t) * TILE : 0) + sizeof(uint32_t) * (W * 256 + 256 + W + 1 + W * 512);
 }
 
 template <typename K, bool PAIRS>
@@ -402,8 +451,12 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  size_t total_tiles = 0;
-  for (int i = 0; i < B; ++i) total_tiles += (n[i] + kSortTile - 1) / kSortTile;
+  constexpr int T = Sweep<K, PAIRS>::T, TILE = Sweep<K, PAIRS>::TILE;
+  size_t total_tiles = 0, hist_tiles = 0;  // sweep tiles (TILE keys) and histogram tiles (kSortTile keys)
+  for (int i = 0; i < B; ++i) {
+    total_tiles += (n[i] + TILE - 1) / TILE;
+    hist_tiles += (n[i] + kSortTile - 1) / kSortTile;
+  }
   if (total_tiles == 0) return BCI_OK;
   if (total_tiles > 0x7fffffffull) { set_error("bci_sort: batch too large for one launch"); return BCI_ERR_INVALID; }
   // scratch: [counters P][ghist B*P*256][status total_tiles*256] [per request: keysA (+keysB, idxA, idxB)]
@@ -439,8 +492,8 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
   rc = upload_batch(reqs.data(), B, kSortTile, &bt);
   if (rc != BCI_OK) return rc;
   {
-    const unsigned grid = (unsigned)(total_tiles < (size_t)c.sm_count * 8 ? total_tiles : (size_t)c.sm_count * 8);
-    digit_hist_kernel<K><<<grid, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, total_tiles, dtype, ghist);
+    const unsigned grid = (unsigned)(hist_tiles < (size_t)c.sm_count * 8 ? hist_tiles : (size_t)c.sm_count * 8);
+    digit_hist_kernel<K><<<grid, kThreads, 0, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, hist_tiles, dtype, ghist);
     BCI_CHECK_LAUNCH();
     digit_scan_kernel<<<(unsigned)(B * P), kThreads, 0, c.stream>>>(ghist, trivial);
     BCI_CHECK_LAUNCH();
@@ -505,21 +558,21 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
         q.s0.i = last ? (int64_t)(intptr_t)out[i] : (int64_t)(intptr_t)((j & 1) ? idxB : idxA);
       }
     }
-    rc = upload_batch(reqs.data(), B, kSortTile, &bt);
+    rc = upload_batch(reqs.data(), B, TILE, &bt);
     if (rc != BCI_OK) return rc;
     BCI_CUDA(cudaMemsetAsync(status, 0, total_tiles * 256 * sizeof(uint32_t), c.stream));
     const unsigned grid = (unsigned)total_tiles;
     const size_t smem = onesweep_smem<K, PAIRS>();
-    // ~ one wave of resident CTAs ahead; measured f32/i64/argsort: off 8.37/22.24/10.94 ms,
+    // ~ one wave of resident CTAs ahead; measured with 4096-key tiles, f32/i64/argsort: off 8.37/22.24/10.94 ms,
     // 600 tiles 8.28/21.64/10.66, 1200 8.31/22.21/10.89, 2400 = off
-    unsigned int prefetch_tiles = 600;
+    unsigned int prefetch_tiles = 600u * (unsigned)kSortTile / (unsigned)TILE;
     if (const char* pf = tuning_env("BCI_SORT_PREFETCH")) prefetch_tiles = (unsigned int)atoi(pf);
     if (first)
-      onesweep_kernel<K, PAIRS, true, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
+      onesweep_kernel<K, PAIRS, true, false><<<grid, T, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
     else if (last)
-      onesweep_kernel<K, PAIRS, false, true><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
+      onesweep_kernel<K, PAIRS, false, true><<<grid, T, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
     else
-      onesweep_kernel<K, PAIRS, false, false><<<grid, kThreads, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
+      onesweep_kernel<K, PAIRS, false, false><<<grid, T, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
     BCI_CHECK_LAUNCH();
   }
   return BCI_OK;
