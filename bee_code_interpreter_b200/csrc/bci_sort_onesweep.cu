@@ -53,7 +53,7 @@ template <typename K, bool PAIRS> struct Sweep {
   static constexpr int T = (sizeof(K) == 4 && !PAIRS) ? 512 : kThreads;
   static constexpr int W = T / 32;
   static constexpr int TILE = T * kSortItems;
-  static constexpr int CTAS = 2;
+  static constexpr int CTAS = T == 512 ? 2 : 3;
 };
 
 // ---- all digit histograms in one read ---------------------------------------------------------
@@ -164,24 +164,21 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K* skeys = reinterpret_cast<K*>(smem_raw);
   uint32_t* sidx = reinterpret_cast<uint32_t*>(smem_raw + sizeof(K) * TILE);
-  uint32_t* warp_hist = sidx + (PAIRS ? TILE : 0);  // [W][256]
-  uint32_t* goff = warp_hist + W * 256;             // [256] global offset - tile-local offset
-  uint32_t* match = goff + 256;                     // [W][2][256] peer masks (16-byte aligned: cleared with STS.128);
-                                                    // after the ranking: [W][256] status words of W earlier tiles
-  uint32_t* wsum = match + W * 512;                 // [W] (+1: dynamic tile id)
+  uint32_t* tab = sidx + (PAIRS ? TILE : 0);  // [2W][256] one table per half-warp: peer mask (low 16 bits) | count << 16,
+                                              // later the tile-local offset of the (half-warp, digit) run
+  uint32_t* goff = tab + 2 * W * 256;         // [256] global offset - tile-local offset
+  uint32_t* lb = goff + 256;                  // [W][256] status words of W earlier tiles (look-back)
+  uint32_t* wsum = lb + W * 256;              // [W] (+1: dynamic tile id)
 
   // tiles are taken in the order CTAs start: whoever a tile waits for is already running
   if (threadIdx.x == 0) wsum[W] = atomicAdd(counter, 1u);
   {
-    // 6 x STS.128 per thread (the scalar loops were 120 of the 1455 warp-instructions per tile)
-    static_assert((W * 256) % (4 * T) == 0 && (W * 512) % (4 * T) == 0, "vector clear");
-    uint4* wh4 = reinterpret_cast<uint4*>(warp_hist);
-    uint4* mm4 = reinterpret_cast<uint4*>(match);
+    // 4 x STS.128 per thread
+    static_assert((2 * W * 256) % (4 * T) == 0, "vector clear");
+    uint4* t4 = reinterpret_cast<uint4*>(tab);
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-    for (int i = 0; i < W * 256 / (4 * T); ++i) wh4[i * T + threadIdx.x] = z;
-#pragma unroll
-    for (int i = 0; i < W * 512 / (4 * T); ++i) mm4[i * T + threadIdx.x] = z;
+    for (int i = 0; i < 2 * W * 256 / (4 * T); ++i) t4[i * T + threadIdx.x] = z;
   }
   __syncthreads();
   const unsigned long long tile = wsum[W];
@@ -217,7 +214,6 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     return;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
   // this request's run start for digit d of this pass (independent load, issued early)
   const uint32_t run_start = __ldg(gbase + ((size_t)r * P + pass) * 256 + (threadIdx.x & 255));
   // L2 prefetch of the tile `prefetch_tiles` further on in the same request (whoever takes it):
@@ -238,8 +234,14 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
       }
     }
   }
-  uint32_t* wh = warp_hist + warp * 256;
-  const int p0 = warp * (32 * kSortItems) + lane;  // striped: row k of warp w = positions w*512 + k*32 + [0,32)
+  // A ranking unit is a HALF-warp: its 16 lanes hold 16 rows of 16 consecutive keys (256 keys in tile order), and its
+  // table word for a digit carries the row's peer mask in the low half and the running count in the high half, so a
+  // row costs three shared-memory operations on ONE word (OR, read, leader's write of count+popc with the mask
+  // cleared) where the warp-wide form with separate mask and counter arrays took five — and the digit-indexed
+  // accesses are what saturates the shared-memory pipe (3.3-way bank conflicts each, ncu r2t).
+  const int l16 = lane & 15;
+  uint32_t* wh = tab + (threadIdx.x >> 4) * 256;
+  const int p0 = (threadIdx.x >> 4) * (16 * kSortItems) + l16;  // row k of unit u = positions u*256 + k*16 + [0,16)
 
   auto body = [&](auto full_c) {
     constexpr bool FULL = decltype(full_c)::value;
@@ -248,72 +250,37 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     uint32_t rank[kSortItems];
     // every load of the tile is issued before anything consumes one
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) key[k] = (FULL || p0 + k * 32 < m) ? src[p0 + k * 32] : K(0);
+    for (int k = 0; k < kSortItems; ++k) key[k] = (FULL || p0 + k * 16 < m) ? src[p0 + k * 16] : K(0);
     if constexpr (PAIRS) {
 #pragma unroll
       for (int k = 0; k < kSortItems; ++k) {
-        if constexpr (FIRST) idx[k] = (uint32_t)(base + p0 + k * 32);
-        else idx[k] = (FULL || p0 + k * 32 < m) ? srci[p0 + k * 32] : 0u;
+        if constexpr (FIRST) idx[k] = (uint32_t)(base + p0 + k * 16);
+        else idx[k] = (FULL || p0 + k * 16 < m) ? srci[p0 + k * 16] : 0u;
       }
     }
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
       if constexpr (FIRST) key[k] = to_key<K>(key[k], dtype);
-      if constexpr (!FULL) key[k] = (p0 + k * 32 < m) ? key[k] : ~K(0);
+      if constexpr (!FULL) key[k] = (p0 + k * 16 < m) ? key[k] : ~K(0);
     }
-    if constexpr (FULL) {
-      // Peers of a row = lanes with the same digit.  Each lane ORs its bit into a per-warp,
-      // per-digit mask word in shared memory and reads the word back: 2 shared-memory
-      // instructions per key where 8 ballots + their selects cost ~45 (ncu r1c: this kernel
-      // is issue-bound at 130-145 instructions per key).  Two rows per step on two mask
-      // arrays; the row leader (lowest peer lane) bumps the warp's digit counter and clears
-      // the mask word, so the arrays are all-zero again when the tile is done.
-      const unsigned my_bit = 1u << lane;
-      uint32_t* mm = match + warp * 512;
-#pragma unroll
-      for (int k = 0; k < kSortItems; k += 2) {
-        const uint32_t d0 = (uint32_t)(key[k] >> shift) & 255u;
-        const uint32_t d1 = (uint32_t)(key[k + 1] >> shift) & 255u;
-        atomicOr(&mm[d0], my_bit);
-        atomicOr(&mm[256 + d1], my_bit);
-        __syncwarp();
-        // every peer reads the digit's running count itself (same address: one broadcast load)
-        // instead of having the leader shuffle it out
-        const unsigned m0 = mm[d0], m1 = mm[256 + d1];
-        const uint32_t c0 = wh[d0];
-        __syncwarp();  // masks and row k's count are read before the leader touches them
-        if (my_bit == (m0 & (0u - m0))) { wh[d0] = c0 + (uint32_t)__popc(m0); mm[d0] = 0; }
-        __syncwarp();  // row k's counter update is visible to row k+1
-        const uint32_t c1 = wh[d1];
-        __syncwarp();
-        if (my_bit == (m1 & (0u - m1))) { wh[d1] = c1 + (uint32_t)__popc(m1); mm[256 + d1] = 0; }
-        rank[k] = c0 + (uint32_t)__popc(m0 & lt_mask);
-        rank[k + 1] = c1 + (uint32_t)__popc(m1 & lt_mask);
-        __syncwarp();
-      }
-    } else {
-      // ragged tile (the last one of a request): 8 ballots per row + one for validity
+    {
+      // Peers of a row = lanes of the half-warp with the same digit.  Each lane ORs its bit into the unit's word for
+      // its digit and reads the word back; the leader (lowest peer lane) writes the new count with the mask cleared,
+      // so the table is counts-only again when the tile is done.  Lanes past the end of a ragged tile sit out.
+      const unsigned my_bit = 1u << l16;
+      const unsigned lt16 = my_bit - 1u;
 #pragma unroll
       for (int k = 0; k < kSortItems; ++k) {
-        const uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-        const bool valid = p0 + k * 32 < m;
-        unsigned peers = __ballot_sync(0xffffffffu, valid);
-        peers = valid ? peers : ~peers;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          const bool bit = (d >> b) & 1u;
-          const unsigned mb = __ballot_sync(0xffffffffu, bit);
-          peers &= bit ? mb : ~mb;
-        }
-        const int leader = __ffs(peers) - 1;
-        uint32_t cnt = 0;
-        if (lane == leader && valid) {
-          cnt = wh[d];
-          wh[d] = cnt + (uint32_t)__popc(peers);
-        }
-        cnt = __shfl_sync(0xffffffffu, cnt, leader);
-        rank[k] = cnt + (uint32_t)__popc(peers & lt_mask);
+        const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
+        const bool valid = FULL || p0 + k * 16 < m;
+        if (valid) atomicOr(&wh[dg], my_bit);
         __syncwarp();
+        const uint32_t w = wh[dg];
+        __syncwarp();  // every peer has read the word before the leader rewrites it
+        const uint32_t peers = w & 0xffffu, cnt = w >> 16;
+        if (valid && my_bit == (peers & (0u - peers))) wh[dg] = (cnt + (uint32_t)__popc(peers)) << 16;
+        rank[k] = cnt + (uint32_t)__popc(peers & lt16);
+        __syncwarp();  // row k's count is visible to row k+1
       }
     }
     __syncthreads();
@@ -327,9 +294,9 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     {
       if (owner) {
 #pragma unroll
-        for (int w = 0; w < W; ++w) {
-          const uint32_t c = warp_hist[w * 256 + d];
-          warp_hist[w * 256 + d] = run;
+        for (int u = 0; u < 2 * W; ++u) {
+          const uint32_t c = tab[u * 256 + d] >> 16;
+          tab[u * 256 + d] = run;
           run += c;
         }
         st_status(my_status, (tl == 0 ? kInclusive : kPartial) | run);
@@ -348,7 +315,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
         local = wprefix + inc - run;  // tile-local start of digit d
         // fold it into the per-warp prefixes: one shared load per key in the placement below
 #pragma unroll
-        for (int w = 0; w < W; ++w) warp_hist[w * 256 + d] += local;
+        for (int u = 0; u < 2 * W; ++u) tab[u * 256 + d] += local;
       }
     }
     __syncthreads();
@@ -358,7 +325,6 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     // instructions per round, ncu r2r).  Words beyond the first INCLUSIVE one are ignored; a word that is not
     // published yet is polled by its owner.  The first round's loads are in flight during the placement.
     const uint32_t tl32 = (uint32_t)tl;
-    uint32_t* lb = match;  // all mask words are zero again and no longer needed
     auto fetch = [&](uint32_t back0, uint4& v0, uint4& v1) {
       const uint32_t b = back0 + (uint32_t)warp;
       v0 = make_uint4(kInclusive, kInclusive, kInclusive, kInclusive);
@@ -373,7 +339,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     if (tl32 > 0) fetch(1u, v0, v1);
 #pragma unroll
     for (int k = 0; k < kSortItems; ++k) {
-      if (FULL || p0 + k * 32 < m) {
+      if (FULL || p0 + k * 16 < m) {
         const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
         const uint32_t lp = wh[dg] + rank[k];
         skeys[lp] = key[k];
