@@ -292,3 +292,36 @@ def test_sort_leaves_out_passes_that_are_constant_for_the_whole_batch(dev):
             assert np.array_equal(dev.download(o, a.size, dt), np.sort(a))
         for p in ins + outs + idx:
             dev.free(p)
+
+
+@pytest.mark.gpu
+def test_sort_sizes_around_the_tile_and_ranking_unit_boundaries(dev):
+    """Every size class of the sweep: below one 16-key row, one 256-key ranking unit +-1, one tile +-1 (4096 keys, 8192
+    for 32-bit keys alone), several tiles with a ragged tail; sorted, reversed and two-valued inputs among them."""
+    rng = np.random.default_rng(14)
+    sizes = [1, 2, 15, 16, 17, 255, 256, 257, 511, 4095, 4096, 4097, 8191, 8192, 8193, 12289, 3 * 8192 - 1, 5 * 8192 + 300]
+    for dt in (np.float32, np.int32, np.int64, np.float64):
+        arrs = []
+        for j, n in enumerate(sizes):
+            if np.issubdtype(dt, np.floating):
+                a = rng.standard_normal(n).astype(dt)
+            else:
+                a = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, n, dtype=dt)
+            if j % 4 == 1:
+                a = np.sort(a)
+            elif j % 4 == 2:
+                a = np.sort(a)[::-1].copy()
+            elif j % 4 == 3:
+                a = np.where(rng.random(n) < 0.5, a[0], a[-1]).astype(dt)
+            arrs.append(a)
+        ns = [a.size for a in arrs]
+        ins = [dev.upload(a) for a in arrs]
+        outs = [dev.alloc(a.nbytes) for a in arrs]
+        idx = [dev.alloc(a.size * 8) for a in arrs]
+        dev.sort(dt, ins, outs, ns)
+        dev.argsort(dt, ins, idx, ns)
+        for a, o, ix in zip(arrs, outs, idx):
+            assert np.array_equal(dev.download(o, a.size, dt), np.sort(a)), (dt, a.size)
+            assert np.array_equal(dev.download(ix, a.size, np.int64), np.argsort(a, kind="stable")), (dt, a.size)
+        for p_ in ins + outs + idx:
+            dev.free(p_)
