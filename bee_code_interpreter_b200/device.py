@@ -239,6 +239,38 @@ def reduce_fused(op: int, ew_op: int, dtype, in0: Sequence[int], in1: Sequence[i
     return _decode_results(raw, op, code)
 
 
+def prepared_reduce(op: int, dtype, in_ptrs: Sequence[int], ns: Sequence[int], pre: int = _lib.PRE_NONE):
+    """`reduce` with the pointer / size tables marshalled once: returns a callable that launches and returns the
+    results.  The broker builds these tables in C++; a Python caller that launches the same batch repeatedly
+    (bench_configs.py) would otherwise spend 0.1-0.3 ms per call converting 1024-entry lists (tools/prof_c3.py)."""
+    code = dtype_code(dtype)
+    B = len(in_ptrs)
+    raw = np.zeros(B, dtype=np.uint64)
+    fn, a0, n, out = _lib.load().bci_reduce, _lib.ptr_array(in_ptrs), _lib.size_array(ns), C.c_void_p(raw.ctypes.data)
+
+    def call() -> np.ndarray:
+        _lib.check(fn(op, pre, code, B, a0, n, out))
+        return _decode_results(raw, op, code)
+    return call
+
+
+def prepared_reduce_fused(op: int, ew_op: int, dtype, in0: Sequence[int], in1: Sequence[int] | None,
+                          scalars: Sequence | None, ns: Sequence[int], pre: int = _lib.PRE_NONE,
+                          addends: Sequence | None = None):
+    """`reduce_fused` with its tables marshalled once (see prepared_reduce)."""
+    code = dtype_code(dtype)
+    B = len(in0)
+    raw = np.zeros(B, dtype=np.uint64)
+    fn = _lib.load().bci_reduce_fused
+    a0, a1 = _lib.ptr_array(in0), (_lib.ptr_array(in1) if in1 is not None else None)
+    sc, ad, n, out = _scalars(scalars, code, B), _scalars(addends, code, B), _lib.size_array(ns), C.c_void_p(raw.ctypes.data)
+
+    def call() -> np.ndarray:
+        _lib.check(fn(op, pre, ew_op, code, B, a0, a1, sc, ad, n, out))
+        return _decode_results(raw, op, code)
+    return call
+
+
 def argext(op: int, dtype, in_ptrs: Sequence[int], ns: Sequence[int]) -> np.ndarray:
     code = dtype_code(dtype)
     B = len(in_ptrs)

@@ -183,6 +183,14 @@ def reduce(op, dtype, in_ptrs, ns, pre=L.PRE_NONE):
         return np.array([RED[op](PRE[pre](_view(p, n, dtype))) for p, n in zip(in_ptrs, ns)])
 
 
+def prepared_reduce(op, dtype, in_ptrs, ns, pre=L.PRE_NONE):
+    return lambda: reduce(op, dtype, in_ptrs, ns, pre)
+
+
+def prepared_reduce_fused(op, ew_op, dtype, in0, in1, scalars, ns, pre=L.PRE_NONE, addends=None):
+    return lambda: reduce_fused(op, ew_op, dtype, in0, in1, scalars, ns, pre, addends)
+
+
 def reduce_fused(op, ew_op, dtype, in0, in1, scalars, ns, pre=L.PRE_NONE, addends=None):
     calls.append(("reduce_fused", len(in0), (op, ew_op, pre, addends is not None)))
     dtype = np.dtype(dtype)

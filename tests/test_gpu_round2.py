@@ -325,3 +325,24 @@ def test_sort_sizes_around_the_tile_and_ranking_unit_boundaries(dev):
             assert np.array_equal(dev.download(ix, a.size, np.int64), np.argsort(a, kind="stable")), (dt, a.size)
         for p_ in ins + outs + idx:
             dev.free(p_)
+
+
+@pytest.mark.gpu
+def test_prepared_reductions_return_what_the_plain_calls_return(dev):
+    """device.prepared_reduce / prepared_reduce_fused marshal the tables once; repeated calls give the plain calls' bits."""
+    from bee_code_interpreter_b200 import _lib as L
+    rng = np.random.default_rng(15)
+    xs = [rng.random(n, dtype=np.float32) for n in (1, 1000, 2**20, 2**20 + 3)]
+    ys = [rng.random(a.size, dtype=np.float32) for a in xs]
+    X, Y, ns = [dev.upload(a) for a in xs], [dev.upload(a) for a in ys], [a.size for a in xs]
+    k1 = dev.prepared_reduce(L.RED_SUM, np.float32, X, ns, pre=L.PRE_SQUARE)
+    k2 = dev.prepared_reduce_fused(L.RED_MEAN, L.EW_MUL, np.float32, X, Y, None, ns, addends=[1.0] * len(ns))
+    k3 = dev.prepared_reduce_fused(L.RED_MAX, L.EW_SUB, np.float32, X, Y, None, ns, pre=L.PRE_ABS)
+    for _ in range(2):
+        assert np.array_equal(k1(), dev.reduce(L.RED_SUM, np.float32, X, ns, pre=L.PRE_SQUARE))
+        assert np.array_equal(k2(), dev.reduce_fused(L.RED_MEAN, L.EW_MUL, np.float32, X, Y, None, ns, addends=[1.0] * len(ns)))
+        assert np.array_equal(k3(), dev.reduce_fused(L.RED_MAX, L.EW_SUB, np.float32, X, Y, None, ns, pre=L.PRE_ABS))
+    want = [np.max(np.abs(a - b)) for a, b in zip(xs, ys)]
+    assert np.array_equal(k3(), np.array(want, dtype=np.float32))
+    for p_ in X + Y:
+        dev.free(p_)
