@@ -99,12 +99,17 @@ digit_hist_kernel(const Req* __restrict__ reqs, const unsigned long long* __rest
 #pragma unroll
       for (int k = 0; k < kSortItems; ++k) {
         const K key = to_key<K>(keys[k], dtype);
+        // Constant digits (exponent byte, high bytes of small integers) would serialise 32 same-address shared
+        // atomics: one add per uniform row instead.  Which bytes are uniform across the row comes from ONE warp
+        // reduction per 32 key bits (OR of key ^ lane 0's key) instead of a shuffle + vote per digit.
+        const K x = key ^ __shfl_sync(0xffffffffu, key, 0);
+        uint32_t diff_lo = __reduce_or_sync(0xffffffffu, (uint32_t)x), diff_hi = 0;
+        if constexpr (sizeof(K) == 8) diff_hi = __reduce_or_sync(0xffffffffu, (uint32_t)((unsigned long long)x >> 32));
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           const uint32_t d = (uint32_t)(key >> (8 * p)) & 255u;
-          // constant digits (exponent byte, high bytes of small integers) would serialise 32
-          // same-address shared atomics: one add per uniform row instead
-          if (__all_sync(0xffffffffu, d == __shfl_sync(0xffffffffu, d, 0))) {
+          const uint32_t diff = ((p < 4 ? diff_lo : diff_hi) >> (8 * (p & 3))) & 255u;
+          if (diff == 0) {  // warp-uniform
             if (lane == 0) atomicAdd(&sh[p][d], 32u);
           } else {
             atomicAdd(&sh[p][d], 1u);
