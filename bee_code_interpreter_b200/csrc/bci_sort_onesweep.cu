@@ -149,7 +149,11 @@ digit_scan_kernel(uint32_t* __restrict__ ghist, uint32_t* __restrict__ trivial) 
   for (int w = 0; w < kSortWarps; ++w) { if (w < warp) wprefix += wsum[w]; total += wsum[w]; }
   h[threadIdx.x] = wprefix + inc - c;
   const int one_digit = __syncthreads_or(total != 0 && c == total);
-  if (threadIdx.x == 0) trivial[blockIdx.x] = one_digit ? 1u : 0u;
+  // 2 = skewed: one digit holds more than a quarter of the keys (sign/exponent byte of floats, a byte with a handful of
+  // values in small integers): the sweep then matches peers with ballots over the few digit bits that differ in a row
+  // instead of shared-memory atomics that would pile up on one or two words
+  const int skewed = __syncthreads_or(total != 0 && c > total / 4);
+  if (threadIdx.x == 0) trivial[blockIdx.x] = one_digit ? 1u : (skewed ? 2u : 0u);
 }
 
 // ---- one pass -----------------------------------------------------------------------------------
@@ -196,7 +200,8 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   const int shift = pass * 8;
   const K* __restrict__ src = reinterpret_cast<const K*>(q.in0) + base;
   const uint32_t* __restrict__ srci = reinterpret_cast<const uint32_t*>(q.in1) + base;  // !FIRST only
-  if (__ldg(trivial + (size_t)r * P + pass)) {
+  const uint32_t pass_kind = __ldg(trivial + (size_t)r * P + pass);
+  if (pass_kind == 1u) {
     // every key of this request carries the same digit in this pass: nothing moves.  Copy the tile (with the key
     // transform of a first / last pass) — ~10 instructions per key instead of a ranking pass; no status is published,
     // the other tiles of this request take the same branch.
@@ -274,6 +279,40 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
       // so the table is counts-only again when the tile is done.  Lanes past the end of a ragged tile sit out.
       const unsigned my_bit = 1u << l16;
       const unsigned lt16 = my_bit - 1u;
+      if (FULL && pass_kind == 2u) {
+        // skewed pass: in most rows only two or three digit BITS differ across the warp (one warp OR-reduction tells
+        // which); peers then come from one ballot per differing bit and nobody touches the table with an atomic
+        const unsigned half_mask = 0xffffu << (lane & 16);
+        const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+        for (int k = 0; k < kSortItems; ++k) {
+          const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
+          uint32_t diff = __reduce_or_sync(0xffffffffu, dg ^ __shfl_sync(0xffffffffu, dg, 0));
+          if (__popc(diff) <= 4) {
+            unsigned peers = half_mask;
+            while (diff) {
+              const uint32_t bit = diff & (0u - diff);
+              diff ^= bit;
+              const unsigned mb = __ballot_sync(0xffffffffu, (dg & bit) != 0);
+              peers &= (dg & bit) ? mb : ~mb;
+            }
+            const uint32_t cnt = wh[dg] >> 16;
+            __syncwarp();  // every peer has read the count before the leader rewrites it
+            if (lane == __ffs(peers) - 1) wh[dg] = (cnt + (uint32_t)__popc(peers)) << 16;
+            rank[k] = cnt + (uint32_t)__popc(peers & below);
+            __syncwarp();
+          } else {
+            atomicOr(&wh[dg], my_bit);
+            __syncwarp();
+            const uint32_t w = wh[dg];
+            __syncwarp();
+            const uint32_t peers = w & 0xffffu, cnt = w >> 16;
+            if (my_bit == (peers & (0u - peers))) wh[dg] = (cnt + (uint32_t)__popc(peers)) << 16;
+            rank[k] = cnt + (uint32_t)__popc(peers & lt16);
+            __syncwarp();
+          }
+        }
+      } else
 #pragma unroll
       for (int k = 0; k < kSortItems; ++k) {
         const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
@@ -487,7 +526,7 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     }
     for (int p = 0; p < P; ++p) {
       bool skip = !hflags.empty() && p != 0 && p != P - 1;
-      for (int i = 0; i < B && skip; ++i) skip = n[i] == 0 || hflags[(size_t)i * P + p] != 0;
+      for (int i = 0; i < B && skip; ++i) skip = n[i] == 0 || hflags[(size_t)i * P + p] == 1u;
       if (!skip) passes.push_back(p);
     }
   }

@@ -38,6 +38,8 @@ def run(name, arrs, arg=False, reps=5):
 
 a32 = rng.standard_normal(10**7).astype(np.float32)
 run("sort f32 32 x 1e7", [a32] * 32)
+run("sort f32 uniform [0,1) 32 x 1e7  (C5's column)", [rng.random(10**7, dtype=np.float32)] * 32)
+run("sort i64 in [0, 1000) 16 x 1e7", [rng.integers(0, 1000, 10**7, dtype=np.int64)] * 16)
 run("sort f32 1 x 1e7", [a32])
 run("sort i64 16 x 1e7", [rng.integers(-2**63, 2**63 - 1, 10**7, dtype=np.int64)] * 16)
 run("sort f64 16 x 1e7", [rng.standard_normal(10**7)] * 16)
