@@ -457,6 +457,7 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
   static bool attr_set = false;
   if (!attr_set) {
     const int smem = (int)onesweep_smem<K, PAIRS>();
+    BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     BCI_CUDA(cudaFuncSetAttribute(onesweep_kernel<K, PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -510,25 +511,26 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     BCI_CHECK_LAUNCH();
   }
   // Passes in which EVERY request of the batch has one digit only (the high bytes of small integers, for instance) move
-  // nothing: they are left out altogether — int64 keys below 2^31 take 5 sweeps instead of 8.  The flags come back
-  // with one small synchronous copy, so this is only done for batches big enough to pay for it; the first and the
-  // last pass always run (they carry the key transforms and fix where the result lands).  Mixed batches keep the
-  // in-kernel copy path.
+  // nothing: they are left out altogether — int64 keys below 2^31 take 4 sweeps instead of 8.  The flags come back
+  // with one small synchronous copy, so this is only done for batches big enough to pay for it.  The key transforms
+  // belong to the first and the last sweep that RUN, whichever digits they are; a batch whose passes are all constant
+  // keeps one sweep (the copy).  Mixed batches keep the in-kernel copy path.
   std::vector<int> passes;
   {
     size_t total_keys = 0;
     for (int i = 0; i < B; ++i) total_keys += n[i];
     std::vector<uint32_t> hflags;
-    if (total_keys >= (1u << 20) && P > 2) {
+    if (total_keys >= (1u << 20)) {
       hflags.resize((size_t)B * P);
       BCI_CUDA(cudaMemcpyAsync(hflags.data(), trivial, hflags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
       BCI_CUDA(cudaStreamSynchronize(c.stream));
     }
     for (int p = 0; p < P; ++p) {
-      bool skip = !hflags.empty() && p != 0 && p != P - 1;
+      bool skip = !hflags.empty();
       for (int i = 0; i < B && skip; ++i) skip = n[i] == 0 || hflags[(size_t)i * P + p] == 1u;
       if (!skip) passes.push_back(p);
     }
+    if (passes.empty()) passes.push_back(0);
   }
   if (!PAIRS && (passes.size() & 1)) {
     // an odd number of sweeps makes the first one write `out` directly, which an in-place sort (in == out) cannot take:
@@ -536,7 +538,7 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     bool in_place = false;
     for (int i = 0; i < B; ++i) in_place = in_place || in[i] == out[i];
     if (in_place) {
-      for (int p = 1; p < P - 1; ++p)
+      for (int p = 0; p < P; ++p)
         if (std::find(passes.begin(), passes.end(), p) == passes.end()) {
           passes.insert(std::lower_bound(passes.begin(), passes.end(), p), p);
           break;
@@ -578,7 +580,9 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     // 600 tiles 8.28/21.64/10.66, 1200 8.31/22.21/10.89, 2400 = off
     unsigned int prefetch_tiles = 600u * (unsigned)kSortTile / (unsigned)TILE;
     if (const char* pf = tuning_env("BCI_SORT_PREFETCH")) prefetch_tiles = (unsigned int)atoi(pf);
-    if (first)
+    if (first && last)
+      onesweep_kernel<K, PAIRS, true, true><<<grid, T, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
+    else if (first)
       onesweep_kernel<K, PAIRS, true, false><<<grid, T, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
     else if (last)
       onesweep_kernel<K, PAIRS, false, true><<<grid, T, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);

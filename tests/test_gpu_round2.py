@@ -268,11 +268,11 @@ def test_sort_leaves_out_passes_that_are_constant_for_the_whole_batch(dev):
     rng = np.random.default_rng(13)
     n = 700_001
     batches = [
-        [rng.integers(0, 2**31, n, dtype=np.int64), rng.integers(0, 2**24, n, dtype=np.int64)],        # 8 -> 5 sweeps
-        [rng.integers(0, 2**16, n, dtype=np.int64), rng.integers(0, 2**9, n, dtype=np.int64)],         # 8 -> 3
-        [rng.integers(0, 2**24, n, dtype=np.int64)] * 2,                                                # 8 -> 4
-        [rng.integers(0, 256, n, dtype=np.int32), rng.integers(0, 3, n, dtype=np.int32)],               # 4 -> 2
-        [rng.integers(0, 2**16, n, dtype=np.int32), rng.integers(0, 2**16, n, dtype=np.int32)],         # 4 -> 3
+        [rng.integers(0, 2**31, n, dtype=np.int64), rng.integers(0, 2**24, n, dtype=np.int64)],        # 8 -> 4 sweeps
+        [rng.integers(0, 2**16, n, dtype=np.int64), rng.integers(0, 2**9, n, dtype=np.int64)],         # 8 -> 2
+        [rng.integers(0, 2**24, n, dtype=np.int64)] * 2,                                                # 8 -> 3
+        [rng.integers(0, 256, n, dtype=np.int32), rng.integers(0, 3, n, dtype=np.int32)],               # 4 -> 1
+        [rng.integers(0, 2**16, n, dtype=np.int32), rng.integers(0, 2**16, n, dtype=np.int32)],         # 4 -> 2
         [rng.integers(0, 2**8, n, dtype=np.int64) << 40, (rng.integers(0, 2**8, n, dtype=np.int64) << 40) + 5],  # middle digit only
         [1.0 + rng.random(n), 1.5 + rng.random(n) / 4],                                                 # f64 in one binade
     ]
