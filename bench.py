@@ -383,7 +383,9 @@ def run_ours(args) -> dict | None:
     return out
 
 
-BC_INFLIGHT = {"c2": 16, "c3": 16, "c4": 48, "c4dev": 48, "c5": 16}      # admitted requests per GPU in the e2e arm of each config
+BC_INFLIGHT = {"c2": 32, "c3": 16, "c4": 48, "c4dev": 48, "c5": 32}      # admitted requests per GPU in the e2e arm of each config
+for _kv in filter(None, os.environ.get("BCI_BENCH_CFG_INFLIGHT", "").split(",")):      # experiments: "c5=32,c2=24"
+    BC_INFLIGHT[_kv.split("=")[0]] = int(_kv.split("=")[1])
 MIN_JOBS = {"c1": 1, "c2": 6, "c3": 5, "c4": 1, "c4dev": 2, "c5": 5}     # broker jobs one request of each workload must cause
 
 

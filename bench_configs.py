@@ -347,7 +347,7 @@ def run_device_arms(dev, L, rank, world, dist, peaks, which, log) -> dict:
 
 
 # ---- request scripts + expected stdout for the e2e arms and the CPU baselines -----------------------------------------
-E2E_SAMPLE = {"c2": 192, "c3": 2048, "c4": 96, "c4dev": 96, "c5": 192}       # requests per GPU in the e2e arms (bounded samples)
+E2E_SAMPLE = {"c2": 768, "c3": 2048, "c4": 96, "c4dev": 96, "c5": 768}       # requests per GPU in the e2e arms (bounded samples)
 if os.environ.get("BCI_BENCH_DRY"):
     E2E_SAMPLE = {"c2": 4, "c3": 8, "c4": 4, "c4dev": 4, "c5": 4}
 CPU_SAMPLE_ROUNDS = {"c2": 1, "c3": 2, "c4": 1, "c5": 1}
