@@ -594,6 +594,69 @@ def argsort(a, axis=-1, kind=None, order=None, **kw):
     return DeviceArray(be, be.argsort_new(a.dtype, a._device_ptr(), a.size), a.shape, np.int64)
 
 
+# ---- order statistics: one device sort, then two or three elements cross the bus -------------------------------
+# numpy partitions the array around the indices it needs (introselect) and interpolates between at most two elements.
+# The same elements come out of the sorted array; the interpolation is done by numpy itself on a two-element stand-in
+# (np.mean / np.quantile), so type rules and rounding are numpy's.
+def _sorted_elem(s, i: int):
+    return s._backend.download(s._device_ptr(), 1, s.dtype, int(i))[0]
+
+
+def _order_stat_operand(a, axis, out, kw):
+    a = _need_dev(a)
+    if out is not None or any(kw.get(k) for k in ("keepdims", "overwrite_input")) or set(kw) - {"keepdims", "overwrite_input"}:
+        raise _Fallback("kwargs")
+    if a.ndim != 1 or axis not in (None, 0, -1) or a.dtype not in SUPPORTED or a.size < 2:
+        raise _Fallback("shape")
+    return a
+
+
+def _np_median(a, axis=None, out=None, **kw):
+    a = _order_stat_operand(a, axis, out, kw)
+    n = a.size
+    s = sort(a)
+    if a.dtype.kind == "f" and np.isnan(_sorted_elem(s, n - 1)):      # NaNs sort last; numpy's median is NaN then
+        return np.median(np.array([np.nan, np.nan], dtype=a.dtype))
+    mid = np.array([_sorted_elem(s, (n - 1) // 2), _sorted_elem(s, n // 2)], dtype=a.dtype)
+    return np.mean(mid[:1] if n % 2 else mid)       # numpy: mean of the middle element(s)
+
+
+def _np_quantile(a, q, axis=None, out=None, method="linear", **kw):
+    weights = kw.pop("weights", None)
+    a = _order_stat_operand(a, axis, out, kw)
+    if method != "linear" or weights is not None or isinstance(q, DeviceArray):
+        raise _Fallback("method")
+    qa = np.asanyarray(q)
+    if qa.dtype.kind not in "fiu" or qa.ndim > 1 or qa.size > 64 or not np.all((qa >= 0) & (qa <= 1)):
+        raise _Fallback("q")
+    n = a.size
+    s = sort(a)
+    nan = a.dtype.kind == "f" and np.isnan(_sorted_elem(s, n - 1))
+
+    def one(qi, as_array: bool):
+        # `as_array`: numpy promotes differently when q is an array (float32 data then gives float64 results)
+        wrap = (lambda g: np.asanyarray([g])) if as_array else (lambda g: g)
+        if nan:
+            return np.quantile(np.array([np.nan, np.nan], dtype=a.dtype), wrap(qi))
+        vi = (n - 1) * np.asanyarray(qi, dtype=np.float64 if np.asanyarray(qi).dtype.kind != "f" else None)   # numpy: (n - 1) * q
+        prev = int(np.floor(vi))
+        if prev >= n - 1:
+            last = _sorted_elem(s, n - 1)
+            return np.quantile(np.array([last, last], dtype=a.dtype), wrap(qi))
+        pair = np.array([_sorted_elem(s, prev), _sorted_elem(s, prev + 1)], dtype=a.dtype)
+        return np.quantile(pair, wrap(vi - prev))    # same two values, same gamma: numpy's own interpolation
+    if qa.ndim == 0:
+        return one(qa[()], False)
+    return np.concatenate([one(qi, True) for qi in qa]) if qa.size else np.quantile(np.zeros(2, a.dtype), qa)
+
+
+def _np_percentile(a, q, axis=None, out=None, method="linear", **kw):
+    if isinstance(q, DeviceArray):
+        raise _Fallback("q")
+    qa = np.true_divide(q, 100)       # numpy/lib/_function_base_impl.py: percentile = quantile(q / 100)
+    return _np_quantile(a, qa, axis=axis, out=out, method=method, **kw)
+
+
 def matmul(a, b, out=None, **kw):
     if out is not None or kw:
         raise _Fallback("kwargs")
@@ -681,6 +744,7 @@ _FUNCTIONS = {
     np.sum: _np_sum, np.mean: _np_mean, np.max: _np_max, np.min: _np_min, np.amax: _np_max, np.amin: _np_min,
     np.argmax: argmax, np.argmin: argmin, np.cumsum: cumsum, np.sort: sort, np.argsort: argsort,
     np.matmul: matmul, np.dot: _dot, np.var: _var, np.std: _std,
+    np.median: _np_median, np.quantile: _np_quantile, np.percentile: _np_percentile,
 }
 
 

@@ -100,6 +100,12 @@ def test_proxy_on_device_matches_numpy(dev):
     assert np.array_equal(np.asarray(np.sort(x)), np.sort(xh))
     k = P.DeviceArray.from_host(be, rng.integers(0, 2**31, 1 << 20, dtype=np.int64))
     assert np.array_equal(np.asarray(np.cumsum(k)), np.cumsum(np.asarray(k)))
+    # order statistics: one device sort + a few elements; values and types are numpy's
+    kh = np.asarray(k).copy()
+    for f, args in ((np.median, ()), (np.percentile, (95,)), (np.quantile, (0.001,)), (np.percentile, ([25, 50, 75],))):
+        for h, d in ((xh, x), (kh, k)):
+            want, got = f(h, *args), f(d, *args)
+            assert type(want) is type(got) and np.array_equal(np.asarray(want), np.asarray(got)), (f.__name__, args)
 
 
 def test_native_executor_server_runs_scripts_on_the_gpu(executor, tmp_path):

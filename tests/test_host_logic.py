@@ -126,6 +126,36 @@ def test_sort_argmax_cumsum_matmul_entry_points(be):
     assert np.array_equal(np.asarray(x), np.sort(h))
 
 
+def test_median_quantile_percentile_are_one_sort_and_a_few_elements(be):
+    """np.median / np.quantile / np.percentile of a DeviceArray: one device sort, the two neighbouring order statistics
+    (and the last element, for NaN) come back, numpy interpolates — values, dtypes and result types are numpy's."""
+    import warnings
+    rng = np.random.default_rng(0)
+    calls = ((np.median, ()), (np.quantile, (0.3,)), (np.quantile, (np.float32(0.25),)), (np.quantile, (1,)), (np.quantile, (0.0,)),
+             (np.percentile, (37,)), (np.percentile, (100,)), (np.percentile, (0,)), (np.percentile, (np.float32(12.5),)),
+             (np.quantile, ([0.1, 0.5, 0.9],)), (np.percentile, (np.array([5.0, 95.0]),)), (np.percentile, ([25, 50, 75],)))
+    for dt in (np.float32, np.float64, np.int32, np.int64):
+        for n in (2, 3, 10, 11, 1000, 1001):
+            a = (rng.standard_normal(n) * 100).astype(dt)
+            for f, args in calls:
+                x = P.DeviceArray.from_host(be, a)
+                fake_device.calls.clear()
+                want, got = f(a, *args), f(x, *args)
+                assert names(fake_device.calls).count("sort") == 1, (f.__name__, args)
+                assert type(want) is type(got) and np.asarray(want).dtype == np.asarray(got).dtype and np.shape(want) == np.shape(got)
+                assert np.array_equal(np.asarray(want), np.asarray(got)), (dt, n, f.__name__, args)
+    a = np.array([1.0, np.nan, 3.0, 2.0], dtype=np.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for f, args in ((np.median, ()), (np.quantile, (0.5,)), (np.quantile, ([0.5, 0.2],))):
+            x = P.DeviceArray.from_host(be, a)
+            want, got = f(a, *args), f(x, *args)
+            assert np.array_equal(np.asarray(want), np.asarray(got), equal_nan=True) and np.asarray(want).dtype == np.asarray(got).dtype
+    # what the device path does not take falls back to numpy: other methods, 2-D, weights
+    x = P.DeviceArray.from_host(be, a)
+    assert np.quantile(x, 0.5, method="nearest") is not None and np.isnan(np.quantile(x, 0.5, method="nearest"))
+
+
 def test_buffers_are_released(be):
     x = P.device_rand(be, (1000,), seed=1)
     y = np.square(x) + 1.0
