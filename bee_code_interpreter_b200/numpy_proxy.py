@@ -230,6 +230,9 @@ class DeviceArray(NDArrayOperatorsMixin):
                     return _binary(BINARY_UFUNCS[ufunc], inputs[0], inputs[1])
                 if ufunc is np.matmul and len(inputs) == 2:
                     return matmul(inputs[0], inputs[1])
+                if ufunc is np.power and len(inputs) == 2 and _is_two(inputs[1]) and isinstance(inputs[0], DeviceArray) \
+                        and _weak_scalar_ok(inputs[1], inputs[0].dtype):
+                    return _unary(L.EW_SQUARE, inputs[0])   # numpy's power loops square for a scalar exponent of 2
             if method == "reduce" and ufunc in REDUCE_UFUNCS and len(inputs) == 1:
                 # ufunc.reduce defaults to axis=0 (NOT a full reduction for ndim > 1)
                 axis = kwargs.get("axis", 0)
@@ -304,6 +307,25 @@ class DeviceArray(NDArrayOperatorsMixin):
                 pass
         out = _h(self).astype(dtype, *a, **kw)
         return out.copy() if out is self._host else out   # astype(copy=False) must not leak the cache
+
+    def __pow__(self, other, mod=None):
+        # ndarray.__pow__ has scalar fast paths (numpy/_core/src/multiarray/number.c: fast_scalar_power): `x ** 2` IS
+        # np.square(x) and `x ** 0.5` IS np.sqrt(x) for float arrays, bit for bit
+        if mod is None and isinstance(other, (int, float)) and not isinstance(other, bool):
+            try:
+                if other == 2 and _weak_scalar_ok(other, self._dtype):
+                    return _unary(L.EW_SQUARE, self)
+                if other == 0.5 and self._dtype.kind == "f":
+                    return _unary(L.EW_SQRT, self)
+            except (_Fallback, L.Unsupported, L.BciError):
+                pass
+        return NDArrayOperatorsMixin.__pow__(self, other)
+
+    def clip(self, min=None, max=None, out=None, **kw):
+        try:
+            return _np_clip(self, min, max, out=out, **kw)
+        except (_Fallback, L.Unsupported, L.BciError, TypeError):
+            return _h(self).clip(min, max, out=out, **kw)
 
     def __copy__(self):
         return self.copy()
@@ -657,6 +679,68 @@ def _np_percentile(a, q, axis=None, out=None, method="linear", **kw):
     return _np_quantile(a, qa, axis=axis, out=out, method=method, **kw)
 
 
+def _is_two(v) -> bool:
+    return isinstance(v, (int, float, np.integer, np.floating)) and not isinstance(v, (bool, np.bool_)) and v == 2
+
+
+def _np_clip(a, a_min=None, a_max=None, out=None, **kw):
+    """np.clip = minimum(maximum(a, lo), hi) (numpy/_core/_methods.py:_clip), each bound a python scalar."""
+    a = _need_dev(a)
+    lo = kw.pop("min", a_min) if a_min is None else a_min
+    hi = kw.pop("max", a_max) if a_max is None else a_max
+    if out is not None or kw or (lo is None and hi is None) or a.dtype not in SUPPORTED:
+        raise _Fallback("kwargs")
+    for b in (lo, hi):
+        if b is not None and (isinstance(b, DeviceArray) or not _weak_scalar_ok(b, a.dtype) or b != b):
+            raise _Fallback("bound")
+    r = a
+    if lo is not None:
+        r = _binary(L.EW_MAXIMUM, r, lo)
+    if hi is not None:
+        r = _binary(L.EW_MINIMUM, r, hi)
+    return r
+
+
+def _np_ptp(a, axis=None, out=None, **kw):
+    a = _need_dev(a)
+    if out is not None or any(v not in (False, np._NoValue) for v in kw.values()) or not (axis is None or (a.ndim == 1 and axis in (0, -1))):
+        raise _Fallback("kwargs")
+    with np.errstate(over="ignore"):
+        return np.subtract(_reduce(L.RED_MAX, a), _reduce(L.RED_MIN, a))      # numpy: umr_maximum(a) - umr_minimum(a)
+
+
+def _np_average(a, axis=None, weights=None, returned=False, **kw):
+    a = _need_dev(a)
+    if weights is not None or returned or any(v not in (False, np._NoValue) for v in kw.values()):
+        raise _Fallback("weights")
+    return _method_reduce(np.mean, L.RED_MEAN, a, axis, None, None, {})          # numpy: a.mean(axis)
+
+
+def _np_norm(x, ord=None, axis=None, keepdims=False):
+    """np.linalg.norm of a real 1-D float array: sqrt(x . x) (numpy/linalg/_linalg.py:norm, the ord=None branch)."""
+    x = _need_dev(x)
+    if axis is not None or keepdims or ord is not None or x.ndim != 1 or x.dtype.kind != "f":
+        raise _Fallback("norm kwargs")      # (ord=2 takes numpy's general path: another operation order)
+    return np.sqrt(_dot(x, x))
+
+
+def _nan_free(a) -> bool:
+    """Floats: np.max propagates NaN, so one reduction tells whether the array holds any.  Integers never do."""
+    return a.dtype.kind != "f" or not np.isnan(_reduce(L.RED_MAX, a))
+
+
+def _nan_reduce(red_op):
+    def handler(a, axis=None, dtype=None, out=None, **kw):
+        a = _need_dev(a)
+        if dtype is not None or out is not None or any(v not in (False, np._NoValue, None) for v in kw.values()) \
+                or not (axis is None or (a.ndim == 1 and axis in (0, -1))) or a.size == 0:
+            raise _Fallback("kwargs")
+        if not _nan_free(a):
+            raise _Fallback("NaNs present: numpy's masked path")
+        return _reduce(red_op, a)          # without NaNs nansum / nanmean / nanmax / nanmin are the plain reductions
+    return handler
+
+
 def matmul(a, b, out=None, **kw):
     if out is not None or kw:
         raise _Fallback("kwargs")
@@ -745,6 +829,9 @@ _FUNCTIONS = {
     np.argmax: argmax, np.argmin: argmin, np.cumsum: cumsum, np.sort: sort, np.argsort: argsort,
     np.matmul: matmul, np.dot: _dot, np.var: _var, np.std: _std,
     np.median: _np_median, np.quantile: _np_quantile, np.percentile: _np_percentile,
+    np.clip: _np_clip, np.ptp: _np_ptp, np.average: _np_average, np.linalg.norm: _np_norm,
+    np.nansum: _nan_reduce(L.RED_SUM), np.nanmean: _nan_reduce(L.RED_MEAN),
+    np.nanmax: _nan_reduce(L.RED_MAX), np.nanmin: _nan_reduce(L.RED_MIN),
 }
 
 

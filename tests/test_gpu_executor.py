@@ -100,6 +100,23 @@ def test_proxy_on_device_matches_numpy(dev):
     assert np.array_equal(np.asarray(np.sort(x)), np.sort(xh))
     k = P.DeviceArray.from_host(be, rng.integers(0, 2**31, 1 << 20, dtype=np.int64))
     assert np.array_equal(np.asarray(np.cumsum(k)), np.cumsum(np.asarray(k)))
+    # powers, clip, ptp, NaN-aware reductions built on the same kernels
+    assert np.array_equal(np.asarray(x ** 2), xh ** 2) and np.array_equal(np.asarray(np.power(x, 2)), np.power(xh, 2))
+    assert np.array_equal(np.asarray(x ** 0.5), xh ** 0.5)
+    ih = rng.integers(-2**20, 2**20, 1 << 20, dtype=np.int32)
+    i32 = P.DeviceArray.from_host(be, ih)
+    assert np.array_equal(np.asarray(i32 ** 2), ih ** 2)                      # wraps like numpy
+    assert np.array_equal(np.asarray(np.clip(x, 0.25, 0.75)), np.clip(xh, 0.25, 0.75))
+    assert np.array_equal(np.asarray(np.clip(i32, -5, None)), np.clip(ih, -5, None))
+    nh = xh.copy(); nh[12345] = np.nan
+    nx = P.DeviceArray.from_host(be, nh)
+    assert np.array_equal(np.asarray(np.clip(nx, 0.25, 0.75)), np.clip(nh, 0.25, 0.75), equal_nan=True)
+    assert np.ptp(x) == np.ptp(xh) and np.ptp(i32) == np.ptp(ih) and type(np.ptp(x)) is type(np.ptp(xh))
+    assert np.nanmax(x) == np.nanmax(xh) and np.nanmin(i32) == np.nanmin(ih)
+    assert abs(np.nansum(x) - np.nansum(xh)) <= 1e-5 * np.nansum(xh) and np.nansum(i32) == np.nansum(ih)
+    assert np.nanmax(nx) == np.nanmax(nh) and abs(np.nanmean(nx) - np.nanmean(nh)) <= 1e-6      # NaN present: numpy's path
+    assert abs(np.linalg.norm(x) - np.linalg.norm(xh)) <= 1e-5 * np.linalg.norm(xh)
+    assert abs(np.sum(x ** 2) - np.sum(xh ** 2)) <= 1e-5 * np.sum(xh ** 2)
     # order statistics: one device sort + a few elements; values and types are numpy's
     kh = np.asarray(k).copy()
     for f, args in ((np.median, ()), (np.percentile, (95,)), (np.quantile, (0.001,)), (np.percentile, ([25, 50, 75],))):

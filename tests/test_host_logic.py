@@ -156,6 +156,42 @@ def test_median_quantile_percentile_are_one_sort_and_a_few_elements(be):
     assert np.quantile(x, 0.5, method="nearest") is not None and np.isnan(np.quantile(x, 0.5, method="nearest"))
 
 
+def test_power_clip_ptp_average_norm_and_nan_reductions_stay_on_the_device(be):
+    """`x ** 2` / np.power(x, 2) are np.square (numpy's own fast paths), `x ** 0.5` is np.sqrt; np.clip is maximum + minimum;
+    np.ptp, np.average, np.linalg.norm and the nan-reductions of NaN-free data run as the plain reductions."""
+    rng = np.random.default_rng(1)
+
+    def same(want, got, exact=True):
+        w, g = np.asarray(want), np.asarray(got)
+        assert w.dtype == g.dtype and w.shape == g.shape
+        assert np.array_equal(w, g, equal_nan=True) if exact else np.allclose(w, g, rtol=1e-6, equal_nan=True)
+
+    for dt in (np.float32, np.float64, np.int32, np.int64):
+        a = (rng.standard_normal(5000) * 100).astype(dt)
+        x = P.DeviceArray.from_host(be, a)
+        is_int = np.dtype(dt).kind == "i"
+        fake_device.calls.clear()
+        same(a ** 2, x ** 2); same(np.power(a, 2), np.power(x, 2)); same(np.sum(a ** 2), np.sum(x ** 2), exact=is_int)
+        same(np.clip(a, -10, 20), np.clip(x, -10, 20)); same(a.clip(-10, 20), x.clip(-10, 20))
+        same(np.clip(a, 0, None), np.clip(x, 0, None)); same(np.clip(a, min=-5, max=5), np.clip(x, min=-5, max=5))
+        same(np.ptp(a), np.ptp(x)); same(np.average(a), np.average(x), exact=False)
+        same(np.nansum(a), np.nansum(x), exact=is_int); same(np.nanmax(a), np.nanmax(x)); same(np.nanmin(a), np.nanmin(x))
+        same(np.nanmean(a), np.nanmean(x), exact=False)
+        assert isinstance(x ** 2, P.DeviceArray) and isinstance(np.clip(x, -1, 1), P.DeviceArray)
+        if not is_int:
+            same(np.abs(a) ** 0.5, np.abs(x) ** 0.5); same(np.power(a, 2.0), np.power(x, 2.0)); same(a ** 3, x ** 3)
+            same(np.linalg.norm(a), np.linalg.norm(x), exact=False)
+            assert isinstance(np.abs(x) ** 0.5, P.DeviceArray)
+        else:
+            same(a ** 2.0, x ** 2.0)          # int ** float promotes to float64: numpy evaluates it
+        kinds = set(names(fake_device.calls))
+        assert {"reduce", "ewise"} <= kinds and (is_int or "reduce_fused" in kinds)
+    a = np.array([1.0, np.nan, 3.0, 2.0] * 1000)
+    x = P.DeviceArray.from_host(be, a)
+    same(np.nansum(a), np.nansum(x)); same(np.nanmax(a), np.nanmax(x)); same(np.nanmean(a), np.nanmean(x))   # NaNs: numpy's masked path
+    same(np.clip(a, 0, 2), np.clip(x, 0, 2))
+
+
 def test_buffers_are_released(be):
     x = P.device_rand(be, (1000,), seed=1)
     y = np.square(x) + 1.0
