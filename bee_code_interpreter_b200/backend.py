@@ -95,7 +95,8 @@ class LocalBackend:
     def ewise_new(self, op, dtype, in0, in1, scalar, n):
         dtype = np.dtype(dtype)
         return self._new(n * dtype.itemsize, lambda out: self.dev.ewise(
-            op, dtype, [in0], [in1] if in1 is not None else None, [scalar] if in1 is None else None, [out], [n]))
+            op, dtype, [in0], [in1] if in1 is not None else None,
+            [scalar] if (in1 is None and scalar is not None) else None, [out], [n]))      # unary ops have neither
 
     def reduce(self, op, dtype, in_ptrs, ns, pre=L.PRE_NONE):
         return self.dev.reduce(op, dtype, in_ptrs, ns, pre=pre)

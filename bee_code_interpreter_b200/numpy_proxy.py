@@ -643,40 +643,69 @@ def _np_median(a, axis=None, out=None, **kw):
     return np.mean(mid[:1] if n % 2 else mid)       # numpy: mean of the middle element(s)
 
 
+def _quantile_linear(a, q):
+    """numpy/lib/_function_base_impl.py:_quantile for method="linear" on a 1-D array, restated step by step with the
+    same numpy operations on the same dtypes; the partition is replaced by the device sort, and only the elements the
+    interpolation reads (two per quantile, and the last one for the NaN check) are fetched."""
+    n = a.size
+    if q.ndim > 1 or q.size > 64 or q.dtype.kind not in "fiu":
+        raise _Fallback("q")
+    if q.size == 0 or not (q.min() >= 0 and q.max() <= 1):
+        raise _Fallback("q range")                           # numpy raises / handles it
+    s = sort(a)
+    vi = np.asanyarray((n - 1) * q)                          # 'linear': virtual index = (n - 1) * q, in q's dtype
+    integral = np.issubdtype(vi.dtype, np.integer)
+    if integral:
+        prev_i = next_i = vi.astype(np.intp)
+    else:
+        prev = np.asanyarray(np.floor(vi))
+        nxt = np.asanyarray(prev + 1)
+        above = vi >= n - 1
+        if above.any():
+            prev[above] = -1
+            nxt[above] = -1
+        prev_i, next_i = prev.astype(np.intp), nxt.astype(np.intp)
+    # the elements numpy would read after its partition, in a small host array indexed the same way
+    wanted = np.unique(np.concatenate(([n - 1], prev_i.ravel() % n, next_i.ravel() % n)))
+    small = np.array([_sorted_elem(s, i) for i in wanted], dtype=a.dtype)
+    at = lambda idx: small[np.searchsorted(wanted, idx % n)]    # noqa: E731  (0-d index -> numpy scalar, like arr[idx])
+    last = small[-1]
+    if integral:
+        result = at(prev_i)                                  # no interpolation: the points themselves
+    else:
+        previous, nxt_v = at(prev_i), at(next_i)
+        gamma = np.asanyarray(np.asanyarray(vi - prev_i), dtype=vi.dtype).reshape(vi.shape)
+        # _lerp(previous, next, gamma)
+        diff_b_a = np.subtract(nxt_v, previous)
+        result = np.asanyarray(np.add(previous, diff_b_a * gamma))
+        np.subtract(nxt_v, diff_b_a * (1 - gamma), out=result, where=gamma >= 0.5, casting="unsafe", dtype=type(result.dtype))
+        if result.ndim == 0:
+            result = result[()]
+    if a.dtype.kind == "f" and np.isnan(last):               # NaNs sort last: every quantile is NaN then
+        if np.ndim(result) == 0:
+            return last
+        np.copyto(result, last)
+    return result
+
+
 def _np_quantile(a, q, axis=None, out=None, method="linear", **kw):
     weights = kw.pop("weights", None)
     a = _order_stat_operand(a, axis, out, kw)
     if method != "linear" or weights is not None or isinstance(q, DeviceArray):
         raise _Fallback("method")
-    qa = np.asanyarray(q)
-    if qa.dtype.kind not in "fiu" or qa.ndim > 1 or qa.size > 64 or not np.all((qa >= 0) & (qa <= 1)):
-        raise _Fallback("q")
-    n = a.size
-    s = sort(a)
-    nan = a.dtype.kind == "f" and np.isnan(_sorted_elem(s, n - 1))
-
-    def one(qi, as_array: bool):
-        # `as_array`: numpy promotes differently when q is an array (float32 data then gives float64 results)
-        wrap = (lambda g: np.asanyarray([g])) if as_array else (lambda g: g)
-        if nan:
-            return np.quantile(np.array([np.nan, np.nan], dtype=a.dtype), wrap(qi))
-        vi = (n - 1) * np.asanyarray(qi, dtype=np.float64 if np.asanyarray(qi).dtype.kind != "f" else None)   # numpy: (n - 1) * q
-        prev = int(np.floor(vi))
-        if prev >= n - 1:
-            last = _sorted_elem(s, n - 1)
-            return np.quantile(np.array([last, last], dtype=a.dtype), wrap(qi))
-        pair = np.array([_sorted_elem(s, prev), _sorted_elem(s, prev + 1)], dtype=a.dtype)
-        return np.quantile(pair, wrap(vi - prev))    # same two values, same gamma: numpy's own interpolation
-    if qa.ndim == 0:
-        return one(qa[()], False)
-    return np.concatenate([one(qi, True) for qi in qa]) if qa.size else np.quantile(np.zeros(2, a.dtype), qa)
+    # numpy.quantile: a python number takes the array's float type, anything else keeps its own
+    qa = np.asanyarray(q, dtype=a.dtype) if isinstance(q, (int, float)) and a.dtype.kind == "f" else np.asanyarray(q)
+    return _quantile_linear(a, qa)
 
 
 def _np_percentile(a, q, axis=None, out=None, method="linear", **kw):
-    if isinstance(q, DeviceArray):
-        raise _Fallback("q")
-    qa = np.true_divide(q, 100)       # numpy/lib/_function_base_impl.py: percentile = quantile(q / 100)
-    return _np_quantile(a, qa, axis=axis, out=out, method=method, **kw)
+    weights = kw.pop("weights", None)
+    a = _order_stat_operand(a, axis, out, kw)
+    if method != "linear" or weights is not None or isinstance(q, DeviceArray):
+        raise _Fallback("method")
+    # numpy.percentile: the divisor takes the array's float type
+    qa = np.true_divide(q, a.dtype.type(100) if a.dtype.kind == "f" else 100, out=...)
+    return _quantile_linear(a, qa)
 
 
 def _is_two(v) -> bool:
