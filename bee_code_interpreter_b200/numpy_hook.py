@@ -396,6 +396,19 @@ def _build_pandas_view():
         def min(self, *a, **kw):
             return float(self._dev.min()) if self._plain(a, kw) and self._clean() else self._series().min(*a, **kw)
 
+        def median(self, *a, **kw):
+            # nanops.nanmedian of NaN-free data is np.median of the values: one device sort, two elements back
+            if self._plain(a, kw) and len(self._dev) >= 2 and self._clean():
+                return real_np.median(self._dev)
+            return self._series().median(*a, **kw)
+
+        def quantile(self, q=0.5, *a, **kw):
+            # pandas (core/array_algos/quantile.py): np.percentile(values, asarray(q) * 100.0, method=interpolation)
+            if self._plain(a, kw) and isinstance(q, (int, float)) and not isinstance(q, bool) and 0 <= q <= 1 \
+                    and len(self._dev) >= 2 and self._clean():
+                return real_np.percentile(self._dev, real_np.asarray([q], dtype=real_np.float64) * 100.0)[0]
+            return self._series().quantile(q, *a, **kw)
+
         def count(self):
             return int(self._dev.size) if self._clean() else self._series().count()
 

@@ -634,14 +634,15 @@ print(type(control).__name__, type(s).__name__, isinstance(s, pd.Series), isinst
 print(repr(s.mean()), repr(pd.Series(experimental).mean()), repr(s.std()), repr(pd.Series(experimental).std()))
 t, p = ttest_ind(control, experimental)
 print(repr(float(t)), repr(float(p)), repr(float(st.ttest_ind(control, experimental, equal_var=False).statistic)))
-print(repr(float(s.median())))
+print(repr(float(s.median())), repr(float(s.quantile(0.95))), repr(float(s.quantile(0.001))), repr(float(s.mode().iloc[0])))
 '''
 
 
 def test_pandas_and_scipy_entry_points_run_as_device_reductions(executor):
     """examples/using_imports.py:25-36 at a size where it matters: pd.Series(x).mean()/.std() and scipy's
     ttest_ind on device arrays run as fused reductions (no host copy), equal to pandas / scipy on the host
-    within float64 summation-order tolerance; anything else (median) is pandas itself."""
+    within float64 summation-order tolerance; median / quantile are one device sort plus two elements and equal
+    pandas bit for bit; anything else (mode) is pandas itself."""
     import pandas as pd
     import scipy.stats as st
 
@@ -658,9 +659,10 @@ def test_pandas_and_scipy_entry_points_run_as_device_reductions(executor):
     t, p = st.ttest_ind(a, b)
     got = [float(x) for x in lines[2].split()]
     assert np.allclose(got, [t, p, st.ttest_ind(a, b, equal_var=False).statistic], rtol=1e-9, atol=0)
-    assert float(lines[3]) == float(pd.Series(a).median())
+    sa = pd.Series(a)
+    assert [float(v) for v in lines[3].split()] == [float(sa.median()), float(sa.quantile(0.95)), float(sa.quantile(0.001)), float(sa.mode().iloc[0])]
     kinds = names(fake_device.calls)
-    assert kinds.count("rand_pcg") == 2 and "reduce_fused" in kinds
+    assert kinds.count("rand_pcg") == 2 and "reduce_fused" in kinds and kinds.count("sort") == 3
 
 
 # ---- creation functions and Generator draws through the view: host-side parameter derivation vs numpy -------------
