@@ -452,9 +452,10 @@ def test_random_expressions_match_numpy(be):
     from hypothesis import given, settings, strategies as st
 
     dtypes = [np.float32, np.float64, np.int32, np.int64]
-    unary = [np.square, np.abs, np.negative]
+    unary = [np.square, np.abs, np.negative, lambda v: v ** 2, lambda v: np.power(v, 2), lambda v: np.clip(v, -3, 4),
+             lambda v: v.clip(min=-1), lambda v: np.clip(v, None, 2)]
     binary = [np.add, np.subtract, np.multiply, np.maximum, np.minimum]
-    reducers = [np.sum, np.max, np.min, np.mean, None, None]
+    reducers = [np.sum, np.max, np.min, np.mean, np.ptp, np.nansum, np.nanmax, np.median, lambda v: np.percentile(v, 30), None, None]
 
     @settings(max_examples=60, deadline=None)
     @given(seed=st.integers(0, 2**31 - 1), depth=st.integers(1, 4), di=st.integers(0, 3), n=st.integers(1, 3000),
@@ -487,7 +488,7 @@ def test_random_expressions_match_numpy(be):
             else:
                 got, want = red(dv), red(hv)
                 assert np.asarray(got).dtype == np.asarray(want).dtype
-                if np.issubdtype(dt, np.integer) and red is not np.mean:
+                if np.issubdtype(dt, np.integer) and red in (np.sum, np.max, np.min, np.ptp, np.nansum, np.nanmax):
                     assert got == want
                 else:
                     assert np.isclose(float(got), float(want), rtol=1e-5 if dt == np.float32 else 1e-11, atol=1e-6)
