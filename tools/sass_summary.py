@@ -37,8 +37,21 @@ def main():
                     per[cur][mark] += 1
                     total[mark] += 1
     names = subprocess.run(["c++filt"], input="\n".join(per), capture_output=True, text=True).stdout.splitlines()
+    def short(n: str) -> str:
+        n = n.replace("(anonymous namespace)::", "").replace("bci::", "")
+        if n.endswith(")"):                      # drop the parameter list: the "(" that matches the final ")"
+            depth = 0
+            for i in range(len(n) - 1, -1, -1):
+                depth += n[i] == ")"
+                depth -= n[i] == "("
+                if depth == 0:
+                    n = n[:i]
+                    break
+        n = re.sub(r"\((?:int|bool|unsigned int)\)", "", n)       # <(int)1, (bool)0> -> <1, 0>
+        return n[5:] if n.startswith("void ") else n
+
     for k, n in zip(per, names):
-        demangle[k] = re.sub(r"\(.*", "", n).replace("bci::", "").replace("(anonymous namespace)::", "")
+        demangle[k] = short(n)
     arch = subprocess.run(["cuobjdump", "-lelf", str(LIB)], capture_output=True, text=True).stdout
     print("# SASS summary of libbci.so (round 2)\n")
     print("`cuobjdump -lelf`: " + ", ".join(sorted(set(re.findall(r"sm_\d+a?", arch)))) + " only.\n")
