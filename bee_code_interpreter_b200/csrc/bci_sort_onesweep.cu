@@ -44,7 +44,7 @@ __device__ __forceinline__ uint4 ld_status4(const uint32_t* p) {
   return v;
 }
 
-// Tile shape of a sweep.  32-bit keys alone: 512 threads x 16 keys = 8192 keys per CTA, 2 CTAs per SM — the same 32
+// Tile shape of a sweep.  32-bit keys alone: 512 threads x 20 keys = 10240 keys per CTA, 2 CTAs per SM — the same 32
 // resident warps as 4 CTAs of 256, but half the tiles: half the status words to publish and read back, half the
 // look-back depth (the depth is set by how many tiles finish ranking per L2 round trip), half the per-tile prologues
 // (ncu r2r: look-back was 28 % of the instructions and 25 % of the stall samples of the 4096-key form).  Measured,
@@ -52,7 +52,11 @@ __device__ __forceinline__ uint4 ld_status4(const uint32_t* p) {
 template <typename K, bool PAIRS> struct Sweep {
   static constexpr int T = (sizeof(K) == 4 && !PAIRS) ? 512 : kThreads;
   static constexpr int W = T / 32;
-  static constexpr int TILE = T * kSortItems;
+  // keys per thread: 20 (16 for the 64-bit pairs, whose staging buffers would otherwise cost the third CTA per SM).
+  // Measured on 32 x 1e7 float32: 16 keys 6.84 ms, 20 keys 6.35 ms, 24 keys 6.28 ms but 7 % slower on 256 x 1e5 (the
+  // longer ragged tail per request); stable argsort float32 8.98 -> 8.56 ms, int64 8.54 -> 8.39 ms with 20.
+  static constexpr int ITEMS = (sizeof(K) == 8 && PAIRS) ? 16 : 20;
+  static constexpr int TILE = T * ITEMS;
   static constexpr int CTAS = T == 512 ? 2 : 3;
 };
 
@@ -168,7 +172,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
                 int pass, int dtype, const uint32_t* __restrict__ gbase, const uint32_t* __restrict__ trivial,
                 uint32_t* __restrict__ status, uint32_t* __restrict__ counter, unsigned int prefetch_tiles) {
   constexpr int P = (int)sizeof(K);
-  constexpr int T = Sweep<K, PAIRS>::T, W = Sweep<K, PAIRS>::W, TILE = Sweep<K, PAIRS>::TILE;
+  constexpr int T = Sweep<K, PAIRS>::T, W = Sweep<K, PAIRS>::W, TILE = Sweep<K, PAIRS>::TILE, ITEMS = Sweep<K, PAIRS>::ITEMS;
   constexpr bool WRITE_KEYS = !(PAIRS && LAST);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   K* skeys = reinterpret_cast<K*>(smem_raw);
@@ -207,7 +211,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     // the other tiles of this request take the same branch.
     K* __restrict__ dstk = reinterpret_cast<K*>(q.out) + base;
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
       const int i = k * T + (int)threadIdx.x;
       if (i < m) {
         K x = src[i];
@@ -251,25 +255,25 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
   // accesses are what saturates the shared-memory pipe (3.3-way bank conflicts each, ncu r2t).
   const int l16 = lane & 15;
   uint32_t* wh = tab + (threadIdx.x >> 4) * 256;
-  const int p0 = (threadIdx.x >> 4) * (16 * kSortItems) + l16;  // row k of unit u = positions u*256 + k*16 + [0,16)
+  const int p0 = (threadIdx.x >> 4) * (16 * ITEMS) + l16;  // row k of unit u = positions u*256 + k*16 + [0,16)
 
   auto body = [&](auto full_c) {
     constexpr bool FULL = decltype(full_c)::value;
-    K key[kSortItems];
-    uint32_t idx[kSortItems];
-    uint32_t rank[kSortItems];
+    K key[ITEMS];
+    uint32_t idx[ITEMS];
+    uint32_t rank[ITEMS];
     // every load of the tile is issued before anything consumes one
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) key[k] = (FULL || p0 + k * 16 < m) ? src[p0 + k * 16] : K(0);
+    for (int k = 0; k < ITEMS; ++k) key[k] = (FULL || p0 + k * 16 < m) ? src[p0 + k * 16] : K(0);
     if constexpr (PAIRS) {
 #pragma unroll
-      for (int k = 0; k < kSortItems; ++k) {
+      for (int k = 0; k < ITEMS; ++k) {
         if constexpr (FIRST) idx[k] = (uint32_t)(base + p0 + k * 16);
         else idx[k] = (FULL || p0 + k * 16 < m) ? srci[p0 + k * 16] : 0u;
       }
     }
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
       if constexpr (FIRST) key[k] = to_key<K>(key[k], dtype);
       if constexpr (!FULL) key[k] = (p0 + k * 16 < m) ? key[k] : ~K(0);
     }
@@ -285,7 +289,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
         const unsigned half_mask = 0xffffu << (lane & 16);
         const unsigned below = (1u << lane) - 1u;
 #pragma unroll
-        for (int k = 0; k < kSortItems; ++k) {
+        for (int k = 0; k < ITEMS; ++k) {
           const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
           uint32_t diff = __reduce_or_sync(0xffffffffu, dg ^ __shfl_sync(0xffffffffu, dg, 0));
           if (__popc(diff) <= 4) {
@@ -314,7 +318,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
         }
       } else
 #pragma unroll
-      for (int k = 0; k < kSortItems; ++k) {
+      for (int k = 0; k < ITEMS; ++k) {
         const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
         const bool valid = FULL || p0 + k * 16 < m;
         if (valid) atomicOr(&wh[dg], my_bit);
@@ -382,7 +386,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     uint4 v0, v1;
     if (tl32 > 0) fetch(1u, v0, v1);
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
       if (FULL || p0 + k * 16 < m) {
         const uint32_t dg = (uint32_t)(key[k] >> shift) & 255u;
         const uint32_t lp = wh[dg] + rank[k];
@@ -426,7 +430,7 @@ onesweep_kernel(const Req* __restrict__ reqs, const unsigned long long* __restri
     }
     K* __restrict__ dst = reinterpret_cast<K*>(q.out);
 #pragma unroll
-    for (int k = 0; k < kSortItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
       const int i = k * T + (int)threadIdx.x;
       if (FULL || i < m) {
         const K x = skeys[i];

@@ -296,10 +296,12 @@ def test_sort_leaves_out_passes_that_are_constant_for_the_whole_batch(dev):
 
 @pytest.mark.gpu
 def test_sort_sizes_around_the_tile_and_ranking_unit_boundaries(dev):
-    """Every size class of the sweep: below one 16-key row, one 256-key ranking unit +-1, one tile +-1 (4096 keys, 8192
-    for 32-bit keys alone), several tiles with a ragged tail; sorted, reversed and two-valued inputs among them."""
+    """Every size class of the sweep: below one 16-key row, one ranking unit (16 lanes x 16 or 20 rows) +-1, one tile +-1
+    (4096 / 5120 keys; 10240 for 32-bit keys alone), several tiles with a ragged tail; sorted, reversed and two-valued
+    inputs among them."""
     rng = np.random.default_rng(14)
-    sizes = [1, 2, 15, 16, 17, 255, 256, 257, 511, 4095, 4096, 4097, 8191, 8192, 8193, 12289, 3 * 8192 - 1, 5 * 8192 + 300]
+    sizes = [1, 2, 15, 16, 17, 255, 256, 257, 319, 320, 321, 4095, 4096, 4097, 5119, 5120, 5121, 8192, 10239, 10240, 10241,
+             12289, 3 * 10240 - 1, 5 * 10240 + 300]
     for dt in (np.float32, np.int32, np.int64, np.float64):
         arrs = []
         for j, n in enumerate(sizes):
