@@ -580,9 +580,10 @@ int onesweep_run(int dtype, int B, const void* const* in, void* const* out, cons
     BCI_CUDA(cudaMemsetAsync(status, 0, total_tiles * 256 * sizeof(uint32_t), c.stream));
     const unsigned grid = (unsigned)total_tiles;
     const size_t smem = onesweep_smem<K, PAIRS>();
-    // ~ one wave of resident CTAs ahead; measured with 4096-key tiles, f32/i64/argsort: off 8.37/22.24/10.94 ms,
-    // 600 tiles 8.28/21.64/10.66, 1200 8.31/22.21/10.89, 2400 = off
-    unsigned int prefetch_tiles = 600u * (unsigned)kSortTile / (unsigned)TILE;
+    // L2 prefetch distance: about half a wave of resident CTAs ahead.  Measured with 20 keys per thread, f32 32 x 1e7 /
+    // i64 16 x 1e7 / argsort f32: off 6.42 / 8.91 / 8.98 ms, 120 tiles 6.30 / 8.23 / 8.44, 240 6.35 / 8.30 / 8.49,
+    // 480 6.38 / 8.41 / 8.57, 960 = off
+    unsigned int prefetch_tiles = (unsigned)(c.sm_count * Sweep<K, PAIRS>::CTAS / 2);
     if (const char* pf = tuning_env("BCI_SORT_PREFETCH")) prefetch_tiles = (unsigned int)atoi(pf);
     if (first && last)
       onesweep_kernel<K, PAIRS, true, true><<<grid, T, smem, c.stream>>>(bt.d_reqs, bt.d_tile_start, B, p, dtype, ghist, trivial, status, counters + p, prefetch_tiles);
