@@ -3,13 +3,17 @@
 //
 //   digit_hist_kernel : ONE read of the keys counts every 8-bit digit of every pass
 //                       (4 histograms for 32-bit keys, 8 for 64-bit) per request;
-//   digit_scan_kernel : exclusive scan over the 256 digits -> where each digit's run starts;
-//   onesweep_kernel   : per pass, a tile ranks its keys stably (8 ballots per 32-key row,
-//                       per-warp digit counters), publishes its 256 digit counts, and obtains
-//                       the counts of all earlier tiles of the SAME request by decoupled
-//                       look-back (status word = 2 flag bits + 30-bit count, one thread per
-//                       digit), then stages the tile in digit order in shared memory and writes
-//                       every digit run with coalesced stores.
+//   digit_scan_kernel : exclusive scan over the 256 digits -> where each digit's run starts; also
+//                       classifies each (request, pass): constant digit / skewed / ordinary;
+//   onesweep_kernel   : per pass, a tile (512 or 256 threads x 20 keys) ranks its keys stably in
+//                       half-warp units (one shared-memory word per unit and digit holds the row's
+//                       peer mask and the running count; skewed passes use ballots over the digit
+//                       bits that differ), publishes its 256 digit counts, places the keys in digit
+//                       order in shared memory, obtains the counts of all earlier tiles of the SAME
+//                       request by a CTA-wide decoupled look-back (status word = 2 flag bits + 30-bit
+//                       count; warp w fetches the status row of the tile w+1 back), and writes every
+//                       digit run with coalesced stores.  Passes whose digit is constant for every
+//                       request of the batch are not launched at all.
 // HBM traffic = 1 + 2 per pass key sweeps: 9*n*4 bytes for float32 = the algorithmic figure of
 // SURVEY.md §8a K5 (the reduce-then-scan form in bci_sort.cu moves 12).  Tiles take their
 // index from an atomic counter, so a tile only ever waits for tiles that already started:
