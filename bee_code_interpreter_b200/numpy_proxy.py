@@ -770,6 +770,23 @@ def _nan_reduce(red_op):
     return handler
 
 
+def _nan_free_then(handler):
+    """nanmedian / nanvar / nanpercentile ... of NaN-free data are the plain functions (numpy removes the NaNs of a
+    1-D array and calls them); with NaNs present numpy's own path runs on the host."""
+    def wrapped(a, *args, **kw):
+        a = _need_dev(a)
+        if a.ndim != 1 or a.size == 0 or not _nan_free(a):
+            raise _Fallback("NaNs present")
+        return handler(a, *args, **kw)
+    return wrapped
+
+
+def _np_inner(a, b):
+    if isinstance(a, DeviceArray) and isinstance(b, DeviceArray) and a.ndim == 1 and b.ndim == 1:
+        return _dot(a, b)          # 1-D real inner / vdot = dot
+    raise _Fallback("inner")
+
+
 def matmul(a, b, out=None, **kw):
     if out is not None or kw:
         raise _Fallback("kwargs")
@@ -861,6 +878,9 @@ _FUNCTIONS = {
     np.clip: _np_clip, np.ptp: _np_ptp, np.average: _np_average, np.linalg.norm: _np_norm,
     np.nansum: _nan_reduce(L.RED_SUM), np.nanmean: _nan_reduce(L.RED_MEAN),
     np.nanmax: _nan_reduce(L.RED_MAX), np.nanmin: _nan_reduce(L.RED_MIN),
+    np.nanmedian: _nan_free_then(_np_median), np.nanquantile: _nan_free_then(_np_quantile),
+    np.nanpercentile: _nan_free_then(_np_percentile), np.nanvar: _nan_free_then(_var), np.nanstd: _nan_free_then(_std),
+    np.inner: _np_inner, np.vdot: _np_inner,
 }
 
 

@@ -190,6 +190,24 @@ def test_power_clip_ptp_average_norm_and_nan_reductions_stay_on_the_device(be):
     x = P.DeviceArray.from_host(be, a)
     same(np.nansum(a), np.nansum(x)); same(np.nanmax(a), np.nanmax(x)); same(np.nanmean(a), np.nanmean(x))   # NaNs: numpy's masked path
     same(np.clip(a, 0, 2), np.clip(x, 0, 2))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        same(np.nanmedian(a), np.nanmedian(x)); same(np.nanvar(a), np.nanvar(x)); same(np.nanpercentile(a, 50), np.nanpercentile(x, 50))
+    # NaN-free data: the nan- order statistics / moments and inner / vdot are the plain device entry points
+    for dt in (np.float32, np.float64, np.int64):
+        a, b = (rng.standard_normal(4001) * 50).astype(dt), (rng.standard_normal(4001) * 50).astype(dt)
+        x, y = P.DeviceArray.from_host(be, a), P.DeviceArray.from_host(be, b)
+        fake_device.calls.clear()
+        same(np.nanmedian(a), np.nanmedian(x)); same(np.nanpercentile(a, 30), np.nanpercentile(x, 30))
+        same(np.nanquantile(a, [0.2, 0.8]), np.nanquantile(x, [0.2, 0.8]))
+        if dt is np.int64:
+            same(np.inner(a, b), np.inner(x, y)); same(np.vdot(a, b), np.vdot(x, y))
+        else:
+            tol = 1e-5 if dt is np.float32 else 1e-12
+            assert np.isclose(np.nanvar(x), np.nanvar(a), rtol=tol) and np.isclose(np.nanstd(x, ddof=1), np.nanstd(a, ddof=1), rtol=tol)
+            assert np.isclose(np.inner(x, y), np.inner(a, b), rtol=tol, atol=tol * 1e4) and type(np.vdot(x, y)) is type(np.vdot(a, b))
+        assert {"sort", "reduce_fused"} <= set(names(fake_device.calls))
 
 
 def test_buffers_are_released(be):
